@@ -1,0 +1,174 @@
+/*
+ * include/xq_b200.h — C ABI of libxq_b200.so (B200 / sm_100a Xiangqi engine).
+ *
+ * This is the drop-in boundary for the reference's self-play hot path.  The
+ * reference (hpy666666/ChineseChessAI) is pure Python with no FFI of its own;
+ * each entry point below names the reference function it replaces
+ * (file:line relative to the reference root).  The Python classes
+ * chinesechessai_b200.chess_env.ChineseChess / self_play.MCTS bind these via
+ * ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers unless the function name ends in
+ *     `_host`.  `stream` is a cudaStream_t passed as void* (NULL = default
+ *     stream).  Calls are asynchronous on that stream; `_host` calls
+ *     synchronise before returning.
+ *   - Return value: 0 on success, negative XQ_E_* otherwise;
+ *     xq_last_error() gives a thread-local message.  No hidden global state;
+ *     no CPU fallback: without a CUDA device every compute call fails.
+ *   - Struct-of-arrays game state, one row per game:
+ *       board    int8 [n_games][XQ_BOARD_STRIDE]  row-major r*9+c, 90 used,
+ *                piece codes of config.py:66-74 (0 empty, +1..+7 red
+ *                K,A,B,N,R,C,P, -1..-7 black)
+ *       meta     xq_meta[n_games]                 32 B, scalars of chess_env.py:17-31,62-65
+ *       pos_hist uint64[n_games][hist_cap]        position_history (chess_env.py:20,338)
+ *   - A move is int16 `from*90 + to` (== the policy-logit index of
+ *     neural_network.py:160); move lists are in the reference's canonical
+ *     order (chess_env.py:82-88 scan order, per-piece generator order).
+ */
+#ifndef XQ_B200_H
+#define XQ_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XQ_ABI_VERSION 1
+#define XQ_NSQ 90
+#define XQ_BOARD_STRIDE 96
+#define XQ_MAX_MOVES 128     /* legal-move list capacity (observed max 67) */
+#define XQ_CAND_CAP 256      /* pseudo-legal candidate capacity (bound 119 for real sets) */
+#define XQ_WINNER_NONE 2     /* Python None */
+#define XQ_PLANES 15
+#define XQ_POLICY 8100
+
+#define XQ_E_ARG (-1)
+#define XQ_E_CUDA (-2)
+#define XQ_E_NODEVICE (-3)
+
+/* end_reason classes (chess_env.py:297,359,366,373,381,389,397,404) */
+enum {
+  XQ_REASON_NONE = 0,
+  XQ_REASON_KING_CAPTURE = 1,
+  XQ_REASON_CHECKMATE = 2,
+  XQ_REASON_REPETITION = 3,
+  XQ_REASON_FIFTY = 4,
+  XQ_REASON_STALEMATE = 5,
+  XQ_REASON_PERPETUAL_CHECK = 6,
+  XQ_REASON_PERPETUAL_CHASE = 7, /* never produced: chess_env.py:674 */
+  XQ_REASON_MOVE_CAP = 8
+};
+
+/* xq_meta.flags */
+#define XQ_F_OVERFLOW 1u /* >XQ_MAX_MOVES legal, >XQ_CAND_CAP candidates or history full */
+
+typedef struct {
+  int8_t player;              /* current_player +1/-1           chess_env.py:62  */
+  int8_t winner;              /* 1/-1/0/XQ_WINNER_NONE          chess_env.py:64  */
+  uint8_t reason;             /* XQ_REASON_*                    chess_env.py:31  */
+  uint8_t done;               /* last make_move returned done (sticky)           */
+  int8_t red_king;            /* cached square or -1 (None)     chess_env.py:27  */
+  int8_t black_king;          /*                                chess_env.py:28  */
+  uint8_t flags;              /* XQ_F_*                                          */
+  uint8_t reserved;
+  int32_t move_count;         /* chess_env.py:63 */
+  int32_t no_capture;         /* chess_env.py:21 */
+  int32_t consecutive_checks; /* chess_env.py:24 */
+  int32_t hist_len;           /* len(position_history)          chess_env.py:20  */
+  uint32_t check_bits;        /* last 32 check_history flags, bit0 = newest (:22) */
+  int32_t check_len;          /* len(check_history)                               */
+} xq_meta;                    /* 32 bytes, 16-byte aligned rows */
+
+/* step flags byte: bit0 done, bit1 reward is a Python int, bits2-3 winner+1
+ * (3 = None), bits4-7 reason */
+#define XQ_STEP_DONE 1u
+#define XQ_STEP_REWARD_INT 2u
+
+typedef struct {
+  int32_t plies;
+  int32_t winner;
+  int32_t reason;
+  int32_t max_legal;
+  double reward_sum;   /* sequential float64 sum of step rewards */
+  uint64_t digest;     /* per-ply digest chain */
+  uint64_t final_hash; /* position key of final board ‖ side to move */
+} xq_playout_result;   /* 40 bytes */
+
+/* ---- library ------------------------------------------------------------ */
+int xq_abi_version(void);
+const char *xq_last_error(void);
+/* number of CUDA devices visible, or XQ_E_NODEVICE */
+int xq_device_count(void);
+/* kernels launched by this library since load (bench.py's gpu_launches) */
+int64_t xq_launch_count(void);
+
+/* ---- rules engine: chess_env.py ---------------------------------------- */
+/* ChineseChess.reset  (chess_env.py:14-67) for n_games boards. */
+int xq_reset(int8_t *board, xq_meta *meta, int n_games, void *stream);
+
+/* 64-bit position key of board ‖ side byte (_get_position_hash, :497-504). */
+int xq_position_hash(const int8_t *board, const xq_meta *meta, uint64_t *out,
+                     int n_games, void *stream);
+
+/* ChineseChess.get_legal_moves (chess_env.py:76-121 incl. _is_move_suicide
+ * :431-464, _is_in_check :506-548, _are_kings_facing :466-495).
+ * moves: int16[n_games][XQ_MAX_MOVES]; n_moves: int16[n_games].
+ * in_check (optional): uint8[n_games] = _is_in_check(current_player). */
+int xq_legal_moves(const int8_t *board, xq_meta *meta, int16_t *moves,
+                   int16_t *n_moves, uint8_t *in_check, int n_games, void *stream);
+
+/* ChineseChess.make_move (chess_env.py:253-406) for one move per game.
+ * move[g] < 0 leaves game g untouched (batched loops freeze finished games;
+ * the reference itself has no guard).  reward: float64[n_games]; flags:
+ * uint8[n_games] (see XQ_STEP_*).  next_moves/next_n (optional) receive the
+ * new side's legal list, which the terminal chain (:354,:376) computes anyway. */
+int xq_step(int8_t *board, xq_meta *meta, uint64_t *pos_hist, int hist_cap,
+            const int16_t *move, double *reward, uint8_t *flags,
+            int16_t *next_moves, int16_t *next_n, int n_games, void *stream);
+
+/* Counter-based uniform move pick shared with the oracle:
+ * philox4x32-10(key=seed, ctr=(first_game_id+g, ply,0,0)); see DESIGN.md.
+ * picked[g] = -1 when n_moves[g]==0 or the game is done. */
+int xq_pick_moves(const int8_t *board, const xq_meta *meta, const int16_t *moves,
+                  const int16_t *n_moves, uint64_t seed, uint32_t first_game_id,
+                  uint32_t ply, int capture_bias, int16_t *picked, int n_games,
+                  void *stream);
+
+/* Fused random playout: up to max_plies x (get_legal_moves -> pick ->
+ * make_move) per game in ONE launch, state in shared memory
+ * (the loop of self_play.py:203-256 with the search replaced by the pick rule).
+ * Optional per-ply traces (NULL to skip), each [n_games][max_plies]:
+ *   tr_moves int16[..][XQ_MAX_MOVES], tr_n int16, tr_pick int16,
+ *   tr_reward float64, tr_flags uint8, tr_boards int8[..][XQ_NSQ]. */
+int xq_playout(int8_t *board, xq_meta *meta, uint64_t *pos_hist, int hist_cap,
+               uint64_t seed, uint32_t first_game_id, int max_plies,
+               int capture_bias, xq_playout_result *results, int16_t *tr_moves,
+               int16_t *tr_n, int16_t *tr_pick, double *tr_reward,
+               uint8_t *tr_flags, int8_t *tr_boards, int n_games, void *stream);
+
+/* Same, end to end from HOST buffers: H2D of board/meta, playout, D2H of the
+ * final board/meta/results.  pos_hist is device scratch owned by the call. */
+int xq_playout_host(int8_t *board_h, xq_meta *meta_h, uint64_t seed,
+                    uint32_t first_game_id, int max_plies, int capture_bias,
+                    xq_playout_result *results_h, int n_games, int device);
+
+/* ---- evaluator glue: neural_network.py ---------------------------------- */
+/* ChessNet.encode_board (neural_network.py:128-146): planes
+ * float32[n][15][10][9]; or bf16 (as uint16) when out_bf16 != 0. */
+int xq_encode_planes(const int8_t *board, int board_stride, const int8_t *player,
+                     int player_stride, void *planes, int out_bf16, int n,
+                     void *stream);
+
+/* ChessNet._logits_to_move_probs (neural_network.py:148-169): gather the
+ * legal moves' logits and softmax in float32.  logits: float32 or bf16
+ * [n][XQ_POLICY]; priors float32[n][XQ_MAX_MOVES]. */
+int xq_policy_priors(const void *logits, int logits_bf16, const int16_t *moves,
+                     int moves_stride, const int16_t *n_moves, float *priors,
+                     int n, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XQ_B200_H */
