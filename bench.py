@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py — board-steps/s of the Xiangqi rules hot path on B200 (BASELINE.json metric).
+
+Workload (N=1): BASELINE.json configs[1] — batched random playouts, 65,536 boards x <=70 plies
+from the initial position, uniform legal move per ply by the shared counter-based pick rule
+(philox4x32-10 keyed by seed, counter (game_id, ply)); one "step" = one such batch through
+the fused playout kernel (get_legal_moves + make_move per ply, every terminal rule).  N>1:
+the same batch per GPU (weak scaling), game ids offset per rank, no data-path collective.
+
+    python bench.py --gpus N --steps K --warmup W          # our arm
+    python bench.py --impl reference ...                   # CPU port of the reference path
+
+Prints ONE JSON line (see the keys at the bottom).  ``value`` is device-resident throughput,
+``e2e`` goes through the host-buffer C-ABI call (H2D + kernel + D2H inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BOARDS = 65536
+PLIES = 70
+SEED = 0x5EED
+# Algorithmic HBM bytes per board-step (DESIGN.md §Measurement / SURVEY.md §8d):
+#   step-per-launch mode: state in 128 + state out 128 + legal list 81 + move 4 + history 8
+BYTES_PER_STEP_LAUNCH_MODE = 352
+#   fused playout: (board+meta in 128, out 128, result 40) / 70 plies + one 8-byte history append
+BYTES_PER_STEP_FUSED = (128 + 128 + 40) / 70.0 + 8.0
+METRIC = "board-steps/sec (legal movegen+step)"
+UNIT = "board-steps/s"
+
+
+def read_peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port_rate(n_games: int, threads: int, seed: int = SEED, first: int = 0):
+    """Oracle (C port of the reference path) on the host cores: plies/s over n_games playouts."""
+    from oracle import xq_oracle as xo
+    xo.build()
+    t0 = time.perf_counter()
+    total, _ = xo.playout_many(n_games, seed, first, PLIES, 0, n_threads=threads)
+    dt = time.perf_counter() - t0
+    return total / dt, total, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm for the path (the reference is pure
+    Python and cannot travel to the GPU box, so this is the C port in oracle/, kind "port"),
+    all host threads, each step a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    rate, _, _ = cpu_port_rate(1024, threads)                   # calibrate
+    games = int(max(256, min(BOARDS, rate * 8.0 / 69.0)))       # ~8 s per step
+    for w in range(args.warmup):
+        cpu_port_rate(min(games, 512), threads, SEED + 1000 + w)
+    tot_plies, tot_t = 0, 0.0
+    for k in range(args.steps):
+        r, plies, dt = cpu_port_rate(games, threads, SEED + k)
+        tot_plies += plies
+        tot_t += dt
+    value = tot_plies / tot_t
+    sample = f"{games} of {BOARDS} games per step from the initial position, <= {PLIES} plies"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8/f64",
+        "data": "synthetic", "config": {"workload": f"cfg2 random playouts {BOARDS}x{PLIES} (sampled)",
+                                        "pick": "philox4x32-10(seed,(game,ply)) mod n_legal"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from chinesechessai_b200 import _lib
+    from chinesechessai_b200.engine import BoardBatch, playout_host, results_host
+    from chinesechessai_b200._lib import BOARD_STRIDE, META_DTYPE, PLAYOUT_RESULT_DTYPE
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference "
+                         "for the CPU port")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    n = args.boards
+    first_id = rank * n
+
+    bb = BoardBatch(n, device=dev, hist_cap=PLIES + 2)
+    results = torch.zeros((n, 40), dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def one_step(k):
+        bb.reset()
+        bb.playout(SEED + k, PLIES, first_game_id=first_id, results=results)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for w in range(max(args.warmup, 0)):
+        one_step(1000 + w)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    launches0 = lib.xq_launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
+           torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    plies = torch.zeros((), dtype=torch.int64, device=dev)
+    barrier()
+    for k in range(args.steps):
+        flush.zero_()                       # L2 flush between timed iterations (untimed)
+        ev[k][0].record()
+        bb.reset()
+        ev[k][1].record()                   # kernel-only window starts after the reset launch
+        bb.playout(SEED + k, PLIES, first_game_id=first_id, results=results)
+        ev[k][2].record()
+        plies += results.view(torch.int32)[:, 0].sum()
+    barrier()
+    launches = lib.xq_launch_count() - launches0
+    step_ms = sum(a.elapsed_time(c) for a, _, c in ev)
+    kern_ms = sum(b.elapsed_time(c) for _, b, c in ev)
+    t = torch.tensor([step_ms, kern_ms], dtype=torch.float64, device=dev)
+    total_plies = plies.clone()
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(total_plies, op=dist.ReduceOp.SUM)
+    step_ms, kern_ms = float(t[0]), float(t[1])
+    total_plies = int(total_plies)
+    value = total_plies / (step_ms * 1e-3)
+
+    # ---- e2e: host buffers through xq_playout_host (H2D + kernel + D2H timed) ----------
+    init = BoardBatch(n, device=dev, hist_cap=1)
+    board0 = init.board.cpu().numpy()
+    meta0 = init.meta_host()
+    hb = torch.empty((n, BOARD_STRIDE), dtype=torch.int8).pin_memory()
+    hm = torch.empty((n, 32), dtype=torch.uint8).pin_memory()
+    hr = torch.empty((n, 40), dtype=torch.uint8).pin_memory()
+    hbn, hmn = hb.numpy(), hm.numpy().view(META_DTYPE).reshape(n)
+    hrn = hr.numpy().view(PLAYOUT_RESULT_DTYPE).reshape(n)
+    e2e_steps = max(1, args.steps)
+    for w in range(2):
+        hbn[:] = board0
+        hmn[:] = meta0
+        playout_host(hbn, hmn, SEED + 2000 + w, PLIES, first_id, 0, local, hrn)
+    barrier()
+    e2e_t, e2e_plies = 0.0, 0
+    for k in range(e2e_steps):
+        hbn[:] = board0
+        hmn[:] = meta0
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        playout_host(hbn, hmn, SEED + k, PLIES, first_id, 0, local, hrn)  # synchronous call
+        e2e_t += time.perf_counter() - t0
+        e2e_plies += int(hrn["plies"].sum())
+    e2e_launches = e2e_steps
+    et = torch.tensor([e2e_t], dtype=torch.float64, device=dev)
+    ep = torch.tensor([e2e_plies], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(et, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ep, op=dist.ReduceOp.SUM)
+    e2e_value = int(ep) / float(et)
+    # device result of step 0 == host-path result of step 0 (same seed): cheap self-check
+    clk = clocks.stop() if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm_peak, peak_src = read_peaks()
+    plies_per_launch = total_plies / (args.steps * world)
+    kern_s = kern_ms * 1e-3 / args.steps
+    achieved = BYTES_PER_STEP_FUSED * plies_per_launch / kern_s / 1e9
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": step_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int8/f64", "data": "synthetic",
+        "config": {"workload": f"cfg2: batched random playouts, {n} boards x <= {PLIES} plies per GPU "
+                               "from the initial position, fused playout kernel",
+                   "boards_per_gpu": n, "max_plies": PLIES,
+                   "pick": "philox4x32-10(seed,(game,ply)) mod n_legal",
+                   "l2": "flushed between timed iterations (256 MiB write)",
+                   "parallelism": f"games sharded over {world} GPU(s), no collective on the path"},
+        "plies_per_step": total_plies / args.steps,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * (BOARD_STRIDE + 32),
+                "d2h_bytes_per_step": n * (BOARD_STRIDE + 32 + 40), "steps": e2e_steps,
+                "api": "xq_playout_host (pinned host buffers)"},
+        "gpu_launches": int(launches + e2e_launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                     "kernel": "xq::playout_kernel<false>",
+                     "bytes_per_board_step": BYTES_PER_STEP_FUSED,
+                     "kernel_ms_per_launch": kern_ms / args.steps,
+                     "note": "integer/latency-bound kernel: SM issue rate binds, not HBM "
+                             "(see profiles/ and DESIGN.md)"},
+        "clocks": clk,
+    }
+    # ---- CPU baseline: C port of the reference path on the host cores, bounded sample ------
+    if world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        rate, _, _ = cpu_port_rate(1024, threads)
+        games = int(max(256, min(BOARDS, rate * 12.0 / 69.0)))
+        rate, plies_c, dt = cpu_port_rate(games, threads)
+        out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                               "sample": f"{games} of {BOARDS} games, {plies_c} plies in {dt:.1f} s "
+                                         "(oracle/xq_oracle.c, pthreads)"}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--boards", type=int, default=BOARDS)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,521 @@
+// xq_kernels.cu — rules-engine kernels and their C-ABI entry points
+// (include/xq_b200.h).  Build: nvcc -gencode arch=compute_100a,code=sm_100a.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include <cuda_bf16.h>
+
+#include "xq_rules.cuh"
+
+namespace xq {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(XQ_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return 0;
+}
+
+static inline int ctas_for(int n_games) { return (n_games + kWarpsPerCta - 1) / kWarpsPerCta; }
+constexpr int kThreads = kWarpsPerCta * 32;
+
+// ---------------------------------------------------------------------------
+// reset (chess_env.py:14-67): one thread per 4 squares.
+__constant__ int8_t c_init_board[XQ_BOARD_STRIDE] = {
+    -5, -4, -3, -2, -1, -2, -3, -4, -5,  //
+    0,  0,  0,  0,  0,  0,  0,  0,  0,   //
+    0,  -6, 0,  0,  0,  0,  0,  -6, 0,   //
+    -7, 0,  -7, 0,  -7, 0,  -7, 0,  -7,  //
+    0,  0,  0,  0,  0,  0,  0,  0,  0,   //
+    0,  0,  0,  0,  0,  0,  0,  0,  0,   //
+    7,  0,  7,  0,  7,  0,  7,  0,  7,   //
+    0,  6,  0,  0,  0,  0,  0,  6,  0,   //
+    0,  0,  0,  0,  0,  0,  0,  0,  0,   //
+    5,  4,  3,  2,  1,  2,  3,  4,  5,   //
+    0,  0,  0,  0,  0,  0};
+
+__global__ void __launch_bounds__(256) reset_kernel(int8_t* __restrict__ board,
+                                                    xq_meta* __restrict__ meta, int n_games) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n_words = (int64_t)n_games * (XQ_BOARD_STRIDE / 4);
+  if (i < n_words) {
+    const int wd = (int)(i % (XQ_BOARD_STRIDE / 4));
+    reinterpret_cast<uint32_t*>(board)[i] = reinterpret_cast<const uint32_t*>(c_init_board)[wd];
+  }
+  if (i < n_games) {
+    uint4 a, b;
+    a.x = 1u | ((uint32_t)XQ_WINNER_NONE << 8);  // player=+1, winner=None, reason 0, done 0
+    a.y = 85u | (4u << 8);                       // red king (9,4), black king (0,4)
+    a.z = a.w = 0u;
+    b.x = b.y = b.z = b.w = 0u;
+    reinterpret_cast<uint4*>(meta + i)[0] = a;
+    reinterpret_cast<uint4*>(meta + i)[1] = b;
+  }
+}
+
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+    position_hash_kernel(const int8_t* __restrict__ board, const xq_meta* __restrict__ meta,
+                         uint64_t* __restrict__ out, int n_games) {
+  __shared__ WarpSmem slab[kWarpsPerCta];
+  const int g = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (g >= n_games) return;
+  WarpSmem& w = slab[threadIdx.x >> 5];
+  load_board(w, board + (size_t)g * XQ_BOARD_STRIDE);
+  const Game G = load_meta(meta + g);
+  const uint64_t k = board_key(w) ^ side_key(G.player);
+  if (lane_id() == 0) out[g] = k;
+}
+
+// ---------------------------------------------------------------------------
+// get_legal_moves (chess_env.py:76-121)
+__global__ void __launch_bounds__(kThreads)
+    legal_moves_kernel(const int8_t* __restrict__ board, xq_meta* __restrict__ meta,
+                       int16_t* __restrict__ moves, int16_t* __restrict__ n_moves,
+                       uint8_t* __restrict__ in_check_out, int n_games) {
+  __shared__ WarpSmem slab[kWarpsPerCta];
+  const int g = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (g >= n_games) return;
+  WarpSmem& w = slab[threadIdx.x >> 5];
+  const int lane = lane_id();
+  load_board(w, board + (size_t)g * XQ_BOARD_STRIDE);
+  build_masks(w);
+  Game G = load_meta(meta + g);
+  const int flags0 = G.flags;
+  const int n = movegen(w, G);
+  int16_t* row = moves + (size_t)g * XQ_MAX_MOVES;
+  for (int i = lane; i < n; i += 32) row[i] = w.moves[i];
+  if (lane == 0) {
+    n_moves[g] = (int16_t)n;
+    if (in_check_out) in_check_out[g] = in_check(w, G, G.player) ? 1 : 0;
+    if (G.flags != flags0) reinterpret_cast<uint8_t*>(meta + g)[6] = (uint8_t)G.flags;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// make_move (chess_env.py:253-406)
+__global__ void __launch_bounds__(kThreads)
+    step_kernel(int8_t* __restrict__ board, xq_meta* __restrict__ meta,
+                uint64_t* __restrict__ pos_hist, int hist_cap, const int16_t* __restrict__ move,
+                double* __restrict__ reward, uint8_t* __restrict__ flags,
+                int16_t* __restrict__ next_moves, int16_t* __restrict__ next_n, int n_games) {
+  __shared__ WarpSmem slab[kWarpsPerCta];
+  const int g = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (g >= n_games) return;
+  WarpSmem& w = slab[threadIdx.x >> 5];
+  const int lane = lane_id();
+  const int mv = move[g];
+  if (mv < 0) {  // frozen game
+    if (lane == 0) {
+      reward[g] = 0.0;
+      const xq_meta m = meta[g];
+      flags[g] = (uint8_t)((m.done & 1) | 2u | (((m.winner + 1) & 3) << 2) | ((m.reason & 15) << 4));
+      if (next_n) next_n[g] = 0;
+    }
+    return;
+  }
+  load_board(w, board + (size_t)g * XQ_BOARD_STRIDE);
+  build_masks(w);
+  Game G = load_meta(meta + g);
+  const StepOut o = step(w, G, mv, pos_hist + (size_t)g * hist_cap, hist_cap);
+  store_board(w, board + (size_t)g * XQ_BOARD_STRIDE);
+  store_meta(meta + g, G);
+  if (lane == 0) {
+    reward[g] = o.reward;
+    flags[g] = step_flags(G, o);
+  }
+  if (next_n) {
+    const int n = o.n_next < 0 ? 0 : o.n_next;
+    if (next_moves) {
+      int16_t* row = next_moves + (size_t)g * XQ_MAX_MOVES;
+      for (int i = lane; i < n; i += 32) row[i] = w.moves[i];
+    }
+    if (lane == 0) next_n[g] = (int16_t)(o.n_next < 0 ? -1 : n);
+  }
+}
+
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+    pick_kernel(const int8_t* __restrict__ board, const xq_meta* __restrict__ meta,
+                const int16_t* __restrict__ moves, const int16_t* __restrict__ n_moves,
+                uint64_t seed, uint32_t first_game_id, uint32_t ply, int capture_bias,
+                int16_t* __restrict__ picked, int n_games) {
+  __shared__ WarpSmem slab[kWarpsPerCta];
+  const int g = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (g >= n_games) return;
+  WarpSmem& w = slab[threadIdx.x >> 5];
+  const int lane = lane_id();
+  const int n = n_moves[g];
+  const int done = meta[g].done;
+  if (n <= 0 || done) {
+    if (lane == 0) picked[g] = -1;
+    return;
+  }
+  load_board(w, board + (size_t)g * XQ_BOARD_STRIDE);
+  const int16_t* row = moves + (size_t)g * XQ_MAX_MOVES;
+  for (int i = lane; i < n; i += 32) w.moves[i] = row[i];
+  __syncwarp();
+  const int idx = pick_index(w, n, seed, first_game_id + (uint32_t)g, ply, capture_bias);
+  if (lane == 0) picked[g] = w.moves[idx];
+}
+
+// ---------------------------------------------------------------------------
+// Fused random playout: state stays in shared memory / registers for all plies.
+__device__ __forceinline__ uint64_t dbits(double d) { return (uint64_t)__double_as_longlong(d); }
+
+template <bool TRACE>
+__global__ void __launch_bounds__(kThreads)
+    playout_kernel(int8_t* __restrict__ board, xq_meta* __restrict__ meta,
+                   uint64_t* __restrict__ pos_hist, int hist_cap, uint64_t seed,
+                   uint32_t first_game_id, int max_plies, int capture_bias,
+                   xq_playout_result* __restrict__ results, int16_t* __restrict__ tr_moves,
+                   int16_t* __restrict__ tr_n, int16_t* __restrict__ tr_pick,
+                   double* __restrict__ tr_reward, uint8_t* __restrict__ tr_flags,
+                   int8_t* __restrict__ tr_boards, int n_games) {
+  __shared__ WarpSmem slab[kWarpsPerCta];
+  const int g = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (g >= n_games) return;
+  WarpSmem& w = slab[threadIdx.x >> 5];
+  const int lane = lane_id();
+  load_board(w, board + (size_t)g * XQ_BOARD_STRIDE);
+  build_masks(w);
+  Game G = load_meta(meta + g);
+  uint64_t* hist = pos_hist + (size_t)g * hist_cap;
+  const uint32_t gid = first_game_id + (uint32_t)g;
+
+  uint64_t digest = 0;
+  double rsum = 0.0;
+  int max_legal = 0, ply = 0;
+  int n = movegen(w, G);
+  for (; ply < max_plies; ++ply) {
+    if (n == 0) break;  // self_play.py:207
+    max_legal = max(max_legal, n);
+    const int idx = pick_index(w, n, seed, gid, (uint32_t)ply, capture_bias);
+    const int mv = w.moves[idx];
+    uint64_t lsum = 0;
+    for (int i = lane; i < n; i += 32)
+      lsum += mix64(((uint64_t)(ply + 1) << 40) | ((uint64_t)(i + 1) << 20) |
+                    (uint64_t)(uint16_t)w.moves[i]);
+    lsum = warp_add64(lsum);
+    if (TRACE) {
+      const size_t t = (size_t)g * max_plies + ply;
+      if (tr_moves)
+        for (int i = lane; i < n; i += 32) tr_moves[t * XQ_MAX_MOVES + i] = w.moves[i];
+      if (lane == 0) {
+        if (tr_n) tr_n[t] = (int16_t)n;
+        if (tr_pick) tr_pick[t] = (int16_t)mv;
+      }
+    }
+    __syncwarp();
+    const StepOut o = step(w, G, mv, hist, hist_cap);
+    rsum = __dadd_rn(rsum, o.reward);
+    uint64_t wsum = lsum;
+    wsum += mix64(0xA5A5000000000000ULL ^ ((uint64_t)n << 16) ^ (uint64_t)mv);
+    wsum += o.key_next;
+    wsum += mix64(dbits(o.reward));
+    wsum += mix64(0x5151000000000000ULL | (uint64_t)(o.done & 1) | ((uint64_t)(G.winner + 2) << 8) |
+                  ((uint64_t)G.reason << 16) | ((uint64_t)(o.is_int & 1) << 24));
+    digest = mix64(digest + wsum);
+    if (TRACE) {
+      const size_t t = (size_t)g * max_plies + ply;
+      if (lane == 0) {
+        if (tr_reward) tr_reward[t] = o.reward;
+        if (tr_flags) tr_flags[t] = step_flags(G, o);
+      }
+      if (tr_boards) {
+        __syncwarp();
+        for (int s = lane; s < XQ_NSQ; s += 32) tr_boards[t * XQ_NSQ + s] = w.sq[s];
+      }
+    }
+    if (o.done) {
+      ++ply;
+      break;
+    }
+    n = o.n_next;
+  }
+  const uint64_t fkey = board_key(w) ^ side_key(G.player);
+  store_board(w, board + (size_t)g * XQ_BOARD_STRIDE);
+  store_meta(meta + g, G);
+  if (lane == 0) {
+    xq_playout_result r;
+    r.plies = ply;
+    r.winner = G.winner;
+    r.reason = G.reason;
+    r.max_legal = max_legal;
+    r.reward_sum = rsum;
+    r.digest = digest;
+    r.final_hash = fkey;
+    results[g] = r;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// encode_board (neural_network.py:128-146): one thread per (game, square);
+// each plane store is a run of consecutive floats across the warp.
+template <typename T>
+__global__ void __launch_bounds__(256)
+    encode_kernel(const int8_t* __restrict__ board, int board_stride,
+                  const int8_t* __restrict__ player, int player_stride, T* __restrict__ planes,
+                  int n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)n * XQ_NSQ) return;
+  const int g = (int)(i / XQ_NSQ), s = (int)(i - (int64_t)g * XQ_NSQ);
+  const int p = board[(size_t)g * board_stride + s];
+  const int pl = player[(size_t)g * player_stride];
+  T* out = planes + (size_t)g * XQ_PLANES * XQ_NSQ + s;
+  const T one = (T)1.0f, zero = (T)0.0f;
+#pragma unroll
+  for (int k = 1; k <= 7; ++k) {
+    out[(k - 1) * XQ_NSQ] = p == k ? one : zero;
+    out[(k + 6) * XQ_NSQ] = p == -k ? one : zero;
+  }
+  out[14 * XQ_NSQ] = pl == 1 ? one : zero;
+}
+
+// _logits_to_move_probs (neural_network.py:148-169): warp per position.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+    priors_kernel(const T* __restrict__ logits, const int16_t* __restrict__ moves, int moves_stride,
+                  const int16_t* __restrict__ n_moves, float* __restrict__ priors, int n) {
+  const int g = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (g >= n) return;
+  const int lane = lane_id();
+  const int cnt = min((int)n_moves[g], XQ_MAX_MOVES);
+  const T* lg = logits + (size_t)g * XQ_POLICY;
+  const int16_t* mv = moves + (size_t)g * moves_stride;
+  float v[XQ_MAX_MOVES / 32];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < XQ_MAX_MOVES / 32; ++k) {
+    const int i = k * 32 + lane;
+    v[k] = i < cnt ? (float)lg[mv[i]] : -INFINITY;
+    mx = fmaxf(mx, v[k]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, o));
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < XQ_MAX_MOVES / 32; ++k) {
+    const int i = k * 32 + lane;
+    v[k] = i < cnt ? expf(v[k] - mx) : 0.f;
+    sum += v[k];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(kFull, sum, o);
+#pragma unroll
+  for (int k = 0; k < XQ_MAX_MOVES / 32; ++k) {
+    const int i = k * 32 + lane;
+    if (i < XQ_MAX_MOVES) priors[(size_t)g * XQ_MAX_MOVES + i] = i < cnt ? __fdiv_rn(v[k], sum) : 0.f;
+  }
+}
+
+}  // namespace xq
+
+// ===========================================================================
+// C ABI
+using namespace xq;
+
+extern "C" {
+
+int xq_abi_version(void) { return XQ_ABI_VERSION; }
+const char* xq_last_error(void) { return g_err; }
+int64_t xq_launch_count(void) { return g_launches.load(); }
+
+int xq_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    return fail(XQ_E_NODEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+  }
+  return n;
+}
+
+#define XQ_REQUIRE(cond, msg) \
+  do {                        \
+    if (!(cond)) return fail(XQ_E_ARG, "%s: %s", __func__, msg); \
+  } while (0)
+
+int xq_reset(int8_t* board, xq_meta* meta, int n_games, void* stream) {
+  XQ_REQUIRE(board && meta && n_games >= 0, "null pointer or negative n_games");
+  if (n_games == 0) return 0;
+  const int64_t n = (int64_t)n_games * (XQ_BOARD_STRIDE / 4);
+  reset_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(board, meta, n_games);
+  return check_launch("xq_reset");
+}
+
+int xq_position_hash(const int8_t* board, const xq_meta* meta, uint64_t* out, int n_games,
+                     void* stream) {
+  XQ_REQUIRE(board && meta && out && n_games >= 0, "null pointer or negative n_games");
+  if (n_games == 0) return 0;
+  position_hash_kernel<<<ctas_for(n_games), kThreads, 0, (cudaStream_t)stream>>>(board, meta, out,
+                                                                                 n_games);
+  return check_launch("xq_position_hash");
+}
+
+int xq_legal_moves(const int8_t* board, xq_meta* meta, int16_t* moves, int16_t* n_moves,
+                   uint8_t* in_check, int n_games, void* stream) {
+  XQ_REQUIRE(board && meta && moves && n_moves && n_games >= 0, "null pointer or negative n_games");
+  if (n_games == 0) return 0;
+  legal_moves_kernel<<<ctas_for(n_games), kThreads, 0, (cudaStream_t)stream>>>(
+      board, meta, moves, n_moves, in_check, n_games);
+  return check_launch("xq_legal_moves");
+}
+
+int xq_step(int8_t* board, xq_meta* meta, uint64_t* pos_hist, int hist_cap, const int16_t* move,
+            double* reward, uint8_t* flags, int16_t* next_moves, int16_t* next_n, int n_games,
+            void* stream) {
+  XQ_REQUIRE(board && meta && pos_hist && move && reward && flags && n_games >= 0 && hist_cap > 0,
+             "null pointer, negative n_games or hist_cap <= 0");
+  XQ_REQUIRE(!(next_moves && !next_n), "next_moves requires next_n");
+  if (n_games == 0) return 0;
+  step_kernel<<<ctas_for(n_games), kThreads, 0, (cudaStream_t)stream>>>(
+      board, meta, pos_hist, hist_cap, move, reward, flags, next_moves, next_n, n_games);
+  return check_launch("xq_step");
+}
+
+int xq_pick_moves(const int8_t* board, const xq_meta* meta, const int16_t* moves,
+                  const int16_t* n_moves, uint64_t seed, uint32_t first_game_id, uint32_t ply,
+                  int capture_bias, int16_t* picked, int n_games, void* stream) {
+  XQ_REQUIRE(board && meta && moves && n_moves && picked && n_games >= 0,
+             "null pointer or negative n_games");
+  XQ_REQUIRE(capture_bias >= 0 && capture_bias <= 256, "capture_bias out of [0,256]");
+  if (n_games == 0) return 0;
+  pick_kernel<<<ctas_for(n_games), kThreads, 0, (cudaStream_t)stream>>>(
+      board, meta, moves, n_moves, seed, first_game_id, ply, capture_bias, picked, n_games);
+  return check_launch("xq_pick_moves");
+}
+
+int xq_playout(int8_t* board, xq_meta* meta, uint64_t* pos_hist, int hist_cap, uint64_t seed,
+               uint32_t first_game_id, int max_plies, int capture_bias, xq_playout_result* results,
+               int16_t* tr_moves, int16_t* tr_n, int16_t* tr_pick, double* tr_reward,
+               uint8_t* tr_flags, int8_t* tr_boards, int n_games, void* stream) {
+  XQ_REQUIRE(board && meta && pos_hist && results && n_games >= 0 && hist_cap > 0 && max_plies >= 0,
+             "null pointer, negative size or hist_cap <= 0");
+  XQ_REQUIRE(capture_bias >= 0 && capture_bias <= 256, "capture_bias out of [0,256]");
+  if (n_games == 0) return 0;
+  const bool trace = tr_moves || tr_n || tr_pick || tr_reward || tr_flags || tr_boards;
+  if (trace)
+    playout_kernel<true><<<ctas_for(n_games), kThreads, 0, (cudaStream_t)stream>>>(
+        board, meta, pos_hist, hist_cap, seed, first_game_id, max_plies, capture_bias, results,
+        tr_moves, tr_n, tr_pick, tr_reward, tr_flags, tr_boards, n_games);
+  else
+    playout_kernel<false><<<ctas_for(n_games), kThreads, 0, (cudaStream_t)stream>>>(
+        board, meta, pos_hist, hist_cap, seed, first_game_id, max_plies, capture_bias, results,
+        nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, n_games);
+  return check_launch("xq_playout");
+}
+
+#define XQ_CUDA(call)                                                             \
+  do {                                                                            \
+    cudaError_t e_ = (call);                                                      \
+    if (e_ != cudaSuccess) {                                                      \
+      rc = fail(XQ_E_CUDA, "%s: %s: %s", __func__, #call, cudaGetErrorString(e_)); \
+      goto done;                                                                  \
+    }                                                                             \
+  } while (0)
+
+int xq_playout_host(int8_t* board_h, xq_meta* meta_h, uint64_t seed, uint32_t first_game_id,
+                    int max_plies, int capture_bias, xq_playout_result* results_h, int n_games,
+                    int device) {
+  XQ_REQUIRE(board_h && meta_h && results_h && n_games >= 0 && max_plies >= 0,
+             "null pointer or negative size");
+  if (n_games == 0) return 0;
+  int rc = 0;
+  int8_t* board = nullptr;
+  xq_meta* meta = nullptr;
+  uint64_t* hist = nullptr;
+  xq_playout_result* res = nullptr;
+  cudaStream_t st = nullptr;
+  const size_t nb = (size_t)n_games * XQ_BOARD_STRIDE, nm = (size_t)n_games * sizeof(xq_meta);
+  int hist_cap = 0;
+  {
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(XQ_E_NODEVICE, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+  }
+  {
+    static thread_local int pool_ready_dev = -1;
+    if (pool_ready_dev != device) {  // keep freed blocks cached between calls
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+      }
+      pool_ready_dev = device;
+    }
+  }
+  // history capacity: existing entries + the plies this call can add
+  for (int g = 0; g < n_games; ++g) hist_cap = meta_h[g].hist_len > hist_cap ? meta_h[g].hist_len : hist_cap;
+  XQ_REQUIRE(hist_cap == 0, "xq_playout_host starts from states without position history");
+  hist_cap = max_plies > 0 ? max_plies : 1;
+  XQ_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  XQ_CUDA(cudaMallocAsync(&board, nb, st));
+  XQ_CUDA(cudaMallocAsync(&meta, nm, st));
+  XQ_CUDA(cudaMallocAsync(&hist, (size_t)n_games * hist_cap * sizeof(uint64_t), st));
+  XQ_CUDA(cudaMallocAsync(&res, (size_t)n_games * sizeof(xq_playout_result), st));
+  XQ_CUDA(cudaMemcpyAsync(board, board_h, nb, cudaMemcpyHostToDevice, st));
+  XQ_CUDA(cudaMemcpyAsync(meta, meta_h, nm, cudaMemcpyHostToDevice, st));
+  rc = xq_playout(board, meta, hist, hist_cap, seed, first_game_id, max_plies, capture_bias, res,
+                  nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, n_games, st);
+  if (rc) goto done;
+  XQ_CUDA(cudaMemcpyAsync(board_h, board, nb, cudaMemcpyDeviceToHost, st));
+  XQ_CUDA(cudaMemcpyAsync(meta_h, meta, nm, cudaMemcpyDeviceToHost, st));
+  XQ_CUDA(cudaMemcpyAsync(results_h, res, (size_t)n_games * sizeof(xq_playout_result),
+                          cudaMemcpyDeviceToHost, st));
+  XQ_CUDA(cudaStreamSynchronize(st));
+done:
+  if (st) {
+    if (board) cudaFreeAsync(board, st);
+    if (meta) cudaFreeAsync(meta, st);
+    if (hist) cudaFreeAsync(hist, st);
+    if (res) cudaFreeAsync(res, st);
+    cudaStreamSynchronize(st);
+    cudaStreamDestroy(st);
+  }
+  return rc;
+}
+
+int xq_encode_planes(const int8_t* board, int board_stride, const int8_t* player, int player_stride,
+                     void* planes, int out_bf16, int n, void* stream) {
+  XQ_REQUIRE(board && player && planes && n >= 0 && board_stride >= XQ_NSQ && player_stride >= 1,
+             "null pointer or bad stride");
+  if (n == 0) return 0;
+  const int64_t total = (int64_t)n * XQ_NSQ;
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  if (out_bf16)
+    encode_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        board, board_stride, player, player_stride, (__nv_bfloat16*)planes, n);
+  else
+    encode_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(board, board_stride, player,
+                                                                 player_stride, (float*)planes, n);
+  return check_launch("xq_encode_planes");
+}
+
+int xq_policy_priors(const void* logits, int logits_bf16, const int16_t* moves, int moves_stride,
+                     const int16_t* n_moves, float* priors, int n, void* stream) {
+  XQ_REQUIRE(logits && moves && n_moves && priors && n >= 0 && moves_stride >= 1,
+             "null pointer or bad stride");
+  if (n == 0) return 0;
+  if (logits_bf16)
+    priors_kernel<__nv_bfloat16><<<ctas_for(n), kThreads, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)logits, moves, moves_stride, n_moves, priors, n);
+  else
+    priors_kernel<float><<<ctas_for(n), kThreads, 0, (cudaStream_t)stream>>>(
+        (const float*)logits, moves, moves_stride, n_moves, priors, n);
+  return check_launch("xq_policy_priors");
+}
+
+}  // extern "C"

@@ -1,0 +1,636 @@
+// xq_rules.cuh — warp-per-board Xiangqi rules engine for sm_100a.
+//
+// One warp owns one board.  The 90 squares, per-row / per-column occupancy
+// masks, the own-piece list, the pseudo-legal candidate list and the legal
+// move list live in a 1 KB shared-memory slab per warp; game scalars are
+// warp-uniform registers.  Semantics restate the reference's rules engine
+// (chess_env.py; file:line cited per function), quirks included (SURVEY.md
+// Appendix A).  Unlike the reference, which simulates each candidate on a
+// board copy and regenerates every opposing piece's moves (:431-464,:506-548),
+// legality is decided by an inverse, king-outward attack test on occupancy
+// bit masks with the candidate applied as an override — no board copies.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/xq_b200.h"
+
+namespace xq {
+
+constexpr int kWarpsPerCta = 8;
+constexpr unsigned kFull = 0xffffffffu;
+
+enum : int { KING = 1, ADVISOR = 2, BISHOP = 3, KNIGHT = 4, ROOK = 5, CANNON = 6, PAWN = 7 };
+
+// Per-warp shared-memory slab (1024 B).
+struct __align__(16) WarpSmem {
+  int8_t sq[XQ_BOARD_STRIDE];  // board, row-major r*9+c (chess_env.py:17)
+  uint16_t rows[16];           // rows[r] bit c = square (r,c) occupied
+  uint16_t cols[16];           // cols[c] bit r = square (r,c) occupied
+  uint8_t own[96];             // squares of the side-to-move's pieces, row-major order
+  uint8_t cf[XQ_CAND_CAP];     // candidate from-squares (canonical order)
+  uint8_t ct[XQ_CAND_CAP];     // candidate to-squares
+  int16_t moves[XQ_MAX_MOVES]; // legal moves, packed from*90+to
+};
+static_assert(sizeof(WarpSmem) == 1024, "WarpSmem must be 1 KB");
+
+// Warp-uniform game scalars (chess_env.py:17-31,62-65).
+struct Game {
+  int player, winner, reason, done, red_king, black_king, flags;
+  int move_count, no_capture, cchecks, hist_len, check_len;
+  unsigned check_bits;
+};
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ULL;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+  return x ^ (x >> 31);
+}
+
+__device__ __forceinline__ uint64_t warp_xor64(uint64_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v ^= __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ uint64_t warp_add64(uint64_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+
+__device__ __forceinline__ uint64_t side_key(int player) {
+  return mix64(0x7000ULL + (player == 1 ? 0u : 1u));  // chess_env.py:503
+}
+
+// Position key without the side byte: XOR of per-(piece,square) keys, computed
+// lane-parallel (3 squares per lane).  _get_position_hash, chess_env.py:497-504.
+__device__ __forceinline__ uint64_t board_key(const WarpSmem& w) {
+  const int lane = lane_id();
+  uint64_t h = 0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    int s = lane + 32 * k;
+    int p = (s < XQ_NSQ) ? w.sq[s] : 0;
+    if (p != 0) h ^= mix64((uint64_t)((p + 8) * 128 + s));
+  }
+  return warp_xor64(h);
+}
+
+// ---- state load / store ---------------------------------------------------
+__device__ __forceinline__ void load_board(WarpSmem& w, const int8_t* __restrict__ board_row) {
+  const int lane = lane_id();
+  if (lane < XQ_BOARD_STRIDE / 4)
+    reinterpret_cast<uint32_t*>(w.sq)[lane] = reinterpret_cast<const uint32_t*>(board_row)[lane];
+  __syncwarp();
+}
+
+__device__ __forceinline__ void store_board(const WarpSmem& w, int8_t* __restrict__ board_row) {
+  const int lane = lane_id();
+  __syncwarp();
+  if (lane < XQ_BOARD_STRIDE / 4)
+    reinterpret_cast<uint32_t*>(board_row)[lane] = reinterpret_cast<const uint32_t*>(w.sq)[lane];
+}
+
+__device__ __forceinline__ Game load_meta(const xq_meta* __restrict__ m) {
+  const uint4* p = reinterpret_cast<const uint4*>(m);
+  uint4 a = p[0], b = p[1];
+  Game g;
+  g.player = (int8_t)(a.x & 0xff);
+  g.winner = (int8_t)((a.x >> 8) & 0xff);
+  g.reason = (a.x >> 16) & 0xff;
+  g.done = (a.x >> 24) & 0xff;
+  g.red_king = (int8_t)(a.y & 0xff);
+  g.black_king = (int8_t)((a.y >> 8) & 0xff);
+  g.flags = (a.y >> 16) & 0xff;
+  g.move_count = (int)a.z;
+  g.no_capture = (int)a.w;
+  g.cchecks = (int)b.x;
+  g.hist_len = (int)b.y;
+  g.check_bits = b.z;
+  g.check_len = (int)b.w;
+  return g;
+}
+
+__device__ __forceinline__ void store_meta(xq_meta* __restrict__ m, const Game& g) {
+  if (lane_id() == 0) {
+    uint4 a, b;
+    a.x = (uint32_t)(g.player & 0xff) | ((uint32_t)(g.winner & 0xff) << 8) |
+          ((uint32_t)(g.reason & 0xff) << 16) | ((uint32_t)(g.done & 0xff) << 24);
+    a.y = (uint32_t)(g.red_king & 0xff) | ((uint32_t)(g.black_king & 0xff) << 8) |
+          ((uint32_t)(g.flags & 0xff) << 16);
+    a.z = (uint32_t)g.move_count;
+    a.w = (uint32_t)g.no_capture;
+    b.x = (uint32_t)g.cchecks;
+    b.y = (uint32_t)g.hist_len;
+    b.z = g.check_bits;
+    b.w = (uint32_t)g.check_len;
+    uint4* p = reinterpret_cast<uint4*>(m);
+    p[0] = a;
+    p[1] = b;
+  }
+}
+
+// Row / column occupancy masks from the staged board.
+__device__ __forceinline__ void build_masks(WarpSmem& w) {
+  const int lane = lane_id();
+  if (lane < 10) {
+    unsigned m = 0;
+#pragma unroll
+    for (int c = 0; c < 9; ++c) m |= (w.sq[lane * 9 + c] != 0 ? 1u : 0u) << c;
+    w.rows[lane] = (uint16_t)m;
+  } else if (lane >= 16 && lane < 25) {
+    const int c = lane - 16;
+    unsigned m = 0;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) m |= (w.sq[r * 9 + c] != 0 ? 1u : 0u) << r;
+    w.cols[c] = (uint16_t)m;
+  }
+  __syncwarp();
+}
+
+// ---- attack test -----------------------------------------------------------
+// Is square K a pseudo-target of any piece of sign `es` (the attackers), with
+// K/A/B/P geometry taken from side `geo` (chess_env.py:506-548 — the reference
+// regenerates attackers' moves with self.current_player's geometry, quirk A.3)?
+// The candidate (from,to,mover) is applied as an override (from<0: none).
+// `exotic` enables the K/A/B probes (warp-uniform hint; always safe to pass true).
+__device__ __forceinline__ bool attacked(const WarpSmem& w, int K, int es, int geo, int from,
+                                         int to, int mover, bool exotic, unsigned* colm_out) {
+  const int kr = K / 9, kc = K - kr * 9;
+  unsigned rowm = w.rows[kr], colm = w.cols[kc];
+  if (from >= 0) {
+    const int fr = from / 9, fc = from - fr * 9, tr = to / 9, tc = to - tr * 9;
+    if (fr == kr) rowm &= ~(1u << fc);
+    if (fc == kc) colm &= ~(1u << fr);
+    if (tr == kr) rowm |= 1u << tc;
+    if (tc == kc) colm |= 1u << tr;
+  }
+  if (colm_out) *colm_out = colm;
+  auto pc = [&](int s) -> int { return s == to ? mover : (s == from ? 0 : (int)w.sq[s]); };
+  const bool kocc = (rowm >> kc) & 1u;
+  const int rook = es * ROOK, cannon = es * CANNON, pawn = es * PAWN, king = es * KING;
+  const bool in_pal = (kc >= 3 && kc <= 5) && (geo == 1 ? kr >= 7 : kr <= 2);  // :127-131
+  const bool side_ok = geo == 1 ? kr < 5 : kr >= 5;                             // :242,:247
+  bool hit = false;
+
+  // rays: first piece = rook / adjacent pawn / adjacent king; cannon over one screen
+  {  // (0,+1)
+    unsigned a = rowm >> (kc + 1);
+    if (a) {
+      int d1 = __ffs(a), q = pc(K + d1);
+      hit |= (q == rook) | (q == cannon && !kocc) |
+             (d1 == 1 && ((q == pawn && side_ok) | (q == king && in_pal)));
+      unsigned a2 = a & (a - 1);
+      if (kocc && a2) hit |= pc(K + __ffs(a2)) == cannon;
+    }
+  }
+  {  // (0,-1)
+    unsigned b = rowm & ((1u << kc) - 1u);
+    if (b) {
+      int hb = 31 - __clz(b), q = pc(kr * 9 + hb);
+      hit |= (q == rook) | (q == cannon && !kocc) |
+             (kc - hb == 1 && ((q == pawn && side_ok) | (q == king && in_pal)));
+      unsigned b2 = b & ~(1u << hb);
+      if (kocc && b2) hit |= pc(kr * 9 + 31 - __clz(b2)) == cannon;
+    }
+  }
+  {  // (+1,0): a pawn below K attacks it iff pawns move toward smaller rows (geo==1, :241)
+    unsigned a = colm >> (kr + 1);
+    if (a) {
+      int d1 = __ffs(a), q = pc(K + 9 * d1);
+      hit |= (q == rook) | (q == cannon && !kocc) |
+             (d1 == 1 && ((q == pawn && geo == 1) | (q == king && in_pal)));
+      unsigned a2 = a & (a - 1);
+      if (kocc && a2) hit |= pc(K + 9 * __ffs(a2)) == cannon;
+    }
+  }
+  {  // (-1,0)
+    unsigned b = colm & ((1u << kr) - 1u);
+    if (b) {
+      int hb = 31 - __clz(b), q = pc(hb * 9 + kc);
+      hit |= (q == rook) | (q == cannon && !kocc) |
+             (kr - hb == 1 && ((q == pawn && geo == -1) | (q == king && in_pal)));
+      unsigned b2 = b & ~(1u << hb);
+      if (kocc && b2) hit |= pc((31 - __clz(b2)) * 9 + kc) == cannon;
+    }
+  }
+  // diagonal neighbours: knight legs (:182-197), bishop eyes (:161-174), advisors (:149-152)
+  const int knight = es * KNIGHT, bishop = es * BISHOP, advisor = es * ADVISOR;
+  const bool bside = geo == 1 ? kr >= 5 : kr <= 3;  // :159,:167-170 (black river = 4: rows 0..3)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int a = (i & 2) ? 1 : -1, b = (i & 1) ? 1 : -1;
+    const int lr = kr + a, lc = kc + b;
+    if (lr < 0 || lr > 9 || lc < 0 || lc > 8) continue;
+    const int ql = pc(lr * 9 + lc);
+    if (ql == 0) {
+      const int r2 = kr + 2 * a, c2 = kc + 2 * b;
+      const bool r2ok = r2 >= 0 && r2 <= 9, c2ok = c2 >= 0 && c2 <= 8;
+      if (r2ok) hit |= pc(r2 * 9 + lc) == knight;
+      if (c2ok) hit |= pc(lr * 9 + c2) == knight;
+      if (exotic && bside && r2ok && c2ok) hit |= pc(r2 * 9 + c2) == bishop;
+    } else if (exotic && in_pal && ql == advisor) {
+      hit = true;
+    }
+  }
+  return hit;
+}
+
+// _is_in_check(player) on the staged board (chess_env.py:506-548).
+__device__ __forceinline__ bool in_check(const WarpSmem& w, const Game& g, int player) {
+  const int K = player == 1 ? g.red_king : g.black_king;
+  if (K < 0) return false;  // :517
+  return attacked(w, K, -player, g.player, -1, -1, 0, true, nullptr);
+}
+
+// _is_move_suicide (chess_env.py:431-464): own king attacked after the move
+// (geometry of the side to move) OR cached kings face each other (:466-495;
+// only the MOVING king's cache is refreshed, :448-451 — stale-cache quirk A.4).
+__device__ __forceinline__ bool suicide(const WarpSmem& w, const Game& g, int from, int to,
+                                        bool exotic) {
+  const int mover = w.sq[from];
+  int red = g.red_king, black = g.black_king;
+  if (mover == KING) red = to;
+  else if (mover == -KING) black = to;
+  const int K = g.player == 1 ? red : black;
+  unsigned colm = 0;
+  bool bad = false;
+  if (K >= 0) bad = attacked(w, K, -g.player, g.player, from, to, mover, exotic, &colm);
+  if (red >= 0 && black >= 0) {
+    const int rr = red / 9, rc = red - rr * 9, br = black / 9, bc = black - br * 9;
+    if (rc == bc) {
+      if (K < 0) return bad;  // unreachable: both caches set implies K >= 0
+      const int lo = min(rr, br), hi = max(rr, br);
+      const unsigned between = ((1u << hi) - 1u) & ~((2u << lo) - 1u);
+      bad |= (colm & between) == 0;
+    }
+  }
+  return bad;
+}
+
+// ---- move generation --------------------------------------------------------
+// get_legal_moves (chess_env.py:76-121).  Fills w.moves in the reference's
+// order and returns the count; *ncand_out = pseudo-legal candidates tested.
+// Phase A: work item = (own piece, direction) -> candidate list via an ordered
+// warp scan.  Phase B: 32 candidates per round through suicide(), ordered
+// compaction with ballot/popc.
+__device__ __forceinline__ int movegen(WarpSmem& w, Game& g) {
+  const int lane = lane_id();
+  const unsigned lt = (1u << lane) - 1u;
+  const int player = g.player;
+
+  // own-piece list in row-major order (:82-87) + "exotic" hint
+  const int ownK = player == 1 ? g.red_king : g.black_king;
+  const int okr = ownK >= 0 ? ownK / 9 : -100;
+  int n_own = 0;
+  bool ex = false;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int s = lane + 32 * k;
+    const int p = s < XQ_NSQ ? (int)w.sq[s] : 0;
+    const bool mine = p * player > 0;
+    const unsigned b = __ballot_sync(kFull, mine);
+    if (mine) w.own[n_own + __popc(b & lt)] = (uint8_t)s;
+    n_own += __popc(b);
+    const int ap = p < 0 ? -p : p;
+    ex |= (p * player < 0) && ap <= BISHOP && abs(s / 9 - okr) <= 3;
+  }
+  const bool exotic = __any_sync(kFull, ex);
+  __syncwarp();
+
+  // Phase A
+  int ncand = 0;
+  const int n_items = n_own * 4;
+  for (int base = 0; base < n_items; base += 32) {
+    const int t = base + lane;
+    int empties = 0, delta = 0, e1 = -1, e2 = -1, from = 0;
+    if (t < n_items) {
+      from = w.own[t >> 2];
+      const int d = t & 3;
+      const int p = w.sq[from];
+      const int pt = p < 0 ? -p : p;
+      const int r = from / 9, c = from - r * 9;
+      auto free_sq = [&](int s) -> bool { return (int)w.sq[s] * player <= 0; };  // :116
+      if (pt == ROOK || pt == CANNON) {  // :199-235, rays (0,1),(0,-1),(1,0),(-1,0)
+        const bool horiz = d < 2, fwd = (d & 1) == 0;
+        const int len = horiz ? 9 : 10;
+        unsigned m = horiz ? w.rows[r] : w.cols[c];
+        int x = horiz ? c : r;
+        if (!fwd) {  // mirror so the ray always runs toward higher bits
+          m = __brev(m) >> (32 - len);
+          x = len - 1 - x;
+        }
+        delta = (horiz ? 1 : 9) * (fwd ? 1 : -1);
+        const unsigned ahead = m >> (x + 1);
+        const int first = ahead ? __ffs(ahead) : 0;
+        empties = first ? first - 1 : len - 1 - x;
+        int hitd = first;
+        if (pt == CANNON) {
+          const unsigned a2 = ahead & (ahead - 1);
+          hitd = a2 ? __ffs(a2) : 0;
+        }
+        if (hitd) {
+          const int s = from + hitd * delta;
+          if (free_sq(s)) e1 = s;
+        }
+      } else if (pt == KNIGHT) {  // :178-197, offsets in pairs sharing a leg
+        const int lr = r + (d == 0 ? 1 : d == 1 ? -1 : 0), lc = c + (d == 2 ? 1 : d == 3 ? -1 : 0);
+        if (lr >= 0 && lr <= 9 && lc >= 0 && lc <= 8 && w.sq[lr * 9 + lc] == 0) {
+          int r1, c1, r2, c2;
+          if (d < 2) {
+            r1 = r2 = r + (d == 0 ? 2 : -2);
+            c1 = c + 1;
+            c2 = c - 1;
+          } else {
+            c1 = c2 = c + (d == 2 ? 2 : -2);
+            r1 = r + 1;
+            r2 = r - 1;
+          }
+          if (r1 >= 0 && r1 <= 9 && c1 >= 0 && c1 <= 8 && free_sq(r1 * 9 + c1)) e1 = r1 * 9 + c1;
+          if (r2 >= 0 && r2 <= 9 && c2 >= 0 && c2 <= 8 && free_sq(r2 * 9 + c2)) e2 = r2 * 9 + c2;
+        }
+      } else if (pt == KING || pt == ADVISOR) {  // :123-154, palace of the side to move
+        int dr, dc;
+        if (pt == KING) {
+          dr = d == 2 ? 1 : d == 3 ? -1 : 0;
+          dc = d == 0 ? 1 : d == 1 ? -1 : 0;
+        } else {
+          dr = d < 2 ? 1 : -1;
+          dc = (d & 1) ? -1 : 1;
+        }
+        const int nr = r + dr, nc = c + dc;
+        const bool pal = nc >= 3 && nc <= 5 && (player == 1 ? (nr >= 7 && nr <= 9) : (nr >= 0 && nr <= 2));
+        if (pal && free_sq(nr * 9 + nc)) e1 = nr * 9 + nc;
+      } else if (pt == BISHOP) {  // :156-176
+        const int dr = d < 2 ? 2 : -2, dc = (d & 1) ? -2 : 2;
+        const int nr = r + dr, nc = c + dc;
+        if (nr >= 0 && nr <= 9 && nc >= 0 && nc <= 8 && (player == 1 ? nr >= 5 : nr <= 3) &&
+            w.sq[(r + dr / 2) * 9 + c + dc / 2] == 0 && free_sq(nr * 9 + nc))
+          e1 = nr * 9 + nc;
+      } else if (pt == PAWN) {  // :237-251
+        const bool crossed = player == 1 ? r < 5 : r >= 5;
+        int nr = r, nc = c;
+        bool ok = true;
+        if (d == 0) nr = r - player;
+        else if (d == 1) { nc = c - 1; ok = crossed; }
+        else if (d == 2) { nc = c + 1; ok = crossed; }
+        else ok = false;
+        if (ok && nr >= 0 && nr <= 9 && nc >= 0 && nc <= 8 && free_sq(nr * 9 + nc)) e1 = nr * 9 + nc;
+      }
+    }
+    const int cnt = empties + (e1 >= 0) + (e2 >= 0);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int v = __shfl_up_sync(kFull, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(kFull, incl, 31);
+    if (ncand + total > XQ_CAND_CAP) {  // warp-uniform; only on absurd poked boards
+      g.flags |= XQ_F_OVERFLOW;
+      break;
+    }
+    int off = ncand + incl - cnt;
+    ncand += total;
+    for (int k = 1; k <= empties; ++k, ++off) {
+      w.cf[off] = (uint8_t)from;
+      w.ct[off] = (uint8_t)(from + k * delta);
+    }
+    if (e1 >= 0) { w.cf[off] = (uint8_t)from; w.ct[off] = (uint8_t)e1; ++off; }
+    if (e2 >= 0) { w.cf[off] = (uint8_t)from; w.ct[off] = (uint8_t)e2; }
+  }
+  __syncwarp();
+
+  // Phase B
+  int n_legal = 0;
+  for (int base = 0; base < ncand; base += 32) {
+    const int j = base + lane;
+    bool ok = false;
+    int from = 0, to = 0;
+    if (j < ncand) {
+      from = w.cf[j];
+      to = w.ct[j];
+      ok = !suicide(w, g, from, to, exotic);  // :118
+    }
+    const unsigned m = __ballot_sync(kFull, ok);
+    const int idx = n_legal + __popc(m & lt);
+    if (ok && idx < XQ_MAX_MOVES) w.moves[idx] = (int16_t)(from * 90 + to);
+    n_legal += __popc(m);
+  }
+  if (n_legal > XQ_MAX_MOVES) {
+    n_legal = XQ_MAX_MOVES;
+    g.flags |= XQ_F_OVERFLOW;
+  }
+  __syncwarp();
+  return n_legal;
+}
+
+// ---- step -------------------------------------------------------------------
+// _evaluate_position_change (chess_env.py:683-737); before the side switch.
+__device__ __forceinline__ double position_change(int type, int player, int from, int to,
+                                                  int enemy_king) {
+  const int fr = from / 9, fc = from - fr * 9, tr = to / 9, tc = to - tr * 9;
+  double score = 0.0;
+  const int advance = player == 1 ? fr - tr : tr - fr;
+  if (advance > 0) {
+    if (type == PAWN) score = __dadd_rn(score, __dmul_rn((double)advance, 2.0));
+    else if (type == ROOK || type == CANNON) score = __dadd_rn(score, __dmul_rn((double)advance, 1.5));
+    else if (type == KNIGHT) score = __dadd_rn(score, (double)advance);
+  }
+  if (tc >= 3 && tc <= 5) {
+    score = __dadd_rn(score, 1.5);
+    if (tr >= 3 && tr <= 6) score = __dadd_rn(score, 1.0);
+  }
+  if (type == PAWN && (player == 1 ? tr < 5 : tr >= 5)) score = __dadd_rn(score, 3.0);
+  if (enemy_king >= 0) {
+    const int kr = enemy_king / 9, kc = enemy_king - kr * 9;
+    const int od = abs(fr - kr) + abs(fc - kc), nd = abs(tr - kr) + abs(tc - kc);
+    if (nd < od) score = __dadd_rn(score, __dmul_rn((double)(od - nd), 0.5));
+  }
+  return score;
+}
+
+struct StepOut {
+  double reward;  // valid on every lane (warp-uniform inputs)
+  int is_int;
+  int done;
+  int n_next;     // legal moves of the new side to move (in w.moves) or -1 if not generated
+  uint64_t key_next;  // position key of the new board ‖ new side to move
+};
+
+// make_move (chess_env.py:253-406).  hist: this game's position_history row.
+__device__ __forceinline__ StepOut step(WarpSmem& w, Game& g, int move, uint64_t* __restrict__ hist,
+                                        int hist_cap) {
+  const int lane = lane_id();
+  const int from = move / 90, to = move - from * 90;
+  const int captured = w.sq[to], moving = w.sq[from];  // :265-266
+  __syncwarp();
+  if (lane == 0) {
+    w.sq[to] = (int8_t)moving;
+    w.sq[from] = 0;
+    const int fr = from / 9, fc = from - fr * 9, tr = to / 9, tc = to - tr * 9;
+    w.rows[fr] &= ~(1u << fc);
+    w.cols[fc] &= ~(1u << fr);
+    if (moving != 0) {
+      w.rows[tr] |= (uint16_t)(1u << tc);
+      w.cols[tc] |= (uint16_t)(1u << tr);
+    } else {
+      w.rows[tr] &= ~(1u << tc);
+      w.cols[tc] &= ~(1u << tr);
+    }
+  }
+  __syncwarp();
+
+  if (moving == KING) g.red_king = to;  // :271-279
+  else if (moving == -KING) g.black_king = to;
+  if (captured == KING) g.red_king = -1;
+  else if (captured == -KING) g.black_king = -1;
+  g.no_capture = captured != 0 ? 0 : g.no_capture + 1;  // :282-285
+
+  StepOut o;
+  double reward = 0.0;
+  int is_int = 1, done = 0;
+  const int acap = captured < 0 ? -captured : captured;
+  if (acap == KING) {  // :292-297
+    g.winner = g.player;
+    reward = 100.0;
+    done = 1;
+    g.reason = XQ_REASON_KING_CAPTURE;
+  } else if (captured != 0) {  // :300-314
+    const double base = acap == ROOK ? 9.0 : acap == CANNON ? 4.5 : acap == KNIGHT ? 4.0
+                        : (acap == BISHOP || acap == ADVISOR) ? 2.0 : acap == PAWN ? 1.0 : 0.0;
+    reward = __dmul_rn(base, 2.0);
+    is_int = 0;
+    if (acap == ADVISOR || acap == BISHOP) reward = __dadd_rn(reward, 3.0);
+  }
+
+  const bool checking = in_check(w, g, -g.player);  // :317, geometry = mover
+  if (!done && checking) {                           // :318-327
+    if (g.cchecks == 0) { reward = __dadd_rn(reward, 15.0); is_int = 0; }
+    else if (g.cchecks == 1) { reward = __dadd_rn(reward, 10.0); is_int = 0; }
+    else if (g.cchecks == 2) { reward = __dadd_rn(reward, 5.0); is_int = 0; }
+    g.cchecks += 1;
+  } else {  // :328-335
+    g.cchecks = 0;
+    if (captured == 0 && !done) {
+      const int ek = g.player == 1 ? g.black_king : g.red_king;
+      const double pcg = position_change(moving < 0 ? -moving : moving, g.player, from, to, ek);
+      reward = __dadd_rn(reward, __dmul_rn(pcg, 0.01));
+      is_int = 0;
+    }
+  }
+
+  const uint64_t bkey = board_key(w);
+  if (g.hist_len < hist_cap) {  // :338, stored with the MOVER's side byte
+    if (lane == 0) hist[g.hist_len] = bkey ^ side_key(g.player);
+    g.hist_len += 1;
+  } else {
+    g.flags |= XQ_F_OVERFLOW;
+  }
+  g.check_bits = (g.check_bits << 1) | (checking ? 1u : 0u);  // :341
+  g.check_len += 1;
+
+  g.player = -g.player;  // :348-349
+  g.move_count += 1;
+  o.key_next = bkey ^ side_key(g.player);
+  o.n_next = -1;
+
+  if (!done) {  // :352-397
+    __syncwarp();
+    const int n_legal = movegen(w, g);
+    o.n_next = n_legal;
+    const bool chk_now = n_legal == 0 ? in_check(w, g, g.player) : false;
+    if (n_legal == 0 && chk_now) {  // :354, :614-628
+      done = 1; reward = 200.0; is_int = 1;
+      g.winner = -g.player;
+      g.reason = XQ_REASON_CHECKMATE;
+    } else {
+      int cnt = 0;  // :362, :598-605 — query uses the NEW side byte (quirk A.7)
+      for (int i = lane; i < g.hist_len; i += 32) cnt += hist[i] == o.key_next;
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) cnt += __shfl_xor_sync(kFull, cnt, s);
+      if (cnt >= 3) {
+        done = 1; reward = 0.0; is_int = 1;
+        g.winner = 0;
+        g.reason = XQ_REASON_REPETITION;
+      } else if (g.no_capture >= 100) {  // :369, :612
+        done = 1; reward = 0.0; is_int = 1;
+        g.winner = 0;
+        g.reason = XQ_REASON_FIFTY;
+      } else if (n_legal == 0) {  // :376, :630-644
+        done = 1; reward = 100.0; is_int = 1;
+        g.winner = -g.player;
+        g.reason = XQ_REASON_STALEMATE;
+      } else if (g.check_len >= 12 && __popc(g.check_bits & 0xFFFu) >= 10) {  // :384, :646-662
+        done = 1; reward = -10.0; is_int = 1;
+        g.winner = -g.player;
+        g.reason = XQ_REASON_PERPETUAL_CHECK;
+      }  // :392 perpetual chase never fires (:674)
+    }
+  }
+  if (!done && g.move_count >= 70) {  // :400-404
+    done = 1; reward = -2.0; is_int = 1;
+    g.winner = 0;
+    g.reason = XQ_REASON_MOVE_CAP;
+  }
+  if (done) g.done = 1;
+  o.reward = reward;
+  o.is_int = is_int;
+  o.done = done;
+  return o;
+}
+
+__device__ __forceinline__ uint8_t step_flags(const Game& g, const StepOut& o) {
+  return (uint8_t)((o.done & 1) | ((o.is_int & 1) << 1) | (((g.winner + 1) & 3) << 2) |
+                   ((g.reason & 15) << 4));
+}
+
+// ---- philox4x32-10 pick ------------------------------------------------------
+__device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                           uint32_t k0, uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+    const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+    c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// Index into w.moves[0..n) chosen by the shared pick rule.
+__device__ __forceinline__ int pick_index(const WarpSmem& w, int n, uint64_t seed, uint32_t game_id,
+                                          uint32_t ply, int capture_bias) {
+  uint32_t x[4];
+  philox4x32(game_id, ply, 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), x);
+  if (capture_bias > 0 && (int)(x[1] & 0xFFu) < capture_bias) {
+    const int lane = lane_id();
+    unsigned masks[XQ_MAX_MOVES / 32];
+    int ncap = 0;
+#pragma unroll
+    for (int k = 0; k < XQ_MAX_MOVES / 32; ++k) {
+      const int i = k * 32 + lane;
+      const bool cap = i < n && w.sq[(int)w.moves[i] % 90] != 0;
+      masks[k] = __ballot_sync(kFull, cap);
+      ncap += __popc(masks[k]);
+    }
+    if (ncap > 0) {
+      int k = (int)(x[0] % (uint32_t)ncap);
+#pragma unroll
+      for (int r = 0; r < XQ_MAX_MOVES / 32; ++r) {
+        const int c = __popc(masks[r]);
+        if (k >= 0 && k < c) return r * 32 + (int)__fns(masks[r], 0, k + 1);
+        k -= c;
+      }
+    }
+  }
+  return (int)(x[0] % (uint32_t)n);
+}
+
+}  // namespace xq

@@ -1,0 +1,58 @@
+"""CPU: the C-ABI library builds, loads and exports exactly what include/xq_b200.h declares.
+No compute entry point is called here (there is no GPU in this container)."""
+import ctypes
+import os
+import re
+
+from conftest import ROOT
+
+
+def _declared():
+    hdr = open(os.path.join(ROOT, "include", "xq_b200.h"), encoding="utf-8").read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(xq_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_header_symbols_exported(built_lib):
+    names = _declared()
+    assert "xq_legal_moves" in names and "xq_step" in names and "xq_playout" in names
+    raw = ctypes.CDLL(os.path.join(ROOT, "chinesechessai_b200", "libxq_b200.so"))
+    for n in names:
+        assert hasattr(raw, n), f"{n} declared in xq_b200.h but not exported"
+
+
+def test_binding_table_matches_header(built_lib):
+    from chinesechessai_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == _declared()
+
+
+def test_abi_version_and_meta_layout(built_lib):
+    from chinesechessai_b200 import _lib
+    assert built_lib.xq_abi_version() == _lib.ABI_VERSION
+    assert _lib.META_DTYPE.itemsize == 32 and _lib.PLAYOUT_RESULT_DTYPE.itemsize == 40
+    assert _lib.META_DTYPE.fields["move_count"][1] == 8
+    assert _lib.META_DTYPE.fields["check_len"][1] == 28
+
+
+def test_fails_loudly_without_device(built_lib):
+    import pytest
+    import torch
+    from chinesechessai_b200 import _lib
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    assert built_lib.xq_device_count() < 0
+    with pytest.raises(_lib.XqError):
+        _lib.require_device()
+    from chinesechessai_b200.engine import BoardBatch
+    with pytest.raises(_lib.XqError):
+        BoardBatch(4)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "chinesechessai_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f), encoding="utf-8").read()
+                assert "oracle" not in src.replace("the oracle", "").replace("CPU oracle", ""), \
+                    f"{f} references oracle/"

@@ -1,0 +1,310 @@
+"""GPU parity tests: CUDA rules engine (through the C ABI) vs the reference goldens and the
+C oracle.  Bar: bit-exact move lists (order included), boards, rewards (float64 bit patterns),
+flags, caches and outcomes."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SEED = 0x5EED
+
+
+@pytest.fixture(scope="module")
+def eng(built_lib):
+    import torch
+    from chinesechessai_b200 import engine
+    assert torch.cuda.is_available()
+    return engine
+
+
+def _meta(n, **kw):
+    from chinesechessai_b200._lib import META_DTYPE
+    m = np.zeros(n, META_DTYPE)
+    m["player"] = 1
+    m["winner"] = 2
+    m["red_king"] = -1
+    m["black_king"] = -1
+    for k, v in kw.items():
+        m[k] = v
+    return m
+
+
+def _positions_batch(eng, P):
+    n = len(P["player"])
+    L = P["ck_len"].astype(np.int64)
+    m = _meta(n, player=P["player"], red_king=P["red"], black_king=P["black"],
+              move_count=P["mc"], no_capture=P["ncap"], consecutive_checks=P["cc"],
+              check_len=L, check_bits=P["ck_bits"])
+    bb = eng.BoardBatch(n)
+    bb.set_state(P["board"], m)
+    return bb
+
+
+def test_initial_position(eng, golden):
+    bb = eng.BoardBatch(3)
+    mv, n = bb.legal_moves()
+    assert n.cpu().tolist() == [44, 44, 44]
+    assert mv[1, :44].cpu().tolist() == golden.kats["initial_legal_moves"]
+    m = bb.meta_host()
+    assert m["player"].tolist() == [1, 1, 1] and m["red_king"].tolist() == [85] * 3
+    assert m["black_king"].tolist() == [4] * 3 and m["winner"].tolist() == [2] * 3
+
+
+def test_legal_moves_arbitrary_positions(eng, golden):
+    import torch
+    P = golden.positions
+    bb = _positions_batch(eng, P)
+    chk = torch.zeros(bb.n, dtype=torch.uint8, device=bb.device)
+    mv, n = bb.legal_moves(in_check=chk)
+    mv, n, chk = mv.cpu().numpy(), n.cpu().numpy(), chk.cpu().numpy()
+    off = P["legal_offset"]
+    bad = [i for i in range(bb.n)
+           if n[i] != off[i + 1] - off[i] or not np.array_equal(mv[i, :n[i]], P["legal"][off[i]:off[i + 1]])]
+    assert not bad, f"{len(bad)} positions differ, first {bad[:5]}"
+    assert np.array_equal(chk, P["chk_self"])
+
+
+def test_step_arbitrary_positions(eng, golden):
+    import torch
+    P = golden.positions
+    bb = _positions_batch(eng, P)
+    move = torch.from_numpy(P["move"].astype(np.int16)).to(bb.device)
+    reward, flags = bb.step(move)
+    sel = P["move"] >= 0
+    f = eng.decode_step_flags(flags.cpu().numpy())
+    assert np.array_equal(reward.cpu().numpy().view(np.uint64)[sel], P["reward"].view(np.uint64)[sel])
+    assert np.array_equal(f["done"][sel], P["done"].astype(bool)[sel])
+    assert np.array_equal(f["reward_is_int"][sel], P["is_int"].astype(bool)[sel])
+    assert np.array_equal(f["winner"][sel], P["winner"][sel])
+    assert np.array_equal(f["reason"][sel], P["reason"][sel])
+    m = bb.meta_host()
+    assert np.array_equal(bb.boards_host()[sel], P["board_after"][sel])
+    assert np.array_equal(m["red_king"][sel], P["red_after"][sel])
+    assert np.array_equal(m["black_king"][sel], P["black_after"][sel])
+    assert np.array_equal(m["consecutive_checks"][sel], P["cc_after"][sel])
+    assert np.array_equal(m["no_capture"][sel], P["ncap_after"][sel])
+    assert np.array_equal((m["check_bits"] & 1)[sel], P["check_flag"][sel])
+    assert np.array_equal(m["winner"][sel], P["winner"][sel])
+    # frozen games (move < 0) are untouched
+    assert np.array_equal(bb.boards_host()[~sel], P["board"][~sel])
+
+
+LINES = ["double_cannon_mate", "knight_shuffle", "quiet_knight", "pawn_line", "cannon_takes_king",
+         "perpetual_check", "odd_cycle_repetition", "fifty_move"]
+
+
+@pytest.mark.parametrize("name", LINES)
+def test_kat_lines(eng, golden, name):
+    import torch
+    k = golden.kats[name]
+    st = k["start"]
+    ck = st["check_history"]
+    bits = sum((1 << i) for i, v in enumerate(ck[::-1]) if v)
+    m = _meta(1, player=st["player"], red_king=st["red"], black_king=st["black"],
+              no_capture=98 if name == "fifty_move" else 0, move_count=10 if name == "fifty_move" else 0,
+              check_len=len(ck), check_bits=bits)
+    bb = eng.BoardBatch(1)
+    bb.set_state(np.array(st["board"], np.int8).reshape(1, 90), m)
+    for i in range(k["plies"]):
+        mv = torch.tensor([eng.pack_move(k["moves"][i])], dtype=torch.int16, device=bb.device)
+        reward, flags = bb.step(mv)
+        f = eng.decode_step_flags(flags.cpu().numpy())
+        assert repr(float(reward[0])) == repr(k["rewards"][i]), i
+        assert bool(f["done"][0]) == k["dones"][i] and bool(f["reward_is_int"][0]) == k["reward_is_int"][i]
+    meta = bb.meta_host()[0]
+    want = 2 if k["winner"] is None else k["winner"]
+    assert meta["winner"] == want and meta["reason"] == k["reason"]
+    assert bb.boards_host()[0].tolist() == k["final_board"]
+    assert meta["consecutive_checks"] == k["consecutive_checks"]
+    assert len(set(bb.pos_hist_host()[0, :meta["hist_len"]].tolist())) == k["distinct_hashes"]
+
+
+def test_kat_positions(eng, golden):
+    for name, p in golden.kats["positions"].items():
+        bb = eng.BoardBatch(1)
+        bb.set_state(np.array(p["board"], np.int8).reshape(1, 90),
+                     _meta(1, player=p["player"], red_king=p["red"], black_king=p["black"]))
+        mv, n = bb.legal_moves()
+        assert mv[0, :int(n[0])].cpu().tolist() == p["legal"], name
+
+
+def _cmp_results(res, ref):
+    for f in ("plies", "winner", "reason", "max_legal", "digest", "final_hash"):
+        bad = np.nonzero(res[f] != ref[f])[0]
+        assert len(bad) == 0, (f, bad[:5], res[f][bad[:5]], ref[f][bad[:5]])
+    assert np.array_equal(res["reward_sum"].view(np.uint64), ref["reward_sum"].view(np.uint64))
+
+
+def test_fused_playout_vs_reference_goldens(eng, golden):
+    S = golden.playouts["summary"]
+    for bias in (0, 192):
+        sel = S[S["bias"] == bias]
+        bb = eng.BoardBatch(len(sel))
+        res = eng.results_host(bb.playout(SEED, 70, first_game_id=int(sel["game_id"][0]),
+                                          capture_bias=bias))
+        _cmp_results(res, sel)
+
+
+def test_fused_playout_traces_vs_reference_goldens(eng, golden):
+    G = golden.playouts
+    S = G["summary"]
+    po, mo = G["full_ply_offset"], G["full_move_offset"]
+    for bias in (0, 192):
+        idx = [k for k, gi in enumerate(G["full_game_index"]) if S["bias"][gi] == bias]
+        gids = [int(S["game_id"][G["full_game_index"][k]]) for k in idx]
+        assert gids == list(range(gids[0], gids[0] + len(gids)))
+        bb = eng.BoardBatch(len(idx))
+        res, tr = bb.playout(SEED, 70, first_game_id=gids[0], capture_bias=bias, trace=True)
+        res = eng.results_host(res)
+        tr = {k: v.cpu().numpy() for k, v in tr.items()}
+        for j, k in enumerate(idx):
+            a, b = int(po[k]), int(po[k + 1])
+            p = b - a
+            assert res["plies"][j] == p
+            assert np.array_equal(tr["n"][j, :p], G["full_n"][a:b])
+            assert np.array_equal(tr["pick"][j, :p], G["full_pick"][a:b])
+            assert np.array_equal(tr["reward"][j, :p].view(np.uint64), G["full_reward"][a:b].view(np.uint64))
+            assert np.array_equal(tr["flags"][j, :p], G["full_flags"][a:b])
+            assert np.array_equal(tr["boards"][j, :p], G["full_boards"][a:b])
+            for q in range(p):
+                assert np.array_equal(tr["moves"][j, q, :tr["n"][j, q]],
+                                      G["full_moves"][mo[a + q]:mo[a + q + 1]]), (k, q)
+        # final king caches of the full games
+        kings = G["full_kings"]
+        meta = bb.meta_host()
+        for j, k in enumerate(idx):
+            last = int(po[k + 1]) - 1
+            assert (meta["red_king"][j], meta["black_king"][j]) == tuple(kings[last, :2])
+
+
+@pytest.mark.parametrize("bias,first", [(0, 5000), (128, 700000), (240, 31)])
+def test_fused_playout_vs_oracle(eng, xo, bias, first):
+    n = 4096
+    bb = eng.BoardBatch(n)
+    res = eng.results_host(bb.playout(SEED + bias, 70, first_game_id=first, capture_bias=bias))
+    total, ref = xo.playout_many(n, SEED + bias, first, 70, bias, n_threads=8)
+    _cmp_results(res, ref)
+    assert int(res["plies"].sum()) == total
+
+
+def test_step_per_launch_equals_fused(eng):
+    import torch
+    n, bias = 2048, 96
+    fused = eng.BoardBatch(n)
+    rf = eng.results_host(fused.playout(SEED, 70, capture_bias=bias))
+    bb = eng.BoardBatch(n)
+    plies = torch.zeros(n, dtype=torch.int32, device=bb.device)
+    rsum = torch.zeros(n, dtype=torch.float64, device=bb.device)
+    bb.legal_moves()
+    for ply in range(70):
+        mv = bb.pick(SEED, ply, capture_bias=bias)
+        plies += (mv >= 0).to(torch.int32)
+        reward, flags = bb.step(mv, want_next=True)
+        rsum += torch.where(mv >= 0, reward, torch.zeros_like(reward))
+    assert np.array_equal(plies.cpu().numpy(), rf["plies"])
+    assert np.array_equal(rsum.cpu().numpy().view(np.uint64), rf["reward_sum"].view(np.uint64))
+    assert np.array_equal(bb.boards_host(), fused.boards_host())
+    a, b = bb.meta_host(), fused.meta_host()
+    for f in a.dtype.names:
+        assert np.array_equal(a[f], b[f]), f
+    assert np.array_equal(bb.pos_hist_host(), fused.pos_hist_host())
+    # API-faithful variant: separate legal_moves launch instead of step's next list
+    cc = eng.BoardBatch(256)
+    cf = eng.BoardBatch(256)
+    cf.playout(SEED, 70)
+    for ply in range(70):
+        cc.legal_moves()
+        cc.step(cc.pick(SEED, ply))
+    assert np.array_equal(cc.boards_host(), cf.boards_host())
+
+
+def test_full_size_properties(eng, xo):
+    """cfg 2 size (65,536 boards x 70 plies): determinism, shard invariance, and the oracle's
+    digests on a strided sample of the same game ids."""
+    n = 65536
+    bb = eng.BoardBatch(n)
+    r1 = eng.results_host(bb.playout(SEED, 70))
+    bb.reset()
+    bb.pos_hist.zero_()
+    r2 = eng.results_host(bb.playout(SEED, 70))
+    assert np.array_equal(r1, r2)
+    assert 4_300_000 < int(r1["plies"].sum()) <= 70 * n
+    assert int(bb.meta_host()["flags"].max()) == 0
+    # sharding: a rank that owns games [a, b) reproduces the slice of the full run
+    a, b = 40000, 41024
+    sh = eng.BoardBatch(b - a)
+    rs = eng.results_host(sh.playout(SEED, 70, first_game_id=a))
+    assert np.array_equal(rs, r1[a:b])
+    # oracle on every 64th game
+    ids = np.arange(0, n, 64)
+    for chunk in np.array_split(ids, 8):
+        for g in chunk[:16]:
+            _, ref = xo.playout_many(1, SEED, int(g), 70, 0, 1)
+            for f in ("plies", "winner", "reason", "digest", "final_hash"):
+                assert r1[f][g] == ref[f][0], (g, f)
+    # checksum of checksums: order-independent fold equals the fold of the oracle's over a block
+    _, ref = xo.playout_many(2048, SEED, 0, 70, 0, 8)
+    assert np.bitwise_xor.reduce(r1["digest"][:2048]) == np.bitwise_xor.reduce(ref["digest"])
+
+
+def test_playout_host_e2e(eng):
+    from chinesechessai_b200._lib import BOARD_STRIDE
+    n = 1024
+    bb = eng.BoardBatch(n)
+    boards = np.ascontiguousarray(bb.board.cpu().numpy())
+    meta = np.ascontiguousarray(bb.meta_host())
+    assert boards.shape == (n, BOARD_STRIDE)
+    rd = eng.results_host(bb.playout(SEED, 70, capture_bias=64))
+    rh = eng.playout_host(boards, meta, SEED, 70, capture_bias=64)
+    assert np.array_equal(rd, rh)
+    assert np.array_equal(boards, bb.board.cpu().numpy())
+    assert np.array_equal(meta, bb.meta_host())
+
+
+def test_ragged_and_empty(eng):
+    import torch
+    bb = eng.BoardBatch(0)
+    bb.legal_moves()
+    bb.playout(SEED, 70)
+    for n in (1, 7, 9, 33):
+        b = eng.BoardBatch(n)
+        r = eng.results_host(b.playout(SEED, 70))
+        assert len(r) == n and (r["plies"] > 0).all()
+    # max_plies = 0 leaves the state untouched
+    b = eng.BoardBatch(4)
+    r = eng.results_host(b.playout(SEED, 0))
+    assert r["plies"].tolist() == [0] * 4 and b.meta_host()["move_count"].tolist() == [0] * 4
+    # history capacity overflow is flagged, not silent
+    b = eng.BoardBatch(2, hist_cap=8)
+    b.playout(SEED, 20)
+    assert (b.meta_host()["flags"] & 1).all()
+    # argument errors come back as codes + message, never a crash
+    from chinesechessai_b200 import _lib
+    rc = b.lib.xq_legal_moves(None, None, None, None, None, 1, None)
+    assert rc == -1
+    with pytest.raises(_lib.XqError, match="xq_legal_moves"):
+        _lib.check(rc)
+
+
+def test_encode_planes_and_priors(eng, xo):
+    import torch
+    n = 512
+    bb = eng.BoardBatch(n)
+    bb.playout(SEED, 23, capture_bias=100)
+    boards, meta = bb.boards_host(), bb.meta_host()
+    pl = bb.meta[:, 0].view(torch.int8)
+    planes = eng.encode_planes(bb.board, pl).cpu().numpy()
+    for i in range(0, n, 7):
+        assert np.array_equal(planes[i], xo.encode_board(boards[i], int(meta["player"][i]))), i
+    pb = eng.encode_planes(bb.board, pl, dtype=torch.bfloat16).float().cpu().numpy()
+    assert np.array_equal(pb, planes)
+    mv, nm = bb.legal_moves()
+    logits = torch.randn(n, 8100, device=bb.device) * 3
+    pri = eng.policy_priors(logits, mv, nm).cpu().numpy()
+    lg, mvh, nmh = logits.cpu().numpy(), mv.cpu().numpy(), nm.cpu().numpy()
+    for i in range(0, n, 5):
+        k = int(nmh[i])
+        ref = xo.logits_to_priors(lg[i], mvh[i, :k])
+        np.testing.assert_allclose(pri[i, :k], ref, rtol=2e-6, atol=1e-9)  # float32 softmax, B.5
+        assert (pri[i, k:] == 0).all() and abs(pri[i].sum() - 1) < 1e-5
+        assert int(np.argmax(pri[i, :k])) == int(np.argmax(ref))
