@@ -11,12 +11,66 @@
 // bit masks with the candidate applied as an override — no board copies.
 #pragma once
 
-#include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "../../include/xq_b200.h"
 
+// Per-lane logic (attack test, suicide filter, candidate generation, reward
+// arithmetic) is XQ_HD so that tests/host_mirror can compile exactly this code
+// with g++ and fuzz it on the CPU; warp-collective code is CUDA-only.
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+#define XQ_HD __host__ __device__ __forceinline__
+#define XQ_ALIGN16 __align__(16)
+#else
+#include <algorithm>
+#include <cstdlib>
+#define XQ_HD inline
+#define XQ_ALIGN16 alignas(16)
+#endif
+
 namespace xq {
+
+XQ_HD int xq_ffs(unsigned x) {
+#if defined(__CUDA_ARCH__)
+  return __ffs((int)x);
+#else
+  return __builtin_ffs((int)x);
+#endif
+}
+XQ_HD int xq_clz(unsigned x) {
+#if defined(__CUDA_ARCH__)
+  return __clz((int)x);
+#else
+  return x ? __builtin_clz(x) : 32;
+#endif
+}
+XQ_HD unsigned xq_brev(unsigned x) {
+#if defined(__CUDA_ARCH__)
+  return __brev(x);
+#else
+  unsigned r = 0;
+  for (int i = 0; i < 32; ++i) r |= ((x >> i) & 1u) << (31 - i);
+  return r;
+#endif
+}
+XQ_HD double xq_dadd(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return xq_dadd(a, b);
+#else
+  return a + b;
+#endif
+}
+XQ_HD double xq_dmul(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return xq_dmul(a, b);
+#else
+  return a * b;
+#endif
+}
+XQ_HD int xq_min(int a, int b) { return a < b ? a : b; }
+XQ_HD int xq_max(int a, int b) { return a > b ? a : b; }
+XQ_HD int xq_abs(int a) { return a < 0 ? -a : a; }
 
 constexpr int kWarpsPerCta = 8;
 constexpr unsigned kFull = 0xffffffffu;
@@ -24,7 +78,7 @@ constexpr unsigned kFull = 0xffffffffu;
 enum : int { KING = 1, ADVISOR = 2, BISHOP = 3, KNIGHT = 4, ROOK = 5, CANNON = 6, PAWN = 7 };
 
 // Per-warp shared-memory slab (1024 B).
-struct __align__(16) WarpSmem {
+struct XQ_ALIGN16 WarpSmem {
   int8_t sq[XQ_BOARD_STRIDE];  // board, row-major r*9+c (chess_env.py:17)
   uint16_t rows[16];           // rows[r] bit c = square (r,c) occupied
   uint16_t cols[16];           // cols[c] bit r = square (r,c) occupied
@@ -42,14 +96,16 @@ struct Game {
   unsigned check_bits;
 };
 
-__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
-__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+XQ_HD uint64_t mix64(uint64_t x) {
   x += 0x9E3779B97F4A7C15ULL;
   x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
   x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
   return x ^ (x >> 31);
 }
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
 __device__ __forceinline__ uint64_t warp_xor64(uint64_t v) {
 #pragma unroll
@@ -62,9 +118,13 @@ __device__ __forceinline__ uint64_t warp_add64(uint64_t v) {
   return v;
 }
 
-__device__ __forceinline__ uint64_t side_key(int player) {
+#endif  // __CUDACC__
+
+XQ_HD uint64_t side_key(int player) {
   return mix64(0x7000ULL + (player == 1 ? 0u : 1u));  // chess_env.py:503
 }
+
+#if defined(__CUDACC__)
 
 // Position key without the side byte: XOR of per-(piece,square) keys, computed
 // lane-parallel (3 squares per lane).  _get_position_hash, chess_env.py:497-504.
@@ -152,13 +212,15 @@ __device__ __forceinline__ void build_masks(WarpSmem& w) {
   __syncwarp();
 }
 
+#endif  // __CUDACC__
+
 // ---- attack test -----------------------------------------------------------
 // Is square K a pseudo-target of any piece of sign `es` (the attackers), with
 // K/A/B/P geometry taken from side `geo` (chess_env.py:506-548 — the reference
 // regenerates attackers' moves with self.current_player's geometry, quirk A.3)?
 // The candidate (from,to,mover) is applied as an override (from<0: none).
 // `exotic` enables the K/A/B probes (warp-uniform hint; always safe to pass true).
-__device__ __forceinline__ bool attacked(const WarpSmem& w, int K, int es, int geo, int from,
+XQ_HD bool attacked(const WarpSmem& w, int K, int es, int geo, int from,
                                          int to, int mover, bool exotic, unsigned* colm_out) {
   const int kr = K / 9, kc = K - kr * 9;
   unsigned rowm = w.rows[kr], colm = w.cols[kc];
@@ -181,41 +243,41 @@ __device__ __forceinline__ bool attacked(const WarpSmem& w, int K, int es, int g
   {  // (0,+1)
     unsigned a = rowm >> (kc + 1);
     if (a) {
-      int d1 = __ffs(a), q = pc(K + d1);
+      int d1 = xq_ffs(a), q = pc(K + d1);
       hit |= (q == rook) | (q == cannon && !kocc) |
              (d1 == 1 && ((q == pawn && side_ok) | (q == king && in_pal)));
       unsigned a2 = a & (a - 1);
-      if (kocc && a2) hit |= pc(K + __ffs(a2)) == cannon;
+      if (kocc && a2) hit |= pc(K + xq_ffs(a2)) == cannon;
     }
   }
   {  // (0,-1)
     unsigned b = rowm & ((1u << kc) - 1u);
     if (b) {
-      int hb = 31 - __clz(b), q = pc(kr * 9 + hb);
+      int hb = 31 - xq_clz(b), q = pc(kr * 9 + hb);
       hit |= (q == rook) | (q == cannon && !kocc) |
              (kc - hb == 1 && ((q == pawn && side_ok) | (q == king && in_pal)));
       unsigned b2 = b & ~(1u << hb);
-      if (kocc && b2) hit |= pc(kr * 9 + 31 - __clz(b2)) == cannon;
+      if (kocc && b2) hit |= pc(kr * 9 + 31 - xq_clz(b2)) == cannon;
     }
   }
   {  // (+1,0): a pawn below K attacks it iff pawns move toward smaller rows (geo==1, :241)
     unsigned a = colm >> (kr + 1);
     if (a) {
-      int d1 = __ffs(a), q = pc(K + 9 * d1);
+      int d1 = xq_ffs(a), q = pc(K + 9 * d1);
       hit |= (q == rook) | (q == cannon && !kocc) |
              (d1 == 1 && ((q == pawn && geo == 1) | (q == king && in_pal)));
       unsigned a2 = a & (a - 1);
-      if (kocc && a2) hit |= pc(K + 9 * __ffs(a2)) == cannon;
+      if (kocc && a2) hit |= pc(K + 9 * xq_ffs(a2)) == cannon;
     }
   }
   {  // (-1,0)
     unsigned b = colm & ((1u << kr) - 1u);
     if (b) {
-      int hb = 31 - __clz(b), q = pc(hb * 9 + kc);
+      int hb = 31 - xq_clz(b), q = pc(hb * 9 + kc);
       hit |= (q == rook) | (q == cannon && !kocc) |
              (kr - hb == 1 && ((q == pawn && geo == -1) | (q == king && in_pal)));
       unsigned b2 = b & ~(1u << hb);
-      if (kocc && b2) hit |= pc((31 - __clz(b2)) * 9 + kc) == cannon;
+      if (kocc && b2) hit |= pc((31 - xq_clz(b2)) * 9 + kc) == cannon;
     }
   }
   // diagonal neighbours: knight legs (:182-197), bishop eyes (:161-174), advisors (:149-152)
@@ -241,7 +303,7 @@ __device__ __forceinline__ bool attacked(const WarpSmem& w, int K, int es, int g
 }
 
 // _is_in_check(player) on the staged board (chess_env.py:506-548).
-__device__ __forceinline__ bool in_check(const WarpSmem& w, const Game& g, int player) {
+XQ_HD bool in_check(const WarpSmem& w, const Game& g, int player) {
   const int K = player == 1 ? g.red_king : g.black_king;
   if (K < 0) return false;  // :517
   return attacked(w, K, -player, g.player, -1, -1, 0, true, nullptr);
@@ -250,7 +312,7 @@ __device__ __forceinline__ bool in_check(const WarpSmem& w, const Game& g, int p
 // _is_move_suicide (chess_env.py:431-464): own king attacked after the move
 // (geometry of the side to move) OR cached kings face each other (:466-495;
 // only the MOVING king's cache is refreshed, :448-451 — stale-cache quirk A.4).
-__device__ __forceinline__ bool suicide(const WarpSmem& w, const Game& g, int from, int to,
+XQ_HD bool suicide(const WarpSmem& w, const Game& g, int from, int to,
                                         bool exotic) {
   const int mover = w.sq[from];
   int red = g.red_king, black = g.black_king;
@@ -264,7 +326,7 @@ __device__ __forceinline__ bool suicide(const WarpSmem& w, const Game& g, int fr
     const int rr = red / 9, rc = red - rr * 9, br = black / 9, bc = black - br * 9;
     if (rc == bc) {
       if (K < 0) return bad;  // unreachable: both caches set implies K >= 0
-      const int lo = min(rr, br), hi = max(rr, br);
+      const int lo = xq_min(rr, br), hi = xq_max(rr, br);
       const unsigned between = ((1u << hi) - 1u) & ~((2u << lo) - 1u);
       bad |= (colm & between) == 0;
     }
@@ -273,8 +335,107 @@ __device__ __forceinline__ bool suicide(const WarpSmem& w, const Game& g, int fr
 }
 
 // ---- move generation --------------------------------------------------------
+// One work item of candidate generation: (own piece at `from`, direction d of
+// the reference's per-piece generator order).  Produces, in generator order,
+// `empties` quiet ray steps from+k*delta (rook/cannon only) followed by up to
+// two explicit targets e1, e2 (-1 = none).  Already filtered by on-board (:113)
+// and not-own-piece (:116).
+struct Item {
+  int from, empties, delta, e1, e2;
+};
+
+XQ_HD Item gen_item(const WarpSmem& w, int player, int from, int d) {
+  Item it{from, 0, 0, -1, -1};
+  const int p = w.sq[from];
+  const int pt = p < 0 ? -p : p;
+  const int r = from / 9, c = from - r * 9;
+  auto free_sq = [&](int s) -> bool { return (int)w.sq[s] * player <= 0; };  // :116
+  if (pt == ROOK || pt == CANNON) {  // :199-235, rays (0,1),(0,-1),(1,0),(-1,0)
+    const bool horiz = d < 2, fwd = (d & 1) == 0;
+    const int len = horiz ? 9 : 10;
+    unsigned m = horiz ? w.rows[r] : w.cols[c];
+    int x = horiz ? c : r;
+    if (!fwd) {  // mirror so the ray always runs toward higher bits
+      m = xq_brev(m) >> (32 - len);
+      x = len - 1 - x;
+    }
+    it.delta = (horiz ? 1 : 9) * (fwd ? 1 : -1);
+    const unsigned ahead = m >> (x + 1);
+    const int first = ahead ? xq_ffs(ahead) : 0;
+    it.empties = first ? first - 1 : len - 1 - x;
+    int hitd = first;
+    if (pt == CANNON) {
+      const unsigned a2 = ahead & (ahead - 1);
+      hitd = a2 ? xq_ffs(a2) : 0;
+    }
+    if (hitd) {
+      const int s = from + hitd * it.delta;
+      if (free_sq(s)) it.e1 = s;
+    }
+  } else if (pt == KNIGHT) {  // :178-197, offsets in pairs sharing a leg
+    const int lr = r + (d == 0 ? 1 : d == 1 ? -1 : 0), lc = c + (d == 2 ? 1 : d == 3 ? -1 : 0);
+    if (lr >= 0 && lr <= 9 && lc >= 0 && lc <= 8 && w.sq[lr * 9 + lc] == 0) {
+      int r1, c1, r2, c2;
+      if (d < 2) {
+        r1 = r2 = r + (d == 0 ? 2 : -2);
+        c1 = c + 1;
+        c2 = c - 1;
+      } else {
+        c1 = c2 = c + (d == 2 ? 2 : -2);
+        r1 = r + 1;
+        r2 = r - 1;
+      }
+      if (r1 >= 0 && r1 <= 9 && c1 >= 0 && c1 <= 8 && free_sq(r1 * 9 + c1)) it.e1 = r1 * 9 + c1;
+      if (r2 >= 0 && r2 <= 9 && c2 >= 0 && c2 <= 8 && free_sq(r2 * 9 + c2)) it.e2 = r2 * 9 + c2;
+    }
+  } else if (pt == KING || pt == ADVISOR) {  // :123-154, palace of the side to move
+    int dr, dc;
+    if (pt == KING) {
+      dr = d == 2 ? 1 : d == 3 ? -1 : 0;
+      dc = d == 0 ? 1 : d == 1 ? -1 : 0;
+    } else {
+      dr = d < 2 ? 1 : -1;
+      dc = (d & 1) ? -1 : 1;
+    }
+    const int nr = r + dr, nc = c + dc;
+    const bool pal = nc >= 3 && nc <= 5 && (player == 1 ? (nr >= 7 && nr <= 9) : (nr >= 0 && nr <= 2));
+    if (pal && free_sq(nr * 9 + nc)) it.e1 = nr * 9 + nc;
+  } else if (pt == BISHOP) {  // :156-176 (black river = 4: rows 0..3 only)
+    const int dr = d < 2 ? 2 : -2, dc = (d & 1) ? -2 : 2;
+    const int nr = r + dr, nc = c + dc;
+    if (nr >= 0 && nr <= 9 && nc >= 0 && nc <= 8 && (player == 1 ? nr >= 5 : nr <= 3) &&
+        w.sq[(r + dr / 2) * 9 + c + dc / 2] == 0 && free_sq(nr * 9 + nc))
+      it.e1 = nr * 9 + nc;
+  } else if (pt == PAWN) {  // :237-251
+    const bool crossed = player == 1 ? r < 5 : r >= 5;
+    int nr = r, nc = c;
+    bool ok = true;
+    if (d == 0) nr = r - player;
+    else if (d == 1) { nc = c - 1; ok = crossed; }
+    else if (d == 2) { nc = c + 1; ok = crossed; }
+    else ok = false;
+    if (ok && nr >= 0 && nr <= 9 && nc >= 0 && nc <= 8 && free_sq(nr * 9 + nc)) it.e1 = nr * 9 + nc;
+  }
+  return it;
+}
+
+// Warp-uniform hint for suicide(): can an enemy K/A/B ever matter?  They only
+// reach squares within two rows of themselves and a king steps one row at most,
+// so in a regular position (exactly one own king piece, standing on its cached
+// square) they are irrelevant unless one stands within 3 rows of that king.
+// Poked boards (several kings, stale or missing cache, :448-451 re-creates the
+// cache wherever a king piece moves) always take the full test.
+XQ_HD bool exotic_piece(int p, int s, int player, int own_king) {
+  const int ap = p < 0 ? -p : p;
+  return (p * player < 0) && ap <= BISHOP && xq_abs(s / 9 - own_king / 9) <= 3;
+}
+XQ_HD bool regular_king(const WarpSmem& w, int player, int own_king, int n_own_kings) {
+  return n_own_kings == 1 && own_king >= 0 && w.sq[own_king] == player * KING;
+}
+
+#if defined(__CUDACC__)
 // get_legal_moves (chess_env.py:76-121).  Fills w.moves in the reference's
-// order and returns the count; *ncand_out = pseudo-legal candidates tested.
+// order and returns the count.
 // Phase A: work item = (own piece, direction) -> candidate list via an ordered
 // warp scan.  Phase B: 32 candidates per round through suicide(), ordered
 // compaction with ballot/popc.
@@ -285,8 +446,7 @@ __device__ __forceinline__ int movegen(WarpSmem& w, Game& g) {
 
   // own-piece list in row-major order (:82-87) + "exotic" hint
   const int ownK = player == 1 ? g.red_king : g.black_king;
-  const int okr = ownK >= 0 ? ownK / 9 : -100;
-  int n_own = 0;
+  int n_own = 0, n_kings = 0;
   bool ex = false;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
@@ -296,10 +456,10 @@ __device__ __forceinline__ int movegen(WarpSmem& w, Game& g) {
     const unsigned b = __ballot_sync(kFull, mine);
     if (mine) w.own[n_own + __popc(b & lt)] = (uint8_t)s;
     n_own += __popc(b);
-    const int ap = p < 0 ? -p : p;
-    ex |= (p * player < 0) && ap <= BISHOP && abs(s / 9 - okr) <= 3;
+    n_kings += __popc(__ballot_sync(kFull, p == player * KING));
+    ex |= exotic_piece(p, s, player, ownK < 0 ? 0 : ownK);
   }
-  const bool exotic = __any_sync(kFull, ex);
+  const bool exotic = !regular_king(w, player, ownK, n_kings) || __any_sync(kFull, ex);
   __syncwarp();
 
   // Phase A
@@ -307,82 +467,9 @@ __device__ __forceinline__ int movegen(WarpSmem& w, Game& g) {
   const int n_items = n_own * 4;
   for (int base = 0; base < n_items; base += 32) {
     const int t = base + lane;
-    int empties = 0, delta = 0, e1 = -1, e2 = -1, from = 0;
-    if (t < n_items) {
-      from = w.own[t >> 2];
-      const int d = t & 3;
-      const int p = w.sq[from];
-      const int pt = p < 0 ? -p : p;
-      const int r = from / 9, c = from - r * 9;
-      auto free_sq = [&](int s) -> bool { return (int)w.sq[s] * player <= 0; };  // :116
-      if (pt == ROOK || pt == CANNON) {  // :199-235, rays (0,1),(0,-1),(1,0),(-1,0)
-        const bool horiz = d < 2, fwd = (d & 1) == 0;
-        const int len = horiz ? 9 : 10;
-        unsigned m = horiz ? w.rows[r] : w.cols[c];
-        int x = horiz ? c : r;
-        if (!fwd) {  // mirror so the ray always runs toward higher bits
-          m = __brev(m) >> (32 - len);
-          x = len - 1 - x;
-        }
-        delta = (horiz ? 1 : 9) * (fwd ? 1 : -1);
-        const unsigned ahead = m >> (x + 1);
-        const int first = ahead ? __ffs(ahead) : 0;
-        empties = first ? first - 1 : len - 1 - x;
-        int hitd = first;
-        if (pt == CANNON) {
-          const unsigned a2 = ahead & (ahead - 1);
-          hitd = a2 ? __ffs(a2) : 0;
-        }
-        if (hitd) {
-          const int s = from + hitd * delta;
-          if (free_sq(s)) e1 = s;
-        }
-      } else if (pt == KNIGHT) {  // :178-197, offsets in pairs sharing a leg
-        const int lr = r + (d == 0 ? 1 : d == 1 ? -1 : 0), lc = c + (d == 2 ? 1 : d == 3 ? -1 : 0);
-        if (lr >= 0 && lr <= 9 && lc >= 0 && lc <= 8 && w.sq[lr * 9 + lc] == 0) {
-          int r1, c1, r2, c2;
-          if (d < 2) {
-            r1 = r2 = r + (d == 0 ? 2 : -2);
-            c1 = c + 1;
-            c2 = c - 1;
-          } else {
-            c1 = c2 = c + (d == 2 ? 2 : -2);
-            r1 = r + 1;
-            r2 = r - 1;
-          }
-          if (r1 >= 0 && r1 <= 9 && c1 >= 0 && c1 <= 8 && free_sq(r1 * 9 + c1)) e1 = r1 * 9 + c1;
-          if (r2 >= 0 && r2 <= 9 && c2 >= 0 && c2 <= 8 && free_sq(r2 * 9 + c2)) e2 = r2 * 9 + c2;
-        }
-      } else if (pt == KING || pt == ADVISOR) {  // :123-154, palace of the side to move
-        int dr, dc;
-        if (pt == KING) {
-          dr = d == 2 ? 1 : d == 3 ? -1 : 0;
-          dc = d == 0 ? 1 : d == 1 ? -1 : 0;
-        } else {
-          dr = d < 2 ? 1 : -1;
-          dc = (d & 1) ? -1 : 1;
-        }
-        const int nr = r + dr, nc = c + dc;
-        const bool pal = nc >= 3 && nc <= 5 && (player == 1 ? (nr >= 7 && nr <= 9) : (nr >= 0 && nr <= 2));
-        if (pal && free_sq(nr * 9 + nc)) e1 = nr * 9 + nc;
-      } else if (pt == BISHOP) {  // :156-176
-        const int dr = d < 2 ? 2 : -2, dc = (d & 1) ? -2 : 2;
-        const int nr = r + dr, nc = c + dc;
-        if (nr >= 0 && nr <= 9 && nc >= 0 && nc <= 8 && (player == 1 ? nr >= 5 : nr <= 3) &&
-            w.sq[(r + dr / 2) * 9 + c + dc / 2] == 0 && free_sq(nr * 9 + nc))
-          e1 = nr * 9 + nc;
-      } else if (pt == PAWN) {  // :237-251
-        const bool crossed = player == 1 ? r < 5 : r >= 5;
-        int nr = r, nc = c;
-        bool ok = true;
-        if (d == 0) nr = r - player;
-        else if (d == 1) { nc = c - 1; ok = crossed; }
-        else if (d == 2) { nc = c + 1; ok = crossed; }
-        else ok = false;
-        if (ok && nr >= 0 && nr <= 9 && nc >= 0 && nc <= 8 && free_sq(nr * 9 + nc)) e1 = nr * 9 + nc;
-      }
-    }
-    const int cnt = empties + (e1 >= 0) + (e2 >= 0);
+    Item it{0, 0, 0, -1, -1};
+    if (t < n_items) it = gen_item(w, player, w.own[t >> 2], t & 3);
+    const int cnt = it.empties + (it.e1 >= 0) + (it.e2 >= 0);
     int incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -396,12 +483,12 @@ __device__ __forceinline__ int movegen(WarpSmem& w, Game& g) {
     }
     int off = ncand + incl - cnt;
     ncand += total;
-    for (int k = 1; k <= empties; ++k, ++off) {
-      w.cf[off] = (uint8_t)from;
-      w.ct[off] = (uint8_t)(from + k * delta);
+    for (int k = 1; k <= it.empties; ++k, ++off) {
+      w.cf[off] = (uint8_t)it.from;
+      w.ct[off] = (uint8_t)(it.from + k * it.delta);
     }
-    if (e1 >= 0) { w.cf[off] = (uint8_t)from; w.ct[off] = (uint8_t)e1; ++off; }
-    if (e2 >= 0) { w.cf[off] = (uint8_t)from; w.ct[off] = (uint8_t)e2; }
+    if (it.e1 >= 0) { w.cf[off] = (uint8_t)it.from; w.ct[off] = (uint8_t)it.e1; ++off; }
+    if (it.e2 >= 0) { w.cf[off] = (uint8_t)it.from; w.ct[off] = (uint8_t)it.e2; }
   }
   __syncwarp();
 
@@ -428,32 +515,34 @@ __device__ __forceinline__ int movegen(WarpSmem& w, Game& g) {
   __syncwarp();
   return n_legal;
 }
+#endif  // __CUDACC__
 
 // ---- step -------------------------------------------------------------------
 // _evaluate_position_change (chess_env.py:683-737); before the side switch.
-__device__ __forceinline__ double position_change(int type, int player, int from, int to,
+XQ_HD double position_change(int type, int player, int from, int to,
                                                   int enemy_king) {
   const int fr = from / 9, fc = from - fr * 9, tr = to / 9, tc = to - tr * 9;
   double score = 0.0;
   const int advance = player == 1 ? fr - tr : tr - fr;
   if (advance > 0) {
-    if (type == PAWN) score = __dadd_rn(score, __dmul_rn((double)advance, 2.0));
-    else if (type == ROOK || type == CANNON) score = __dadd_rn(score, __dmul_rn((double)advance, 1.5));
-    else if (type == KNIGHT) score = __dadd_rn(score, (double)advance);
+    if (type == PAWN) score = xq_dadd(score, xq_dmul((double)advance, 2.0));
+    else if (type == ROOK || type == CANNON) score = xq_dadd(score, xq_dmul((double)advance, 1.5));
+    else if (type == KNIGHT) score = xq_dadd(score, (double)advance);
   }
   if (tc >= 3 && tc <= 5) {
-    score = __dadd_rn(score, 1.5);
-    if (tr >= 3 && tr <= 6) score = __dadd_rn(score, 1.0);
+    score = xq_dadd(score, 1.5);
+    if (tr >= 3 && tr <= 6) score = xq_dadd(score, 1.0);
   }
-  if (type == PAWN && (player == 1 ? tr < 5 : tr >= 5)) score = __dadd_rn(score, 3.0);
+  if (type == PAWN && (player == 1 ? tr < 5 : tr >= 5)) score = xq_dadd(score, 3.0);
   if (enemy_king >= 0) {
     const int kr = enemy_king / 9, kc = enemy_king - kr * 9;
-    const int od = abs(fr - kr) + abs(fc - kc), nd = abs(tr - kr) + abs(tc - kc);
-    if (nd < od) score = __dadd_rn(score, __dmul_rn((double)(od - nd), 0.5));
+    const int od = xq_abs(fr - kr) + xq_abs(fc - kc), nd = xq_abs(tr - kr) + xq_abs(tc - kc);
+    if (nd < od) score = xq_dadd(score, xq_dmul((double)(od - nd), 0.5));
   }
   return score;
 }
 
+#if defined(__CUDACC__)
 struct StepOut {
   double reward;  // valid on every lane (warp-uniform inputs)
   int is_int;
@@ -503,23 +592,23 @@ __device__ __forceinline__ StepOut step(WarpSmem& w, Game& g, int move, uint64_t
   } else if (captured != 0) {  // :300-314
     const double base = acap == ROOK ? 9.0 : acap == CANNON ? 4.5 : acap == KNIGHT ? 4.0
                         : (acap == BISHOP || acap == ADVISOR) ? 2.0 : acap == PAWN ? 1.0 : 0.0;
-    reward = __dmul_rn(base, 2.0);
+    reward = xq_dmul(base, 2.0);
     is_int = 0;
-    if (acap == ADVISOR || acap == BISHOP) reward = __dadd_rn(reward, 3.0);
+    if (acap == ADVISOR || acap == BISHOP) reward = xq_dadd(reward, 3.0);
   }
 
   const bool checking = in_check(w, g, -g.player);  // :317, geometry = mover
   if (!done && checking) {                           // :318-327
-    if (g.cchecks == 0) { reward = __dadd_rn(reward, 15.0); is_int = 0; }
-    else if (g.cchecks == 1) { reward = __dadd_rn(reward, 10.0); is_int = 0; }
-    else if (g.cchecks == 2) { reward = __dadd_rn(reward, 5.0); is_int = 0; }
+    if (g.cchecks == 0) { reward = xq_dadd(reward, 15.0); is_int = 0; }
+    else if (g.cchecks == 1) { reward = xq_dadd(reward, 10.0); is_int = 0; }
+    else if (g.cchecks == 2) { reward = xq_dadd(reward, 5.0); is_int = 0; }
     g.cchecks += 1;
   } else {  // :328-335
     g.cchecks = 0;
     if (captured == 0 && !done) {
       const int ek = g.player == 1 ? g.black_king : g.red_king;
       const double pcg = position_change(moving < 0 ? -moving : moving, g.player, from, to, ek);
-      reward = __dadd_rn(reward, __dmul_rn(pcg, 0.01));
+      reward = xq_dadd(reward, xq_dmul(pcg, 0.01));
       is_int = 0;
     }
   }
@@ -632,5 +721,7 @@ __device__ __forceinline__ int pick_index(const WarpSmem& w, int n, uint64_t see
   }
   return (int)(x[0] % (uint32_t)n);
 }
+
+#endif  // __CUDACC__
 
 }  // namespace xq

@@ -1,0 +1,75 @@
+// tests/host_mirror/xq_host_mirror.cpp — TEST HARNESS ONLY (never shipped, never a fallback).
+// Compiles the per-lane device logic of chinesechessai_b200/csrc/xq_rules.cuh (attacked,
+// suicide, gen_item, exotic_piece — all XQ_HD) with g++ and runs the warp's work items
+// sequentially, so the kernel's legality logic can be fuzzed against the oracle on the CPU.
+#include <cstring>
+
+#include "../../chinesechessai_b200/csrc/xq_rules.cuh"
+
+using namespace xq;
+
+static void stage(WarpSmem& w, const int8_t* board) {
+  std::memset(&w, 0, sizeof(w));
+  std::memcpy(w.sq, board, XQ_NSQ);
+  for (int r = 0; r < 10; ++r)
+    for (int c = 0; c < 9; ++c)
+      if (w.sq[r * 9 + c] != 0) {
+        w.rows[r] |= (uint16_t)(1u << c);
+        w.cols[c] |= (uint16_t)(1u << r);
+      }
+}
+
+extern "C" int xqh_legal_moves(const int8_t* board, int player, int red_king, int black_king,
+                               int16_t* moves, int* ncand_out) {
+  WarpSmem w;
+  stage(w, board);
+  Game g{};
+  g.player = player;
+  g.red_king = red_king;
+  g.black_king = black_king;
+  const int ownK = player == 1 ? red_king : black_king;
+  int n_own = 0, n_kings = 0;
+  bool exotic = false;
+  for (int s = 0; s < XQ_NSQ; ++s) {
+    if ((int)w.sq[s] * player > 0) w.own[n_own++] = (uint8_t)s;
+    n_kings += w.sq[s] == player * KING;
+    exotic |= exotic_piece(w.sq[s], s, player, ownK < 0 ? 0 : ownK);
+  }
+  exotic = exotic || !regular_king(w, player, ownK, n_kings);
+  int ncand = 0;
+  for (int t = 0; t < n_own * 4; ++t) {
+    const Item it = gen_item(w, player, w.own[t >> 2], t & 3);
+    const int cnt = it.empties + (it.e1 >= 0) + (it.e2 >= 0);
+    if (ncand + cnt > XQ_CAND_CAP) return -1;
+    for (int k = 1; k <= it.empties; ++k, ++ncand) {
+      w.cf[ncand] = (uint8_t)it.from;
+      w.ct[ncand] = (uint8_t)(it.from + k * it.delta);
+    }
+    if (it.e1 >= 0) { w.cf[ncand] = (uint8_t)it.from; w.ct[ncand] = (uint8_t)it.e1; ++ncand; }
+    if (it.e2 >= 0) { w.cf[ncand] = (uint8_t)it.from; w.ct[ncand] = (uint8_t)it.e2; ++ncand; }
+  }
+  if (ncand_out) *ncand_out = ncand;
+  int n = 0;
+  for (int j = 0; j < ncand; ++j)
+    if (!suicide(w, g, w.cf[j], w.ct[j], exotic)) {
+      if (n < XQ_MAX_MOVES) moves[n] = (int16_t)(w.cf[j] * 90 + w.ct[j]);
+      ++n;
+    }
+  return n;
+}
+
+// _is_in_check(player) with geometry of `current_player` (chess_env.py:506-548)
+extern "C" int xqh_in_check(const int8_t* board, int player, int current_player, int red_king,
+                            int black_king) {
+  WarpSmem w;
+  stage(w, board);
+  Game g{};
+  g.player = current_player;
+  g.red_king = red_king;
+  g.black_king = black_king;
+  return in_check(w, g, player) ? 1 : 0;
+}
+
+extern "C" double xqh_position_change(int type, int player, int from, int to, int enemy_king) {
+  return position_change(type, player, from, to, enemy_king);
+}

@@ -1,0 +1,88 @@
+"""CPU: the kernel's per-lane legality logic (xq_rules.cuh: attacked / suicide / gen_item,
+compiled for the host by tests/host_mirror) against the goldens and fuzzed against the oracle.
+This is a test harness for the device code, not a product path."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+
+@pytest.fixture(scope="module")
+def hm():
+    from tests.host_mirror.build import build
+    lib = C.CDLL(build())
+    lib.xqh_legal_moves.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.xqh_in_check.argtypes = [C.c_void_p] + [C.c_int] * 4
+    lib.xqh_position_change.argtypes = [C.c_int] * 5
+    lib.xqh_position_change.restype = C.c_double
+    return lib
+
+
+def _legal(hm, board, player, red, black):
+    b = np.ascontiguousarray(board, np.int8).reshape(90)
+    mv = np.zeros(128, np.int16)
+    nc = C.c_int(0)
+    n = hm.xqh_legal_moves(b.ctypes.data, int(player), int(red), int(black), mv.ctypes.data, C.byref(nc))
+    return mv[:n].copy(), nc.value
+
+
+def test_golden_positions(hm, golden):
+    P = golden.positions
+    off = P["legal_offset"]
+    for i in range(len(P["player"])):
+        mv, _ = _legal(hm, P["board"][i], P["player"][i], P["red"][i], P["black"][i])
+        assert np.array_equal(mv, P["legal"][off[i]:off[i + 1]]), i
+        b = np.ascontiguousarray(P["board"][i])
+        pl = int(P["player"][i])
+        assert hm.xqh_in_check(b.ctypes.data, pl, pl, int(P["red"][i]), int(P["black"][i])) == P["chk_self"][i], i
+        assert hm.xqh_in_check(b.ctypes.data, -pl, pl, int(P["red"][i]), int(P["black"][i])) == P["chk_opp"][i], i
+
+
+@pytest.mark.parametrize("bias", [0, 200])
+def test_fuzz_playouts_vs_oracle(hm, xo, bias):
+    max_cand = 0
+    for g in range(150):
+        e = xo.Env()
+        for ply in range(70):
+            lm = e.legal_moves_packed()
+            mv, nc = _legal(hm, e.board, e.s.player, e.s.red_king, e.s.black_king)
+            max_cand = max(max_cand, nc)
+            assert np.array_equal(mv, lm), (g, ply)
+            assert nc == e.pseudo_count()
+            b = np.ascontiguousarray(e.board.reshape(90))
+            for who in (1, -1):
+                assert hm.xqh_in_check(b.ctypes.data, who, e.s.player, e.s.red_king, e.s.black_king) == \
+                    int(e.is_in_check(who)), (g, ply, who)
+            if len(lm) == 0:
+                break
+            idx = xo.lib().xqo_pick_move(e.s, lm.ctypes.data, len(lm), 99, g, ply, bias)
+            _, _, done = e.make_move(int(lm[idx]))
+            if done:
+                break
+    assert max_cand <= 128
+
+
+def test_fuzz_arbitrary_boards_vs_oracle(hm, xo):
+    rng = np.random.default_rng(123)
+    for it in range(4000):
+        board = np.zeros(90, np.int8)
+        k = int(rng.integers(2, 30))
+        sq = rng.choice(90, size=k, replace=False)
+        board[sq] = rng.integers(1, 8, size=k) * rng.choice([-1, 1], size=k)
+        player = int(rng.choice([-1, 1]))
+
+        def cache(code):
+            u = rng.random()
+            w = np.flatnonzero(board == code)
+            if u < 0.6 and len(w):
+                return int(w[0])
+            if u < 0.8:
+                return int(rng.integers(0, 90))
+            return -1
+        red, black = cache(1), cache(-1)
+        pos = lambda s: None if s < 0 else (s // 9, s % 9)
+        e = xo.Env().load(board.reshape(10, 9), player, 0, None, pos(red), pos(black))
+        if e.pseudo_count() > 256:
+            continue
+        mv, _ = _legal(hm, board, player, red, black)
+        assert np.array_equal(mv, e.legal_moves_packed()), it
