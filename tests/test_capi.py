@@ -4,7 +4,7 @@ import ctypes
 import os
 import re
 
-from conftest import ROOT
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _declared():
