@@ -350,8 +350,8 @@ int xq_device_count(void) {
   } while (0)
 
 int xq_reset(int8_t* board, xq_meta* meta, int n_games, void* stream) {
-  XQ_REQUIRE(board && meta && n_games >= 0, "null pointer or negative n_games");
   if (n_games == 0) return 0;
+  XQ_REQUIRE(board && meta && n_games >= 0, "null pointer or negative n_games");
   const int64_t n = (int64_t)n_games * (XQ_BOARD_STRIDE / 4);
   reset_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(board, meta, n_games);
   return check_launch("xq_reset");
@@ -359,8 +359,8 @@ int xq_reset(int8_t* board, xq_meta* meta, int n_games, void* stream) {
 
 int xq_position_hash(const int8_t* board, const xq_meta* meta, uint64_t* out, int n_games,
                      void* stream) {
-  XQ_REQUIRE(board && meta && out && n_games >= 0, "null pointer or negative n_games");
   if (n_games == 0) return 0;
+  XQ_REQUIRE(board && meta && out && n_games >= 0, "null pointer or negative n_games");
   position_hash_kernel<<<ctas_for(n_games), kThreads, 0, (cudaStream_t)stream>>>(board, meta, out,
                                                                                  n_games);
   return check_launch("xq_position_hash");
@@ -368,8 +368,8 @@ int xq_position_hash(const int8_t* board, const xq_meta* meta, uint64_t* out, in
 
 int xq_legal_moves(const int8_t* board, xq_meta* meta, int16_t* moves, int16_t* n_moves,
                    uint8_t* in_check, int n_games, void* stream) {
-  XQ_REQUIRE(board && meta && moves && n_moves && n_games >= 0, "null pointer or negative n_games");
   if (n_games == 0) return 0;
+  XQ_REQUIRE(board && meta && moves && n_moves && n_games >= 0, "null pointer or negative n_games");
   legal_moves_kernel<<<ctas_for(n_games), kThreads, 0, (cudaStream_t)stream>>>(
       board, meta, moves, n_moves, in_check, n_games);
   return check_launch("xq_legal_moves");
@@ -378,10 +378,10 @@ int xq_legal_moves(const int8_t* board, xq_meta* meta, int16_t* moves, int16_t* 
 int xq_step(int8_t* board, xq_meta* meta, uint64_t* pos_hist, int hist_cap, const int16_t* move,
             double* reward, uint8_t* flags, int16_t* next_moves, int16_t* next_n, int n_games,
             void* stream) {
+  if (n_games == 0) return 0;
   XQ_REQUIRE(board && meta && pos_hist && move && reward && flags && n_games >= 0 && hist_cap > 0,
              "null pointer, negative n_games or hist_cap <= 0");
   XQ_REQUIRE(!(next_moves && !next_n), "next_moves requires next_n");
-  if (n_games == 0) return 0;
   step_kernel<<<ctas_for(n_games), kThreads, 0, (cudaStream_t)stream>>>(
       board, meta, pos_hist, hist_cap, move, reward, flags, next_moves, next_n, n_games);
   return check_launch("xq_step");
@@ -390,10 +390,10 @@ int xq_step(int8_t* board, xq_meta* meta, uint64_t* pos_hist, int hist_cap, cons
 int xq_pick_moves(const int8_t* board, const xq_meta* meta, const int16_t* moves,
                   const int16_t* n_moves, uint64_t seed, uint32_t first_game_id, uint32_t ply,
                   int capture_bias, int16_t* picked, int n_games, void* stream) {
+  if (n_games == 0) return 0;
   XQ_REQUIRE(board && meta && moves && n_moves && picked && n_games >= 0,
              "null pointer or negative n_games");
   XQ_REQUIRE(capture_bias >= 0 && capture_bias <= 256, "capture_bias out of [0,256]");
-  if (n_games == 0) return 0;
   pick_kernel<<<ctas_for(n_games), kThreads, 0, (cudaStream_t)stream>>>(
       board, meta, moves, n_moves, seed, first_game_id, ply, capture_bias, picked, n_games);
   return check_launch("xq_pick_moves");
@@ -403,10 +403,10 @@ int xq_playout(int8_t* board, xq_meta* meta, uint64_t* pos_hist, int hist_cap, u
                uint32_t first_game_id, int max_plies, int capture_bias, xq_playout_result* results,
                int16_t* tr_moves, int16_t* tr_n, int16_t* tr_pick, double* tr_reward,
                uint8_t* tr_flags, int8_t* tr_boards, int n_games, void* stream) {
+  if (n_games == 0) return 0;
   XQ_REQUIRE(board && meta && pos_hist && results && n_games >= 0 && hist_cap > 0 && max_plies >= 0,
              "null pointer, negative size or hist_cap <= 0");
   XQ_REQUIRE(capture_bias >= 0 && capture_bias <= 256, "capture_bias out of [0,256]");
-  if (n_games == 0) return 0;
   const bool trace = tr_moves || tr_n || tr_pick || tr_reward || tr_flags || tr_boards;
   if (trace)
     playout_kernel<true><<<ctas_for(n_games), kThreads, 0, (cudaStream_t)stream>>>(
@@ -431,9 +431,9 @@ int xq_playout(int8_t* board, xq_meta* meta, uint64_t* pos_hist, int hist_cap, u
 int xq_playout_host(int8_t* board_h, xq_meta* meta_h, uint64_t seed, uint32_t first_game_id,
                     int max_plies, int capture_bias, xq_playout_result* results_h, int n_games,
                     int device) {
+  if (n_games == 0) return 0;
   XQ_REQUIRE(board_h && meta_h && results_h && n_games >= 0 && max_plies >= 0,
              "null pointer or negative size");
-  if (n_games == 0) return 0;
   int rc = 0;
   int8_t* board = nullptr;
   xq_meta* meta = nullptr;
@@ -490,9 +490,9 @@ done:
 
 int xq_encode_planes(const int8_t* board, int board_stride, const int8_t* player, int player_stride,
                      void* planes, int out_bf16, int n, void* stream) {
+  if (n == 0) return 0;
   XQ_REQUIRE(board && player && planes && n >= 0 && board_stride >= XQ_NSQ && player_stride >= 1,
              "null pointer or bad stride");
-  if (n == 0) return 0;
   const int64_t total = (int64_t)n * XQ_NSQ;
   const unsigned grid = (unsigned)((total + 255) / 256);
   if (out_bf16)
@@ -506,9 +506,9 @@ int xq_encode_planes(const int8_t* board, int board_stride, const int8_t* player
 
 int xq_policy_priors(const void* logits, int logits_bf16, const int16_t* moves, int moves_stride,
                      const int16_t* n_moves, float* priors, int n, void* stream) {
+  if (n == 0) return 0;
   XQ_REQUIRE(logits && moves && n_moves && priors && n >= 0 && moves_stride >= 1,
              "null pointer or bad stride");
-  if (n == 0) return 0;
   if (logits_bf16)
     priors_kernel<__nv_bfloat16><<<ctas_for(n), kThreads, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)logits, moves, moves_stride, n_moves, priors, n);

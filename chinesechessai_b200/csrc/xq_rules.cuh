@@ -56,14 +56,14 @@ XQ_HD unsigned xq_brev(unsigned x) {
 }
 XQ_HD double xq_dadd(double a, double b) {
 #if defined(__CUDA_ARCH__)
-  return xq_dadd(a, b);
+  return __dadd_rn(a, b);
 #else
   return a + b;
 #endif
 }
 XQ_HD double xq_dmul(double a, double b) {
 #if defined(__CUDA_ARCH__)
-  return xq_dmul(a, b);
+  return __dmul_rn(a, b);
 #else
   return a * b;
 #endif
