@@ -1,0 +1,466 @@
+// xq_mcts.cu — MCTS select / expand / backup over a flat per-game node pool
+// (self_play.py:19-175), one warp per tree, sm_100a.
+//
+// Layout of one tree (xq_mcts_tree_bytes(n) bytes, 16-byte aligned):
+//   TreeHeader                       64 B
+//   Node nodes[1 + 128*waves]        32 B each; children of a node contiguous,
+//                                    in legal-move order (MCTSNode.children dict order)
+//   StateRec states[waves + 2]       board 96 B + xq_meta 32 B + path history u64[waves+1]
+// waves = ceil(n/8).  At most one node is expanded per wave, so
+// the pools cannot overflow.  Expanded nodes keep their env state: a simulation
+// walks the tree with PUCT only and steps the rules engine once, at its leaf.
+// No atomics: a tree is touched by exactly one warp.
+#include <cuda_bf16.h>
+
+#include "xq_rules.cuh"
+
+namespace xq {
+
+int fail(int code, const char* fmt, ...);
+int check_launch(const char* what);
+
+constexpr int kWave = 8;  // self_play.py:101
+constexpr int kThreadsM = kWarpsPerCta * 32;
+
+struct TreeHeader {
+  int32_t sims_total, sims_done, n_nodes, n_states;
+  int32_t pending_node, pending_m, node_cap, state_cap;
+  int32_t hist_cap, overflow, pad[6];
+};
+static_assert(sizeof(TreeHeader) == 64, "TreeHeader");
+
+struct __align__(16) Node {
+  double value_sum;     // self_play.py:27
+  int32_t visits;       // :26
+  float prior;          // :28 (numpy.float32)
+  int32_t first_child;  // -1 = leaf (:36-38)
+  int32_t parent;       // :22
+  int16_t n_children;
+  int16_t move;         // :23
+  int16_t state;        // index into states[] once the env state is known
+  int8_t term;          // 0 unknown, 1 non-terminal, 2 terminal leaf
+  int8_t tval;          // terminal value +1/-1/0 (:128-133)
+};
+static_assert(sizeof(Node) == 32, "Node");
+
+struct TreeDims {
+  int waves, node_cap, state_cap, hist_cap;
+  int64_t node_off, state_off, state_bytes, bytes;
+};
+
+__host__ __device__ inline TreeDims tree_dims(int n_sims) {
+  TreeDims d;
+  d.waves = (n_sims + kWave - 1) / kWave;
+  if (d.waves < 1) d.waves = 1;
+  d.node_cap = 1 + XQ_MAX_MOVES * d.waves;
+  d.state_cap = d.waves + 2;
+  d.hist_cap = d.waves + 1;
+  d.node_off = sizeof(TreeHeader);
+  d.state_off = d.node_off + (int64_t)d.node_cap * sizeof(Node);
+  d.state_bytes = XQ_BOARD_STRIDE + sizeof(xq_meta) + (int64_t)d.hist_cap * 8;
+  d.state_bytes = (d.state_bytes + 15) & ~15LL;
+  d.bytes = d.state_off + d.state_bytes * d.state_cap;
+  d.bytes = (d.bytes + 63) & ~63LL;
+  return d;
+}
+
+struct Tree {
+  TreeHeader* h;
+  Node* nodes;
+  char* states;
+  int64_t state_bytes;
+  __device__ int8_t* board(int s) const { return reinterpret_cast<int8_t*>(states + s * state_bytes); }
+  __device__ xq_meta* meta(int s) const {
+    return reinterpret_cast<xq_meta*>(states + s * state_bytes + XQ_BOARD_STRIDE);
+  }
+  __device__ uint64_t* hist(int s) const {
+    return reinterpret_cast<uint64_t*>(states + s * state_bytes + XQ_BOARD_STRIDE + sizeof(xq_meta));
+  }
+};
+
+__device__ __forceinline__ Tree tree_at(void* trees, const TreeDims& d, int g) {
+  char* base = reinterpret_cast<char*>(trees) + (int64_t)g * d.bytes;
+  Tree t;
+  t.h = reinterpret_cast<TreeHeader*>(base);
+  t.nodes = reinterpret_cast<Node*>(base + d.node_off);
+  t.states = base + d.state_off;
+  t.state_bytes = d.state_bytes;
+  return t;
+}
+
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreadsM)
+    mcts_init_kernel(void* trees, int n_sims, const int8_t* __restrict__ board,
+                     const xq_meta* __restrict__ meta, const uint8_t* __restrict__ active,
+                     int n_games) {
+  const int g = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (g >= n_games) return;
+  const int lane = lane_id();
+  const TreeDims d = tree_dims(n_sims);
+  Tree t = tree_at(trees, d, g);
+  const bool on = active ? active[g] != 0 : true;
+  if (lane < XQ_BOARD_STRIDE / 4)
+    reinterpret_cast<uint32_t*>(t.board(0))[lane] =
+        reinterpret_cast<const uint32_t*>(board + (size_t)g * XQ_BOARD_STRIDE)[lane];
+  if (lane == 0) {
+    TreeHeader h = {};
+    h.sims_total = on ? n_sims : 0;
+    h.n_nodes = 1;
+    h.n_states = 1;
+    h.pending_node = -1;
+    h.node_cap = d.node_cap;
+    h.state_cap = d.state_cap;
+    h.hist_cap = d.hist_cap;
+    *t.h = h;
+    Node r = {};
+    r.first_child = -1;
+    r.parent = -1;
+    r.move = -1;
+    r.state = 0;
+    t.nodes[0] = r;
+    // MCTS._copy_env (self_play.py:156-175)
+    xq_meta m = meta[g];
+    xq_meta c = {};
+    c.player = m.player;
+    c.winner = m.winner;
+    c.red_king = m.red_king;
+    c.black_king = m.black_king;
+    c.move_count = m.move_count;
+    c.no_capture = m.no_capture;
+    *t.meta(0) = c;
+  }
+}
+
+// select_child (self_play.py:40-59): float32 PUCT, strict '>' => first max wins.
+__device__ __forceinline__ int puct_select(const Tree& t, int node) {
+  const int lane = lane_id();
+  const Node nd = t.nodes[node];
+  const float sq = (float)sqrt((double)nd.visits);
+  float best = -INFINITY;
+  int best_i = 0x7fffffff;
+  for (int i = lane; i < nd.n_children; i += 32) {
+    const Node* c = &t.nodes[nd.first_child + i];
+    const uint4 raw = *reinterpret_cast<const uint4*>(c);  // value_sum, visits, prior
+    const double vs = __hiloint2double((int)raw.y, (int)raw.x);
+    const int n = (int)raw.z;
+    const float p = __uint_as_float(raw.w);
+    const float q = n == 0 ? 0.0f : __double2float_rn(vs / (double)n);  // :30-34
+    float u = __fmul_rn(1.5f, p);
+    u = __fmul_rn(u, sq);
+    u = __fdiv_rn(u, (float)(1 + n));
+    const float s = __fadd_rn(q, u);
+    if (s > best) {
+      best = s;
+      best_i = i;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(kFull, best, o);
+    const int oi = __shfl_xor_sync(kFull, best_i, o);
+    if (ob > best || (ob == best && oi < best_i)) {
+      best = ob;
+      best_i = oi;
+    }
+  }
+  return nd.first_child + best_i;
+}
+
+// MCTSNode.update (self_play.py:70-80): sequential float64 adds up the parent chain.
+__device__ __forceinline__ void backup_path(const Tree& t, int node, double v) {
+  while (node >= 0) {
+    Node* nd = &t.nodes[node];
+    nd->visits += 1;
+    nd->value_sum = __dadd_rn(nd->value_sum, v);
+    v = -v;
+    node = nd->parent;
+  }
+}
+
+__global__ void __launch_bounds__(kThreadsM)
+    mcts_select_kernel(void* trees, int n_sims, int wave_size, int8_t* __restrict__ leaf_board,
+                       int8_t* __restrict__ leaf_player, int16_t* __restrict__ leaf_moves,
+                       int16_t* __restrict__ leaf_n, int16_t* __restrict__ leaf_mult, int n_games) {
+  __shared__ WarpSmem slab[kWarpsPerCta];
+  const int g = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (g >= n_games) return;
+  WarpSmem& w = slab[threadIdx.x >> 5];
+  const int lane = lane_id();
+  const TreeDims d = tree_dims(n_sims);
+  Tree t = tree_at(trees, d, g);
+  TreeHeader h = *t.h;
+  const int count = min(wave_size, h.sims_total - h.sims_done);  // :104-105
+  int pending = -1, mult = 0, pend_n = 0;
+  for (int k = 0; k < count; ++k) {
+    int node = 0;
+    while (true) {  // :117-119
+      const Node nd = t.nodes[node];
+      if (nd.first_child >= 0) {
+        node = puct_select(t, node);
+        continue;
+      }
+      int term = nd.term, tval = nd.tval;
+      if (term == 0) {  // first visit: derive this node's env state
+        Game G;
+        int n_legal;
+        int slot;
+        if (nd.parent < 0) {  // root: state 0 was written by init
+          slot = 0;
+          load_board(w, t.board(0));
+          build_masks(w);
+          G = load_meta(t.meta(0));
+          n_legal = movegen(w, G);  // :123
+        } else {
+          const int ps = t.nodes[nd.parent].state;
+          slot = h.n_states;  // scratch until proven non-terminal
+          load_board(w, t.board(ps));
+          build_masks(w);
+          G = load_meta(t.meta(ps));
+          uint64_t* hs = t.hist(slot);
+          const uint64_t* hp = t.hist(ps);
+          for (int i = lane; i < G.hist_len; i += 32) hs[i] = hp[i];
+          __syncwarp();
+          const StepOut o = step(w, G, nd.move, hs, d.hist_cap);  // :119
+          n_legal = o.n_next < 0 ? 0 : o.n_next;
+          if (o.n_next < 0 && G.winner == XQ_WINNER_NONE) n_legal = 0;
+        }
+        if (n_legal == 0 || G.winner != XQ_WINNER_NONE) {  // :126-133
+          term = 2;
+          tval = G.winner == G.player ? 1 : (G.winner == -G.player ? -1 : 0);
+        } else {
+          term = 1;
+          store_board(w, t.board(slot));
+          store_meta(t.meta(slot), G);
+          if (slot != 0) h.n_states += 1;
+          int16_t* lm = leaf_moves + (size_t)g * XQ_MAX_MOVES;
+          for (int i = lane; i < n_legal; i += 32) lm[i] = w.moves[i];
+          pend_n = n_legal;
+          if (lane == 0) t.nodes[node].state = (int16_t)slot;
+        }
+        if (lane == 0) {
+          t.nodes[node].term = (int8_t)term;
+          t.nodes[node].tval = (int8_t)tval;
+        }
+        __syncwarp();
+      }
+      if (term == 2) {  // :134-135
+        if (lane == 0) backup_path(t, node, (double)tval);
+        __syncwarp();
+      } else {  // :138-139 — every remaining sim of the wave reaches this same leaf
+        pending = node;
+        mult = count - k;
+      }
+      break;
+    }
+    if (pending >= 0) break;
+  }
+  // leaf outputs
+  if (pending >= 0) {
+    const int s = t.nodes[pending].state;
+    if (pend_n == 0) {  // unreachable: a non-terminal leaf is materialised in the wave that finds it
+      h.overflow |= 2;
+    }
+    if (lane < XQ_BOARD_STRIDE / 4)
+      reinterpret_cast<uint32_t*>(leaf_board + (size_t)g * XQ_BOARD_STRIDE)[lane] =
+          reinterpret_cast<const uint32_t*>(t.board(s))[lane];
+    if (lane == 0) leaf_player[g] = t.meta(s)->player;
+  }
+  if (lane == 0) {
+    leaf_n[g] = (int16_t)(pending >= 0 ? pend_n : 0);
+    leaf_mult[g] = (int16_t)mult;
+    h.sims_done += count > 0 ? count : 0;
+    h.pending_node = pending;
+    h.pending_m = mult;
+    *t.h = h;
+  }
+}
+
+template <typename V>
+__global__ void __launch_bounds__(kThreadsM)
+    mcts_backup_kernel(void* trees, int n_sims, const int16_t* __restrict__ leaf_moves,
+                       const int16_t* __restrict__ leaf_n, const float* __restrict__ priors,
+                       const V* __restrict__ values, int values_per_game, int n_games) {
+  const int g = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (g >= n_games) return;
+  const int lane = lane_id();
+  const TreeDims d = tree_dims(n_sims);
+  Tree t = tree_at(trees, d, g);
+  TreeHeader h = *t.h;
+  const int node = h.pending_node;
+  if (node < 0) return;
+  const int n = leaf_n[g];
+  if (t.nodes[node].first_child < 0) {  // expand (:61-68); idempotent
+    const int first = h.n_nodes;
+    if (first + n > h.node_cap) {
+      if (lane == 0) {
+        h.overflow |= 1;
+        h.pending_node = -1;
+        *t.h = h;
+      }
+      return;
+    }
+    for (int i = lane; i < n; i += 32) {
+      Node c = {};
+      c.prior = priors[(size_t)g * XQ_MAX_MOVES + i];
+      c.first_child = -1;
+      c.parent = node;
+      c.move = leaf_moves[(size_t)g * XQ_MAX_MOVES + i];
+      c.state = -1;
+      t.nodes[first + i] = c;
+    }
+    if (lane == 0) {
+      t.nodes[node].first_child = first;
+      t.nodes[node].n_children = (int16_t)n;
+    }
+    h.n_nodes = first + n;
+  }
+  __syncwarp();
+  if (lane == 0) {  // one update per queued simulation, in queue order (:146-148)
+    for (int k = 0; k < h.pending_m; ++k) {
+      const double v = (double)values[values_per_game == 1 ? (size_t)g : (size_t)g * kWave + k];
+      backup_path(t, node, v);
+    }
+    h.pending_node = -1;
+    h.pending_m = 0;
+    *t.h = h;
+  }
+}
+
+__global__ void __launch_bounds__(kThreadsM)
+    mcts_root_visits_kernel(const void* trees, int n_sims, int16_t* __restrict__ moves,
+                            int32_t* __restrict__ visits, int16_t* __restrict__ n_children,
+                            int n_games) {
+  const int g = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (g >= n_games) return;
+  const int lane = lane_id();
+  const TreeDims d = tree_dims(n_sims);
+  Tree t = tree_at(const_cast<void*>(trees), d, g);
+  const Node root = t.nodes[0];
+  const int n = root.first_child >= 0 ? root.n_children : 0;
+  for (int i = lane; i < XQ_MAX_MOVES; i += 32) {
+    const bool ok = i < n;
+    moves[(size_t)g * XQ_MAX_MOVES + i] = ok ? t.nodes[root.first_child + i].move : (int16_t)-1;
+    visits[(size_t)g * XQ_MAX_MOVES + i] = ok ? t.nodes[root.first_child + i].visits : 0;
+  }
+  if (lane == 0) n_children[g] = (int16_t)n;
+}
+
+// Mirror of the oracle's deterministic evaluator (order-independent arithmetic).
+__global__ void __launch_bounds__(kThreadsM)
+    hash_eval_kernel(const int8_t* __restrict__ board, int board_stride,
+                     const int8_t* __restrict__ player, const int16_t* __restrict__ moves,
+                     const int16_t* __restrict__ n_moves, int flat, float* __restrict__ priors,
+                     double* __restrict__ values, int n) {
+  __shared__ WarpSmem slab[kWarpsPerCta];
+  const int g = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (g >= n) return;
+  WarpSmem& w = slab[threadIdx.x >> 5];
+  const int lane = lane_id();
+  for (int s = lane; s < XQ_NSQ; s += 32) w.sq[s] = board[(size_t)g * board_stride + s];
+  __syncwarp();
+  const uint64_t hsh = board_key(w) ^ side_key(player[g]);
+  const int cnt = n_moves[g];
+  double wts[XQ_MAX_MOVES / 32];
+  double sum = 0.0;
+#pragma unroll
+  for (int k = 0; k < XQ_MAX_MOVES / 32; ++k) {
+    const int i = k * 32 + lane;
+    double x = 0.0;
+    if (i < cnt) {
+      const uint64_t u =
+          flat ? 0ULL
+               : mix64(hsh ^ ((uint64_t)(uint16_t)moves[(size_t)g * XQ_MAX_MOVES + i] * 0x9E3779B97F4A7C15ULL));
+      x = (double)((u >> 40) + 1);
+    }
+    wts[k] = x;
+    sum += x;  // integers < 2^24: exact in any order
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(kFull, sum, o);
+#pragma unroll
+  for (int k = 0; k < XQ_MAX_MOVES / 32; ++k) {
+    const int i = k * 32 + lane;
+    priors[(size_t)g * XQ_MAX_MOVES + i] = i < cnt ? __double2float_rn(wts[k] / sum) : 0.0f;
+  }
+  if (lane == 0) values[g] = (double)((hsh >> 11) & 0xFFFFFu) / 524288.0 - 1.0;
+}
+
+}  // namespace xq
+
+using namespace xq;
+
+extern "C" {
+
+#define XQM_REQUIRE(cond, msg)                                     \
+  do {                                                             \
+    if (!(cond)) return fail(XQ_E_ARG, "%s: %s", __func__, msg);   \
+  } while (0)
+
+static inline int ctas_m(int n) { return (n + kWarpsPerCta - 1) / kWarpsPerCta; }
+
+int64_t xq_mcts_tree_bytes(int num_simulations) { return tree_dims(num_simulations).bytes; }
+
+int xq_mcts_init(void* trees, int num_simulations, const int8_t* board, const xq_meta* meta,
+                 const uint8_t* active, int n_games, void* stream) {
+  if (n_games == 0) return 0;
+  XQM_REQUIRE(trees && board && meta && n_games > 0 && num_simulations > 0,
+              "null pointer or non-positive size");
+  mcts_init_kernel<<<ctas_m(n_games), kThreadsM, 0, (cudaStream_t)stream>>>(
+      trees, num_simulations, board, meta, active, n_games);
+  return check_launch("xq_mcts_init");
+}
+
+int xq_mcts_select(void* trees, int num_simulations, int wave_size, int8_t* leaf_board,
+                   int8_t* leaf_player, int16_t* leaf_moves, int16_t* leaf_n, int16_t* leaf_mult,
+                   int n_games, void* stream) {
+  if (n_games == 0) return 0;
+  XQM_REQUIRE(trees && leaf_board && leaf_player && leaf_moves && leaf_n && leaf_mult && n_games > 0,
+              "null pointer or non-positive size");
+  XQM_REQUIRE(wave_size >= 1 && wave_size <= kWave && num_simulations > 0, "wave_size not in [1,8]");
+  mcts_select_kernel<<<ctas_m(n_games), kThreadsM, 0, (cudaStream_t)stream>>>(
+      trees, num_simulations, wave_size, leaf_board, leaf_player, leaf_moves, leaf_n, leaf_mult,
+      n_games);
+  return check_launch("xq_mcts_select");
+}
+
+int xq_mcts_backup(void* trees, int num_simulations, const int16_t* leaf_moves,
+                   const int16_t* leaf_n, const float* priors, const void* values, int values_f32,
+                   int values_per_game, int n_games, void* stream) {
+  if (n_games == 0) return 0;
+  XQM_REQUIRE(trees && leaf_moves && leaf_n && priors && values && n_games > 0,
+              "null pointer or non-positive size");
+  XQM_REQUIRE(values_per_game == 1 || values_per_game == kWave, "values_per_game must be 1 or 8");
+  if (values_f32)
+    mcts_backup_kernel<float><<<ctas_m(n_games), kThreadsM, 0, (cudaStream_t)stream>>>(
+        trees, num_simulations, leaf_moves, leaf_n, priors, (const float*)values, values_per_game,
+        n_games);
+  else
+    mcts_backup_kernel<double><<<ctas_m(n_games), kThreadsM, 0, (cudaStream_t)stream>>>(
+        trees, num_simulations, leaf_moves, leaf_n, priors, (const double*)values, values_per_game,
+        n_games);
+  return check_launch("xq_mcts_backup");
+}
+
+int xq_mcts_root_visits(const void* trees, int num_simulations, int16_t* moves, int32_t* visits,
+                        int16_t* n_children, int n_games, void* stream) {
+  if (n_games == 0) return 0;
+  XQM_REQUIRE(trees && moves && visits && n_children && n_games > 0 && num_simulations > 0,
+              "null pointer or non-positive size");
+  mcts_root_visits_kernel<<<ctas_m(n_games), kThreadsM, 0, (cudaStream_t)stream>>>(
+      trees, num_simulations, moves, visits, n_children, n_games);
+  return check_launch("xq_mcts_root_visits");
+}
+
+int xq_hash_eval(const int8_t* board, int board_stride, const int8_t* player, const int16_t* moves,
+                 const int16_t* n_moves, int flat, float* priors, double* values, int n,
+                 void* stream) {
+  if (n == 0) return 0;
+  XQM_REQUIRE(board && player && moves && n_moves && priors && values && n > 0 &&
+                  board_stride >= XQ_NSQ,
+              "null pointer or bad stride");
+  hash_eval_kernel<<<ctas_m(n), kThreadsM, 0, (cudaStream_t)stream>>>(
+      board, board_stride, player, moves, n_moves, flat, priors, values, n);
+  return check_launch("xq_hash_eval");
+}
+
+}  // extern "C"

@@ -1,0 +1,122 @@
+"""Batched MCTS on the GPU: one tree per game, all games advance wave by wave.
+
+Device-side counterpart of ``MCTS.search`` (self_play.py:89-154): per wave ONE
+``xq_mcts_select`` launch walks every tree to its network leaf, ONE evaluator call scores all
+leaves (the only dense contraction — a single batched ``ChessNet.forward``), ONE
+``xq_mcts_backup`` launch expands and backs up.  No host synchronisation inside a search.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import BOARD_STRIDE, MAX_MOVES, check
+from .engine import _ptr, _stream, encode_planes, policy_priors
+
+WAVE = 8  # self_play.py:101
+
+
+class HashEvaluator:
+    """Deterministic stand-in for the network (the function is specified in DESIGN.md);
+    used by parity tests and by search-only benchmarks."""
+
+    def __init__(self, flat: bool = False):
+        self.flat = flat
+        self.lib = _lib.load()
+
+    def __call__(self, leaf_board, leaf_player, leaf_moves, leaf_n):
+        n = leaf_board.shape[0]
+        pri = torch.empty((n, MAX_MOVES), dtype=torch.float32, device=leaf_board.device)
+        val = torch.empty((n,), dtype=torch.float64, device=leaf_board.device)
+        with torch.cuda.device(leaf_board.device):
+            check(self.lib.xq_hash_eval(_ptr(leaf_board), leaf_board.stride(0), _ptr(leaf_player),
+                                        _ptr(leaf_moves), _ptr(leaf_n), 1 if self.flat else 0,
+                                        _ptr(pri), _ptr(val), n, _stream()))
+        return pri, val
+
+
+class NetEvaluator:
+    """encode_board -> ChessNet.forward -> gather+softmax, all on device
+    (neural_network.py:96-126 without the per-sample D2H of :120-124)."""
+
+    def __init__(self, net: torch.nn.Module, dtype: torch.dtype = torch.float32):
+        self.net = net
+        self.dtype = dtype
+
+    @torch.no_grad()
+    def __call__(self, leaf_board, leaf_player, leaf_moves, leaf_n):
+        planes = encode_planes(leaf_board, leaf_player, dtype=self.dtype)
+        if self.dtype == torch.float32:
+            logits, value = self.net(planes)
+        else:
+            with torch.autocast("cuda", dtype=self.dtype):
+                logits, value = self.net(planes)
+        logits = logits.contiguous()
+        if logits.dtype not in (torch.float32, torch.bfloat16):
+            logits = logits.float()
+        pri = policy_priors(logits, leaf_moves, leaf_n)
+        return pri, value.reshape(-1).float().contiguous()
+
+
+class BatchedMCTS:
+    def __init__(self, n_games: int, num_simulations: int, device: Optional[torch.device] = None):
+        self.lib = _lib.load()
+        _lib.require_device()
+        self.n = int(n_games)
+        self.num_simulations = int(num_simulations)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        d = self.device
+        self.tree_bytes = int(self.lib.xq_mcts_tree_bytes(self.num_simulations))
+        self.trees = torch.empty((max(self.n, 1) * self.tree_bytes,), dtype=torch.uint8, device=d)
+        self.leaf_board = torch.zeros((self.n, BOARD_STRIDE), dtype=torch.int8, device=d)
+        self.leaf_player = torch.ones((self.n,), dtype=torch.int8, device=d)
+        self.leaf_moves = torch.zeros((self.n, MAX_MOVES), dtype=torch.int16, device=d)
+        self.leaf_n = torch.zeros((self.n,), dtype=torch.int16, device=d)
+        self.leaf_mult = torch.zeros((self.n,), dtype=torch.int16, device=d)
+        self.root_moves = torch.zeros((self.n, MAX_MOVES), dtype=torch.int16, device=d)
+        self.root_visits = torch.zeros((self.n, MAX_MOVES), dtype=torch.int32, device=d)
+        self.root_n = torch.zeros((self.n,), dtype=torch.int16, device=d)
+
+    # -- the three kernels ---------------------------------------------------------------
+    def init(self, board: torch.Tensor, meta: torch.Tensor, active: Optional[torch.Tensor] = None):
+        with torch.cuda.device(self.device):
+            check(self.lib.xq_mcts_init(_ptr(self.trees), self.num_simulations, _ptr(board), _ptr(meta),
+                                        _ptr(active), self.n, _stream()))
+
+    def select(self, wave_size: int):
+        with torch.cuda.device(self.device):
+            check(self.lib.xq_mcts_select(_ptr(self.trees), self.num_simulations, wave_size,
+                                          _ptr(self.leaf_board), _ptr(self.leaf_player),
+                                          _ptr(self.leaf_moves), _ptr(self.leaf_n),
+                                          _ptr(self.leaf_mult), self.n, _stream()))
+
+    def backup(self, priors: torch.Tensor, values: torch.Tensor, values_per_game: int = 1):
+        assert priors.dtype == torch.float32 and priors.is_contiguous()
+        assert values.dtype in (torch.float32, torch.float64) and values.is_contiguous()
+        with torch.cuda.device(self.device):
+            check(self.lib.xq_mcts_backup(_ptr(self.trees), self.num_simulations, _ptr(self.leaf_moves),
+                                          _ptr(self.leaf_n), _ptr(priors), _ptr(values),
+                                          1 if values.dtype == torch.float32 else 0,
+                                          values_per_game, self.n, _stream()))
+
+    def visits(self):
+        with torch.cuda.device(self.device):
+            check(self.lib.xq_mcts_root_visits(_ptr(self.trees), self.num_simulations,
+                                               _ptr(self.root_moves), _ptr(self.root_visits),
+                                               _ptr(self.root_n), self.n, _stream()))
+        return self.root_moves, self.root_visits, self.root_n
+
+    # -- MCTS.search for the whole batch ---------------------------------------------------
+    def search(self, board: torch.Tensor, meta: torch.Tensor, evaluator: Callable,
+               active: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """Returns (moves int16[n,128], visit counts int32[n,128], n_children int16[n]); rows are
+        the root's children in ``get_legal_moves()`` order, like the dict of self_play.py:151-154."""
+        self.init(board, meta, active)
+        for start in range(0, self.num_simulations, WAVE):
+            self.select(min(WAVE, self.num_simulations - start))
+            priors, values = evaluator(self.leaf_board, self.leaf_player, self.leaf_moves, self.leaf_n)
+            self.backup(priors, values)
+        return self.visits()
+

