@@ -56,6 +56,7 @@ SIGNATURES = {
     "xq_reset": (_i, [_vp, _vp, _i, _vp]),
     "xq_position_hash": (_i, [_vp, _vp, _vp, _i, _vp]),
     "xq_legal_moves": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "xq_query_checks": (_i, [_vp, _vp, _vp, _i, _vp]),
     "xq_step": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "xq_pick_moves": (_i, [_vp, _vp, _vp, _vp, _u64, _u32, _u32, _i, _vp, _i, _vp]),
     "xq_playout": (_i, [_vp, _vp, _vp, _i, _u64, _u32, _i, _i, _vp,

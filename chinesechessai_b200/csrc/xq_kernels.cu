@@ -106,6 +106,37 @@ __global__ void __launch_bounds__(kThreads)
 }
 
 // ---------------------------------------------------------------------------
+// _is_in_check(+1), _is_in_check(-1), _are_kings_facing (chess_env.py:506-548, :466-495)
+__global__ void __launch_bounds__(kThreads)
+    query_checks_kernel(const int8_t* __restrict__ board, const xq_meta* __restrict__ meta,
+                        uint8_t* __restrict__ out, int n_games) {
+  __shared__ WarpSmem slab[kWarpsPerCta];
+  const int g = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (g >= n_games) return;
+  WarpSmem& w = slab[threadIdx.x >> 5];
+  load_board(w, board + (size_t)g * XQ_BOARD_STRIDE);
+  build_masks(w);
+  const Game G = load_meta(meta + g);
+  if (lane_id() == 0) {
+    bool facing = false;
+    if (G.red_king >= 0 && G.black_king >= 0) {
+      const int rr = G.red_king / 9, rc = G.red_king % 9, br = G.black_king / 9, bc = G.black_king % 9;
+      if (rc == bc) {
+        const int lo = min(rr, br), hi = max(rr, br);
+        const unsigned between = ((1u << hi) - 1u) & ~((2u << lo) - 1u);
+        facing = (w.cols[rc] & between) == 0;
+      }
+    }
+    uchar4 r;
+    r.x = in_check(w, G, 1) ? 1 : 0;
+    r.y = in_check(w, G, -1) ? 1 : 0;
+    r.z = facing ? 1 : 0;
+    r.w = 0;
+    reinterpret_cast<uchar4*>(out)[g] = r;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // make_move (chess_env.py:253-406)
 __global__ void __launch_bounds__(kThreads)
     step_kernel(int8_t* __restrict__ board, xq_meta* __restrict__ meta,
@@ -373,6 +404,15 @@ int xq_legal_moves(const int8_t* board, xq_meta* meta, int16_t* moves, int16_t* 
   legal_moves_kernel<<<ctas_for(n_games), kThreads, 0, (cudaStream_t)stream>>>(
       board, meta, moves, n_moves, in_check, n_games);
   return check_launch("xq_legal_moves");
+}
+
+int xq_query_checks(const int8_t* board, const xq_meta* meta, uint8_t* out, int n_games,
+                    void* stream) {
+  if (n_games == 0) return 0;
+  XQ_REQUIRE(board && meta && out && n_games >= 0, "null pointer or negative n_games");
+  query_checks_kernel<<<ctas_for(n_games), kThreads, 0, (cudaStream_t)stream>>>(board, meta, out,
+                                                                                n_games);
+  return check_launch("xq_query_checks");
 }
 
 int xq_step(int8_t* board, xq_meta* meta, uint64_t* pos_hist, int hist_cap, const int16_t* move,

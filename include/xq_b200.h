@@ -119,6 +119,12 @@ int xq_position_hash(const int8_t *board, const xq_meta *meta, uint64_t *out,
 int xq_legal_moves(const int8_t *board, xq_meta *meta, int16_t *moves,
                    int16_t *n_moves, uint8_t *in_check, int n_games, void *stream);
 
+/* _is_in_check / _are_kings_facing (chess_env.py:506-548, :466-495) on the current
+ * state.  out: uint8[n_games][4] = { _is_in_check(+1), _is_in_check(-1),
+ * _are_kings_facing(), 0 }, attack geometry of meta.player as in the reference. */
+int xq_query_checks(const int8_t *board, const xq_meta *meta, uint8_t *out, int n_games,
+                    void *stream);
+
 /* ChineseChess.make_move (chess_env.py:253-406) for one move per game.
  * move[g] < 0 leaves game g untouched (batched loops freeze finished games;
  * the reference itself has no guard).  reward: float64[n_games]; flags:

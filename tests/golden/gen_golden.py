@@ -449,6 +449,31 @@ def gen_mcts(pool, quick):
     return out
 
 
+# ---- self_play_game (self_play.py:178-312) with the injected evaluator ----------------------
+def selfplay_job(args):
+    seed, n_sims, temperature, opponent = args
+    chess_env, self_play = import_reference()
+    np.random.seed(seed)
+    net = StubNet(False)
+    opp = StubNet(True) if opponent else None
+    data, winner, reason = self_play.self_play_game(net, temperature=temperature,
+                                                    num_simulations=n_sims, opponent_network=opp)
+    return dict(seed=seed, n_sims=n_sims, temperature=temperature, opponent=bool(opponent),
+                winner=int(winner), end_reason=reason,
+                boards=[b.reshape(90).tolist() for b, _, _ in data],
+                moves=[[pack(m) for m in d.keys()] for _, d, _ in data],
+                probs=[[float(p) for p in d.values()] for _, d, _ in data],
+                rewards=[float(r) for _, _, r in data])
+
+
+def gen_selfplay(pool, quick):
+    jobs = [(1, 15, 1.0, False), (2, 30, 1.0, False), (3, 30, 0.5, False), (4, 50, 1.0, False),
+            (5, 30, 1.0, True), (6, 30, 0.001, False)]
+    if quick:
+        jobs = jobs[:2]
+    return pool.map(selfplay_job, jobs, chunksize=1)
+
+
 # ---- known-answer vectors ---------------------------------------------
 def gen_kats():
     chess_env, _ = import_reference()
@@ -589,6 +614,11 @@ def main():
             np.savez_compressed(os.path.join(HERE, "mcts.npz"), **mc)
             manifest["mcts_searches"] = int(len(mc["player"]))
             print("mcts", len(mc["player"]), time.time() - t0, flush=True)
+        if not only or "selfplay" in only:
+            sp = gen_selfplay(pool, a.quick)
+            json.dump(sp, open(os.path.join(HERE, "selfplay.json"), "w"), ensure_ascii=False)
+            manifest["selfplay_games"] = len(sp)
+            print("selfplay", len(sp), time.time() - t0, flush=True)
         if not only or "playouts" in only:
             nu, nb, nf = (32, 32, 8) if a.quick else (384, 640, 48)
             po, reasons, recs = gen_playouts(pool, nu, nb, nf)
