@@ -154,7 +154,7 @@ class ChineseChess:
         check(dev.lib.xq_step(_ptr(dev.board), _ptr(dev.meta), _ptr(dev.hist), dev.hist_cap,
                               _ptr(dev.move), _ptr(dev.reward), _ptr(dev.flags), None, None, 1,
                               _stream()))
-        m = dev.meta.cpu().numpy().view(META_DTYPE)[0]
+        m = dev.meta.cpu().numpy().view(META_DTYPE).reshape(-1)[0]
         flags = int(dev.flags[0])
         reward = float(dev.reward[0])
         self.board = dev.board[0, :90].cpu().numpy().reshape(BOARD_SIZE, BOARD_WIDTH).copy()
