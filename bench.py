@@ -34,6 +34,11 @@ SEED = 0x5EED
 BYTES_PER_STEP_LAUNCH_MODE = 352
 #   fused playout: (board+meta in 128, out 128, result 40) / 70 plies + one 8-byte history append
 BYTES_PER_STEP_FUSED = (128 + 128 + 40) / 70.0 + 8.0
+# warp-instructions per board-step of playout_kernel<false>, from ncu smsp__inst_executed.sum /
+# plies of the same launch (profiles/r1/playout_v1_ncu_summary.txt); refreshed with every capture
+WARP_INST_PER_STEP = 2534.0
+FLOP_PER_LEAF_EVAL = 263_209_216          # ChessNet.forward, SURVEY.md §8d
+MCTS_GAMES, MCTS_SIMS, MCTS_OPENING_PLIES = 4096, 15, 4
 METRIC = "board-steps/sec (legal movegen+step)"
 UNIT = "board-steps/s"
 
@@ -136,6 +141,65 @@ def run_reference(args):
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
+
+
+def measure_step_per_launch(torch, BoardBatch, n, first_id, steps, flush):
+    """API-faithful mode: one xq_pick_moves + one xq_step (which also returns the next legal
+    list) per ply, state round-trips through HBM every ply (352 algorithmic bytes/board-step)."""
+    bb = BoardBatch(n, hist_cap=PLIES + 2)
+    mv = torch.empty((n,), dtype=torch.int16, device=bb.device)
+
+    def one(k):
+        bb.reset()
+        bb.legal_moves()
+        for ply in range(PLIES):
+            bb.pick(SEED + k, ply, first_game_id=first_id, out=mv)
+            bb.step(mv, want_next=True)
+    one(1000)
+    torch.cuda.synchronize()
+    ms, plies = 0.0, 0
+    for k in range(steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        one(k)
+        b.record()
+        torch.cuda.synchronize()
+        ms += a.elapsed_time(b)
+        plies += int(bb.meta_host()["move_count"].sum())
+    return plies / (ms * 1e-3), ms / steps, 2 * PLIES + 2
+
+
+def measure_mcts(torch, dev, plies_timed=6):
+    """cfg 3: 4,096 concurrent self-play games, 15 sims/move (2 waves of 8+7), random-init ChessNet
+    (torch.manual_seed(0)), temperature 1.0; games diversified by 4 random opening plies."""
+    from chinesechessai_b200.neural_network import ChessNet
+    from chinesechessai_b200.self_play import BatchedSelfPlay
+    torch.manual_seed(0)
+    net = ChessNet().to(dev).eval()
+    sp = BatchedSelfPlay(net, MCTS_GAMES, MCTS_SIMS, temperature=1.0, device=dev,
+                         net_dtype=torch.bfloat16, seed=0)
+    sp.boards.playout(SEED, MCTS_OPENING_PLIES)          # diversify the batch
+    sp.play(3, check_done=False)                         # warm-up plies (cuDNN autotune etc.)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0 = sp.plies
+    a.record()
+    sp.play(plies_timed, check_done=False)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    played = int(sp.rec_played[p0:sp.plies].sum())
+    sims = played * MCTS_SIMS
+    waves = (MCTS_SIMS + 7) // 8
+    evals = played * waves
+    return {"metric": "MCTS sims/sec", "value": sims / (ms * 1e-3), "unit": "sims/s",
+            "config": {"workload": f"cfg3: {MCTS_GAMES} concurrent games, {MCTS_SIMS} sims/move, "
+                                   f"random-init ChessNet, T=1.0, {MCTS_OPENING_PLIES} random opening plies",
+                       "plies_timed": plies_timed, "nn_dtype": "bf16 autocast (reference: fp32)"},
+            "ms_per_ply": ms / plies_timed, "unique_leaf_evals_per_s": evals / (ms * 1e-3),
+            "roofline": {"bound": "tensor", "achieved": evals / (ms * 1e-3) * FLOP_PER_LEAF_EVAL / 1e12,
+                         "unit": "TFLOP/s", "flop_per_leaf_eval": FLOP_PER_LEAF_EVAL}}
 
 
 def run_ours(args):
@@ -274,6 +338,33 @@ def run_ours(args):
                              "(see profiles/ and DESIGN.md)"},
         "clocks": clk,
     }
+    sm_hz = (clk.get("sm_mhz") or 1965.0) * 1e6 if clk else 1965.0e6
+    issue_peak = 148 * 4 * sm_hz
+    kern_steps_per_s = plies_per_launch / kern_s
+    out["issue"] = {"achieved": kern_steps_per_s * WARP_INST_PER_STEP, "peak": issue_peak,
+                    "unit": "warp-inst/s", "frac": kern_steps_per_s * WARP_INST_PER_STEP / issue_peak,
+                    "warp_inst_per_board_step": WARP_INST_PER_STEP,
+                    "source": "ncu smsp__inst_executed.sum / plies (profiles/), peak = 148 SM x 4 x f_SM"}
+    if world == 1 and not args.fast:
+        v, ms, launches_per_step = measure_step_per_launch(torch, BoardBatch, n, first_id, 2, flush)
+        out["step_per_launch"] = {
+            "value": v, "unit": UNIT, "ms_per_step": ms, "launches_per_step": launches_per_step,
+            "roofline": {"bound": "hbm", "achieved": v * BYTES_PER_STEP_LAUNCH_MODE / 1e9,
+                         "peak": hbm_peak, "unit": "GB/s",
+                         "frac": v * BYTES_PER_STEP_LAUNCH_MODE / 1e9 / hbm_peak,
+                         "bytes_per_board_step": BYTES_PER_STEP_LAUNCH_MODE}}
+        out["gpu_launches"] += 3 * launches_per_step
+        l0 = lib.xq_launch_count()
+        mc = measure_mcts(torch, dev)
+        tf_peak = None
+        try:
+            tf_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"])
+        except Exception:
+            tf_peak = 1400.0
+        mc["roofline"]["peak"] = tf_peak
+        mc["roofline"]["frac"] = mc["roofline"]["achieved"] / tf_peak
+        mc["gpu_launches"] = int(lib.xq_launch_count() - l0)
+        out["mcts"] = mc
     # ---- CPU baseline: C port of the reference path on the host cores, bounded sample ------
     if world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
@@ -296,6 +387,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--boards", type=int, default=BOARDS)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--fast", action="store_true", help="skip the step-per-launch and MCTS legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

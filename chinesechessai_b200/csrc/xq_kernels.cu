@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include <cuda_bf16.h>
@@ -207,8 +208,8 @@ __global__ void __launch_bounds__(kThreads)
 // Fused random playout: state stays in shared memory / registers for all plies.
 __device__ __forceinline__ uint64_t dbits(double d) { return (uint64_t)__double_as_longlong(d); }
 
-template <bool TRACE>
-__global__ void __launch_bounds__(kThreads)
+template <bool TRACE, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
     playout_kernel(int8_t* __restrict__ board, xq_meta* __restrict__ meta,
                    uint64_t* __restrict__ pos_hist, int hist_cap, uint64_t seed,
                    uint32_t first_game_id, int max_plies, int capture_bias,
@@ -448,14 +449,25 @@ int xq_playout(int8_t* board, xq_meta* meta, uint64_t* pos_hist, int hist_cap, u
              "null pointer, negative size or hist_cap <= 0");
   XQ_REQUIRE(capture_bias >= 0 && capture_bias <= 256, "capture_bias out of [0,256]");
   const bool trace = tr_moves || tr_n || tr_pick || tr_reward || tr_flags || tr_boards;
-  if (trace)
-    playout_kernel<true><<<ctas_for(n_games), kThreads, 0, (cudaStream_t)stream>>>(
-        board, meta, pos_hist, hist_cap, seed, first_game_id, max_plies, capture_bias, results,
-        tr_moves, tr_n, tr_pick, tr_reward, tr_flags, tr_boards, n_games);
-  else
-    playout_kernel<false><<<ctas_for(n_games), kThreads, 0, (cudaStream_t)stream>>>(
-        board, meta, pos_hist, hist_cap, seed, first_game_id, max_plies, capture_bias, results,
-        nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, n_games);
+  // resident CTAs per SM the register allocation is bounded for (tuning knob; default 4 = 64 regs)
+  static const int minb = [] {
+    const char* e = getenv("XQ_PLAYOUT_MINB");
+    const int v = e ? atoi(e) : 4;
+    return v >= 2 && v <= 5 ? v : 4;
+  }();
+  const dim3 grid(ctas_for(n_games)), block(kThreads);
+  const cudaStream_t st = (cudaStream_t)stream;
+#define XQ_LAUNCH_PLAYOUT(T, M)                                                                  \
+  playout_kernel<T, M><<<grid, block, 0, st>>>(board, meta, pos_hist, hist_cap, seed,            \
+                                               first_game_id, max_plies, capture_bias, results, \
+                                               tr_moves, tr_n, tr_pick, tr_reward, tr_flags,     \
+                                               tr_boards, n_games)
+  if (trace) XQ_LAUNCH_PLAYOUT(true, 4);
+  else if (minb == 2) XQ_LAUNCH_PLAYOUT(false, 2);
+  else if (minb == 3) XQ_LAUNCH_PLAYOUT(false, 3);
+  else if (minb == 5) XQ_LAUNCH_PLAYOUT(false, 5);
+  else XQ_LAUNCH_PLAYOUT(false, 4);
+#undef XQ_LAUNCH_PLAYOUT
   return check_launch("xq_playout");
 }
 

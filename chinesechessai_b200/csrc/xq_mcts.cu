@@ -177,7 +177,7 @@ __device__ __forceinline__ void backup_path(const Tree& t, int node, double v) {
   }
 }
 
-__global__ void __launch_bounds__(kThreadsM)
+__global__ void __launch_bounds__(kThreadsM, 4)
     mcts_select_kernel(void* trees, int n_sims, int wave_size, int8_t* __restrict__ leaf_board,
                        int8_t* __restrict__ leaf_player, int16_t* __restrict__ leaf_moves,
                        int16_t* __restrict__ leaf_n, int16_t* __restrict__ leaf_mult, int n_games) {

@@ -193,6 +193,7 @@ class BatchedSelfPlay:
         self.rec_reward = torch.zeros((P, self.n), dtype=torch.float64, device=d)
         self.rec_played = torch.zeros((P, self.n), dtype=torch.bool, device=d)
         self.plies = 0
+        self.done = torch.zeros(self.n, dtype=torch.bool, device=d)
 
     def _search(self, active: torch.Tensor):
         m, b = self.mcts, self.boards
@@ -214,11 +215,14 @@ class BatchedSelfPlay:
         return m.visits()
 
     @torch.no_grad()
-    def play(self, max_plies: int = MAX_PLIES) -> None:
-        b, d = self.boards, self.device
-        done = torch.zeros(self.n, dtype=torch.bool, device=d)
+    def play(self, max_plies: int = MAX_PLIES, check_done: bool = True) -> None:
+        """Advance every unfinished game by up to ``max_plies`` further plies (the reference's
+        cap of MAX_MOVES plies per game applies to the total).  ``check_done=False`` skips the
+        per-ply "all games over?" host read (benchmarks that time a fixed number of plies)."""
+        b = self.boards
+        done = self.done
         inv_t = 1.0 / self.temperature if self.temperature >= 0.01 else None
-        for ply in range(max_plies):
+        for ply in range(self.plies, min(MAX_PLIES, self.plies + max_plies)):
             active = (~done).to(torch.uint8)
             mv, vis, nc = self._search(active)
             live = (nc > 0) & ~done  # self_play.py:207,216: no legal move / empty search ends the game
@@ -242,8 +246,9 @@ class BatchedSelfPlay:
             reward, flags = b.step(move.contiguous())
             self.rec_reward[ply].copy_(reward)
             done = done | ~live | ((flags & 1) != 0)
+            self.done = done
             self.plies = ply + 1
-            if bool(done.all()):
+            if check_done and bool(done.all()):
                 break
 
     def stats(self) -> Dict[str, int]:
