@@ -88,6 +88,8 @@ __global__ void __launch_bounds__(kThreads)
                        int16_t* __restrict__ moves, int16_t* __restrict__ n_moves,
                        uint8_t* __restrict__ in_check_out, int n_games) {
   __shared__ WarpSmem slab[kWarpsPerCta];
+  __shared__ uint32_t s_leap[32];
+  load_leap_table(s_leap);
   const int g = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   if (g >= n_games) return;
   WarpSmem& w = slab[threadIdx.x >> 5];
@@ -96,7 +98,7 @@ __global__ void __launch_bounds__(kThreads)
   build_masks(w);
   Game G = load_meta(meta + g);
   const int flags0 = G.flags;
-  const int n = movegen(w, G);
+  const int n = movegen(w, G, s_leap);
   int16_t* row = moves + (size_t)g * XQ_MAX_MOVES;
   for (int i = lane; i < n; i += 32) row[i] = w.moves[i];
   if (lane == 0) {
@@ -145,6 +147,8 @@ __global__ void __launch_bounds__(kThreads)
                 double* __restrict__ reward, uint8_t* __restrict__ flags,
                 int16_t* __restrict__ next_moves, int16_t* __restrict__ next_n, int n_games) {
   __shared__ WarpSmem slab[kWarpsPerCta];
+  __shared__ uint32_t s_leap[32];
+  load_leap_table(s_leap);
   const int g = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   if (g >= n_games) return;
   WarpSmem& w = slab[threadIdx.x >> 5];
@@ -162,7 +166,8 @@ __global__ void __launch_bounds__(kThreads)
   load_board(w, board + (size_t)g * XQ_BOARD_STRIDE);
   build_masks(w);
   Game G = load_meta(meta + g);
-  const StepOut o = step(w, G, mv, pos_hist + (size_t)g * hist_cap, hist_cap);
+  G.bkey = board_key(w);
+  const StepOut o = step(w, G, mv, pos_hist + (size_t)g * hist_cap, hist_cap, s_leap);
   store_board(w, board + (size_t)g * XQ_BOARD_STRIDE);
   store_meta(meta + g, G);
   if (lane == 0) {
@@ -218,6 +223,8 @@ __global__ void __launch_bounds__(kThreads, MINB)
                    double* __restrict__ tr_reward, uint8_t* __restrict__ tr_flags,
                    int8_t* __restrict__ tr_boards, int n_games) {
   __shared__ WarpSmem slab[kWarpsPerCta];
+  __shared__ uint32_t s_leap[32];
+  load_leap_table(s_leap);
   const int g = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   if (g >= n_games) return;
   WarpSmem& w = slab[threadIdx.x >> 5];
@@ -225,60 +232,73 @@ __global__ void __launch_bounds__(kThreads, MINB)
   load_board(w, board + (size_t)g * XQ_BOARD_STRIDE);
   build_masks(w);
   Game G = load_meta(meta + g);
+  G.bkey = board_key(w);
   uint64_t* hist = pos_hist + (size_t)g * hist_cap;
   const uint32_t gid = first_game_id + (uint32_t)g;
 
-  uint64_t digest = 0;
+  uint64_t digest = 0, word_a = 0;
   double rsum = 0.0;
   int max_legal = 0, ply = 0;
-  int n = movegen(w, G);
-  for (; ply < max_plies; ++ply) {
-    if (n == 0) break;  // self_play.py:207
-    max_legal = max(max_legal, n);
-    const int idx = pick_index(w, n, seed, gid, (uint32_t)ply, capture_bias);
-    const int mv = w.moves[idx];
-    uint64_t lsum = 0;
-    for (int i = lane; i < n; i += 32)
-      lsum += mix64(((uint64_t)(ply + 1) << 40) | ((uint64_t)(i + 1) << 20) |
-                    (uint64_t)(uint16_t)w.moves[i]);
-    lsum = warp_add64(lsum);
-    if (TRACE) {
-      const size_t t = (size_t)g * max_plies + ply;
-      if (tr_moves)
-        for (int i = lane; i < n; i += 32) tr_moves[t * XQ_MAX_MOVES + i] = w.moves[i];
-      if (lane == 0) {
-        if (tr_n) tr_n[t] = (int16_t)n;
-        if (tr_pick) tr_pick[t] = (int16_t)mv;
-      }
-    }
-    __syncwarp();
-    const StepOut o = step(w, G, mv, hist, hist_cap);
+  bool pending = false;  // a move was applied; its terminal chain waits for the movegen below
+  StepOut o;
+  o.done = 0;
+  // Bookkeeping of one finished make_move: reward sum, digest chain, traces.
+  auto account = [&]() {
     rsum = __dadd_rn(rsum, o.reward);
-    uint64_t wsum = lsum;
-    wsum += mix64(0xA5A5000000000000ULL ^ ((uint64_t)n << 16) ^ (uint64_t)mv);
-    wsum += o.key_next;
-    wsum += mix64(dbits(o.reward));
-    wsum += mix64(0x5151000000000000ULL | (uint64_t)(o.done & 1) | ((uint64_t)(G.winner + 2) << 8) |
-                  ((uint64_t)G.reason << 16) | ((uint64_t)(o.is_int & 1) << 24));
-    digest = mix64(digest + wsum);
+    const uint64_t word_c = (uint64_t)(o.done & 1) | ((uint64_t)(G.winner + 2) << 8) |
+                            ((uint64_t)G.reason << 16) | ((uint64_t)(o.is_int & 1) << 24);
+    const uint64_t t = word_a * 0x9E3779B97F4A7C15ULL + dbits(o.reward) * 0xC2B2AE3D27D4EB4FULL +
+                       word_c * 0x165667B19E3779F9ULL + o.key_next * 0x27D4EB2F165667C5ULL;
+    digest = mix64(digest ^ t);
     if (TRACE) {
-      const size_t t = (size_t)g * max_plies + ply;
+      const size_t tt = (size_t)g * max_plies + ply;
       if (lane == 0) {
-        if (tr_reward) tr_reward[t] = o.reward;
-        if (tr_flags) tr_flags[t] = step_flags(G, o);
+        if (tr_reward) tr_reward[tt] = o.reward;
+        if (tr_flags) tr_flags[tt] = step_flags(G, o);
       }
       if (tr_boards) {
         __syncwarp();
-        for (int s = lane; s < XQ_NSQ; s += 32) tr_boards[t * XQ_NSQ + s] = w.sq[s];
+        for (int s = lane; s < XQ_NSQ; s += 32) tr_boards[tt * XQ_NSQ + s] = w.sq[s];
       }
     }
-    if (o.done) {
-      ++ply;
+    ++ply;
+  };
+  // One movegen site per iteration: it closes the previous make_move (:354,:376 need the new
+  // side's move count) and is the get_legal_moves of the next ply (self_play.py:205).
+  for (;;) {
+    const int n = movegen(w, G, s_leap);
+    if (pending) {
+      step_finish(w, G, o, n, hist);
+      pending = false;
+      account();
+      if (o.done) break;
+    }
+    if (ply >= max_plies || n == 0) break;  // self_play.py:203,207
+    max_legal = max(max_legal, n);
+    const int idx = pick_index(w, n, seed, gid, (uint32_t)ply, capture_bias);
+    const int mv = w.moves[idx];
+    unsigned lsum = 0;
+    for (int i = lane; i < n; i += 32) lsum += (unsigned)((int)w.moves[i] + 1) * (unsigned)(2 * i + 1);
+    lsum = __reduce_add_sync(kFull, lsum);
+    word_a = (uint64_t)lsum | ((uint64_t)n << 32) | ((uint64_t)mv << 40) | ((uint64_t)(ply + 1) << 54);
+    if (TRACE) {
+      const size_t tt = (size_t)g * max_plies + ply;
+      if (tr_moves)
+        for (int i = lane; i < n; i += 32) tr_moves[tt * XQ_MAX_MOVES + i] = w.moves[i];
+      if (lane == 0) {
+        if (tr_n) tr_n[tt] = (int16_t)n;
+        if (tr_pick) tr_pick[tt] = (int16_t)mv;
+      }
+    }
+    __syncwarp();
+    o = step_apply(w, G, mv, hist, hist_cap);
+    if (o.done) {  // king capture: make_move skips the terminal chain (:352)
+      account();
       break;
     }
-    n = o.n_next;
+    pending = true;
   }
-  const uint64_t fkey = board_key(w) ^ side_key(G.player);
+  const uint64_t fkey = G.bkey ^ side_key(G.player);
   store_board(w, board + (size_t)g * XQ_BOARD_STRIDE);
   store_meta(meta + g, G);
   if (lane == 0) {

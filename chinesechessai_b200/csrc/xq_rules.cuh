@@ -77,23 +77,27 @@ constexpr unsigned kFull = 0xffffffffu;
 
 enum : int { KING = 1, ADVISOR = 2, BISHOP = 3, KNIGHT = 4, ROOK = 5, CANNON = 6, PAWN = 7 };
 
-// Per-warp shared-memory slab (1024 B).
+// Per-warp shared-memory slab (1536 B).
 struct XQ_ALIGN16 WarpSmem {
   int8_t sq[XQ_BOARD_STRIDE];  // board, row-major r*9+c (chess_env.py:17)
   uint16_t rows[16];           // rows[r] bit c = square (r,c) occupied
   uint16_t cols[16];           // cols[c] bit r = square (r,c) occupied
   uint8_t own[96];             // squares of the side-to-move's pieces, row-major order
-  uint8_t cf[XQ_CAND_CAP];     // candidate from-squares (canonical order)
-  uint8_t ct[XQ_CAND_CAP];     // candidate to-squares
+  // candidates in canonical order: from<<8 | to; bit 7 = "cannot affect king safety"
+  // (legal iff the position itself is safe), bit 15 = tested and found illegal
+  uint16_t cand[XQ_CAND_CAP];
+  uint16_t wl[XQ_CAND_CAP];    // worklist of candidate indices that need the full test
   int16_t moves[XQ_MAX_MOVES]; // legal moves, packed from*90+to
 };
-static_assert(sizeof(WarpSmem) == 1024, "WarpSmem must be 1 KB");
+static_assert(sizeof(WarpSmem) == 1536, "WarpSmem must be 1.5 KB");
+constexpr uint16_t kCandIrrelevant = 0x0080, kCandIllegal = 0x8000, kWlSentinel = 0xFFFF;
 
 // Warp-uniform game scalars (chess_env.py:17-31,62-65).
 struct Game {
   int player, winner, reason, done, red_king, black_king, flags;
   int move_count, no_capture, cchecks, hist_len, check_len;
   unsigned check_bits;
+  uint64_t bkey;  // position key of the staged board without the side byte (kept incrementally)
 };
 
 
@@ -123,6 +127,7 @@ __device__ __forceinline__ uint64_t warp_add64(uint64_t v) {
 XQ_HD uint64_t side_key(int player) {
   return mix64(0x7000ULL + (player == 1 ? 0u : 1u));  // chess_env.py:503
 }
+XQ_HD uint64_t piece_key(int piece, int s) { return mix64((uint64_t)((piece + 8) * 128 + s)); }
 
 #if defined(__CUDACC__)
 
@@ -135,7 +140,7 @@ __device__ __forceinline__ uint64_t board_key(const WarpSmem& w) {
   for (int k = 0; k < 3; ++k) {
     int s = lane + 32 * k;
     int p = (s < XQ_NSQ) ? w.sq[s] : 0;
-    if (p != 0) h ^= mix64((uint64_t)((p + 8) * 128 + s));
+    if (p != 0) h ^= piece_key(p, s);
   }
   return warp_xor64(h);
 }
@@ -302,7 +307,51 @@ XQ_HD bool attacked(const WarpSmem& w, int K, int es, int geo, int from,
   return hit;
 }
 
-// _is_in_check(player) on the staged board (chess_env.py:506-548).
+// One of the 8 probes of attacked() on the staged board without an override: dir 0..3 =
+// rays (0,+1),(0,-1),(+1,0),(-1,0); dir 4..7 = the diagonal neighbours.  The OR over the
+// 8 directions equals attacked(w, K, es, geo, -1, -1, 0, true) — one lane per direction
+// gives the warp-parallel check test of make_move (:317).
+XQ_HD bool attacked_dir(const WarpSmem& w, int K, int es, int geo, int dir) {
+  const int kr = K / 9, kc = K - kr * 9;
+  const bool in_pal = (kc >= 3 && kc <= 5) && (geo == 1 ? kr >= 7 : kr <= 2);
+  if (dir < 4) {
+    const bool horiz = dir < 2, fwd = (dir & 1) == 0;
+    const int len = horiz ? 9 : 10;
+    unsigned m = horiz ? w.rows[kr] : w.cols[kc];
+    int x = horiz ? kc : kr;
+    const bool kocc = (m >> x) & 1u;
+    if (!fwd) {
+      m = xq_brev(m) >> (32 - len);
+      x = len - 1 - x;
+    }
+    const int delta = (horiz ? 1 : 9) * (fwd ? 1 : -1);
+    const unsigned a = m >> (x + 1);
+    if (!a) return false;
+    const int d1 = xq_ffs(a), q = w.sq[K + d1 * delta];
+    const bool pawn_dir = horiz ? (geo == 1 ? kr < 5 : kr >= 5) : (geo == (fwd ? 1 : -1));
+    bool hit = (q == es * ROOK) | (q == es * CANNON && !kocc) |
+               (d1 == 1 && ((q == es * PAWN && pawn_dir) | (q == es * KING && in_pal)));
+    const unsigned a2 = a & (a - 1);
+    if (kocc && a2) hit |= w.sq[K + xq_ffs(a2) * delta] == es * CANNON;
+    return hit;
+  }
+  const int i = dir - 4;
+  const int a = (i & 2) ? 1 : -1, b = (i & 1) ? 1 : -1;
+  const int lr = kr + a, lc = kc + b;
+  if (lr < 0 || lr > 9 || lc < 0 || lc > 8) return false;
+  const int ql = w.sq[lr * 9 + lc];
+  if (ql != 0) return in_pal && ql == es * ADVISOR;
+  const int r2 = kr + 2 * a, c2 = kc + 2 * b;
+  const bool r2ok = r2 >= 0 && r2 <= 9, c2ok = c2 >= 0 && c2 <= 8;
+  const bool bside = geo == 1 ? kr >= 5 : kr <= 3;
+  bool hit = false;
+  if (r2ok) hit |= w.sq[r2 * 9 + lc] == es * KNIGHT;
+  if (c2ok) hit |= w.sq[lr * 9 + c2] == es * KNIGHT;
+  if (bside && r2ok && c2ok) hit |= w.sq[r2 * 9 + c2] == es * BISHOP;
+  return hit;
+}
+
+// _is_in_check(player) on the staged board (chess_env.py:506-548), single-lane form.
 XQ_HD bool in_check(const WarpSmem& w, const Game& g, int player) {
   const int K = player == 1 ? g.red_king : g.black_king;
   if (K < 0) return false;  // :517
@@ -312,9 +361,9 @@ XQ_HD bool in_check(const WarpSmem& w, const Game& g, int player) {
 // _is_move_suicide (chess_env.py:431-464): own king attacked after the move
 // (geometry of the side to move) OR cached kings face each other (:466-495;
 // only the MOVING king's cache is refreshed, :448-451 — stale-cache quirk A.4).
-XQ_HD bool suicide(const WarpSmem& w, const Game& g, int from, int to,
-                                        bool exotic) {
-  const int mover = w.sq[from];
+// from < 0 evaluates the position itself (no move).
+XQ_HD bool suicide(const WarpSmem& w, const Game& g, int from, int to, bool exotic) {
+  const int mover = from >= 0 ? (int)w.sq[from] : 0;
   int red = g.red_king, black = g.black_king;
   if (mover == KING) red = to;
   else if (mover == -KING) black = to;
@@ -325,13 +374,21 @@ XQ_HD bool suicide(const WarpSmem& w, const Game& g, int from, int to,
   if (red >= 0 && black >= 0) {
     const int rr = red / 9, rc = red - rr * 9, br = black / 9, bc = black - br * 9;
     if (rc == bc) {
-      if (K < 0) return bad;  // unreachable: both caches set implies K >= 0
       const int lo = xq_min(rr, br), hi = xq_max(rr, br);
       const unsigned between = ((1u << hi) - 1u) & ~((2u << lo) - 1u);
       bad |= (colm & between) == 0;
     }
   }
   return bad;
+}
+
+// Squares whose content attacked()/facing can read for a king on (kr,kc) when the K/A/B
+// probes are off: its row, its column, the 4 diagonal neighbours and the 8 knight squares.
+// A non-king move touching none of them leaves the king exactly as safe as it is now.
+XQ_HD bool touches(int kr, int kc, int s) {
+  const int r = s / 9, c = s - r * 9;
+  const int dr = xq_abs(r - kr), dc = xq_abs(c - kc);
+  return dr == 0 || dc == 0 || (dr <= 2 && dc <= 2 && dr + dc <= 3);
 }
 
 // ---- move generation --------------------------------------------------------
@@ -344,12 +401,37 @@ struct Item {
   int from, empties, delta, e1, e2;
 };
 
-XQ_HD Item gen_item(const WarpSmem& w, int player, int from, int d) {
+// Leaper table, entry [piece_type*4 + d]: byte0/byte1 = targets, byte2 = square that must be
+// empty (knight leg :189-195, bishop eye :171-174), each (dr+2)|(dc+2)<<3 or 0xFF = none;
+// byte3 = zone: 0 on-board, 1 palace of the side to move (:127-131,:143-147), 2 own side of
+// the river (:159-170), 3 pawn forward (dr is multiplied by the side, :241,:246), 4 pawn
+// sideways (needs a crossed pawn, :242,:247).
+#define XQ_OFF(dr, dc) (uint32_t)(((dr) + 2) | (((dc) + 2) << 3))
+#define XQ_LEAP(t1, t2, bk, zone) ((t1) | ((t2) << 8) | ((bk) << 16) | ((uint32_t)(zone) << 24))
+#define XQ_NONE 0xFFu
+#define XQ_LEAPER_TABLE_INIT                                                                      \
+  {0, 0, 0, 0, /* KING */                                                                         \
+   XQ_LEAP(XQ_OFF(0, 1), XQ_NONE, XQ_NONE, 1), XQ_LEAP(XQ_OFF(0, -1), XQ_NONE, XQ_NONE, 1),       \
+   XQ_LEAP(XQ_OFF(1, 0), XQ_NONE, XQ_NONE, 1), XQ_LEAP(XQ_OFF(-1, 0), XQ_NONE, XQ_NONE, 1),       \
+   /* ADVISOR */                                                                                  \
+   XQ_LEAP(XQ_OFF(1, 1), XQ_NONE, XQ_NONE, 1), XQ_LEAP(XQ_OFF(1, -1), XQ_NONE, XQ_NONE, 1),       \
+   XQ_LEAP(XQ_OFF(-1, 1), XQ_NONE, XQ_NONE, 1), XQ_LEAP(XQ_OFF(-1, -1), XQ_NONE, XQ_NONE, 1),     \
+   /* BISHOP */                                                                                   \
+   XQ_LEAP(XQ_OFF(2, 2), XQ_NONE, XQ_OFF(1, 1), 2), XQ_LEAP(XQ_OFF(2, -2), XQ_NONE, XQ_OFF(1, -1), 2),     \
+   XQ_LEAP(XQ_OFF(-2, 2), XQ_NONE, XQ_OFF(-1, 1), 2), XQ_LEAP(XQ_OFF(-2, -2), XQ_NONE, XQ_OFF(-1, -1), 2), \
+   /* KNIGHT: offset pairs sharing a leg (:182-187) */                                            \
+   XQ_LEAP(XQ_OFF(2, 1), XQ_OFF(2, -1), XQ_OFF(1, 0), 0), XQ_LEAP(XQ_OFF(-2, 1), XQ_OFF(-2, -1), XQ_OFF(-1, 0), 0), \
+   XQ_LEAP(XQ_OFF(1, 2), XQ_OFF(-1, 2), XQ_OFF(0, 1), 0), XQ_LEAP(XQ_OFF(1, -2), XQ_OFF(-1, -2), XQ_OFF(0, -1), 0), \
+   0, 0, 0, 0, /* ROOK */ 0, 0, 0, 0, /* CANNON */                                                \
+   /* PAWN: forward, left, right (:241-249) */                                                    \
+   XQ_LEAP(XQ_OFF(-1, 0), XQ_NONE, XQ_NONE, 3), XQ_LEAP(XQ_OFF(0, -1), XQ_NONE, XQ_NONE, 4),      \
+   XQ_LEAP(XQ_OFF(0, 1), XQ_NONE, XQ_NONE, 4), XQ_LEAP(XQ_NONE, XQ_NONE, XQ_NONE, 0)}
+
+XQ_HD Item gen_item(const WarpSmem& w, const uint32_t* __restrict__ leap, int player, int from, int d) {
   Item it{from, 0, 0, -1, -1};
   const int p = w.sq[from];
   const int pt = p < 0 ? -p : p;
   const int r = from / 9, c = from - r * 9;
-  auto free_sq = [&](int s) -> bool { return (int)w.sq[s] * player <= 0; };  // :116
   if (pt == ROOK || pt == CANNON) {  // :199-235, rays (0,1),(0,-1),(1,0),(-1,0)
     const bool horiz = d < 2, fwd = (d & 1) == 0;
     const int len = horiz ? 9 : 10;
@@ -370,51 +452,33 @@ XQ_HD Item gen_item(const WarpSmem& w, int player, int from, int d) {
     }
     if (hitd) {
       const int s = from + hitd * it.delta;
-      if (free_sq(s)) it.e1 = s;
+      if ((int)w.sq[s] * player <= 0) it.e1 = s;  // :116
     }
-  } else if (pt == KNIGHT) {  // :178-197, offsets in pairs sharing a leg
-    const int lr = r + (d == 0 ? 1 : d == 1 ? -1 : 0), lc = c + (d == 2 ? 1 : d == 3 ? -1 : 0);
-    if (lr >= 0 && lr <= 9 && lc >= 0 && lc <= 8 && w.sq[lr * 9 + lc] == 0) {
-      int r1, c1, r2, c2;
-      if (d < 2) {
-        r1 = r2 = r + (d == 0 ? 2 : -2);
-        c1 = c + 1;
-        c2 = c - 1;
-      } else {
-        c1 = c2 = c + (d == 2 ? 2 : -2);
-        r1 = r + 1;
-        r2 = r - 1;
-      }
-      if (r1 >= 0 && r1 <= 9 && c1 >= 0 && c1 <= 8 && free_sq(r1 * 9 + c1)) it.e1 = r1 * 9 + c1;
-      if (r2 >= 0 && r2 <= 9 && c2 >= 0 && c2 <= 8 && free_sq(r2 * 9 + c2)) it.e2 = r2 * 9 + c2;
+    return it;
+  }
+  if (pt < KING || pt > PAWN) return it;
+  const uint32_t e = leap[pt * 4 + d];
+  const int zone = (int)(e >> 24);
+  const uint32_t bk = (e >> 16) & 0xFFu;
+  bool ok = true;
+  if (bk != XQ_NONE) {
+    const int br = r + (int)(bk & 7u) - 2, bc = c + (int)((bk >> 3) & 7u) - 2;
+    ok = br >= 0 && br <= 9 && bc >= 0 && bc <= 8 && w.sq[br * 9 + bc] == 0;
+  }
+  if (zone == 4) ok = player == 1 ? r < 5 : r >= 5;
+  const int sgn = zone == 3 ? player : 1;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const uint32_t t = (e >> (8 * k)) & 0xFFu;
+    if (!ok || t == XQ_NONE) continue;
+    const int nr = r + ((int)(t & 7u) - 2) * sgn, nc = c + (int)((t >> 3) & 7u) - 2;
+    bool good = nr >= 0 && nr <= 9 && nc >= 0 && nc <= 8;
+    if (zone == 1) good = good && nc >= 3 && nc <= 5 && (player == 1 ? nr >= 7 : nr <= 2);
+    if (zone == 2) good = good && (player == 1 ? nr >= 5 : nr <= 3);
+    if (good && (int)w.sq[nr * 9 + nc] * player <= 0) {
+      if (k == 0) it.e1 = nr * 9 + nc;
+      else it.e2 = nr * 9 + nc;
     }
-  } else if (pt == KING || pt == ADVISOR) {  // :123-154, palace of the side to move
-    int dr, dc;
-    if (pt == KING) {
-      dr = d == 2 ? 1 : d == 3 ? -1 : 0;
-      dc = d == 0 ? 1 : d == 1 ? -1 : 0;
-    } else {
-      dr = d < 2 ? 1 : -1;
-      dc = (d & 1) ? -1 : 1;
-    }
-    const int nr = r + dr, nc = c + dc;
-    const bool pal = nc >= 3 && nc <= 5 && (player == 1 ? (nr >= 7 && nr <= 9) : (nr >= 0 && nr <= 2));
-    if (pal && free_sq(nr * 9 + nc)) it.e1 = nr * 9 + nc;
-  } else if (pt == BISHOP) {  // :156-176 (black river = 4: rows 0..3 only)
-    const int dr = d < 2 ? 2 : -2, dc = (d & 1) ? -2 : 2;
-    const int nr = r + dr, nc = c + dc;
-    if (nr >= 0 && nr <= 9 && nc >= 0 && nc <= 8 && (player == 1 ? nr >= 5 : nr <= 3) &&
-        w.sq[(r + dr / 2) * 9 + c + dc / 2] == 0 && free_sq(nr * 9 + nc))
-      it.e1 = nr * 9 + nc;
-  } else if (pt == PAWN) {  // :237-251
-    const bool crossed = player == 1 ? r < 5 : r >= 5;
-    int nr = r, nc = c;
-    bool ok = true;
-    if (d == 0) nr = r - player;
-    else if (d == 1) { nc = c - 1; ok = crossed; }
-    else if (d == 2) { nc = c + 1; ok = crossed; }
-    else ok = false;
-    if (ok && nr >= 0 && nr <= 9 && nc >= 0 && nc <= 8 && free_sq(nr * 9 + nc)) it.e1 = nr * 9 + nc;
   }
   return it;
 }
@@ -434,12 +498,24 @@ XQ_HD bool regular_king(const WarpSmem& w, int player, int own_king, int n_own_k
 }
 
 #if defined(__CUDACC__)
+static __constant__ uint32_t c_leap[32] = XQ_LEAPER_TABLE_INIT;
+
+// Copies the leaper table into shared memory (divergent lookups from constant memory would
+// serialise).  Must be called by every thread of the CTA before any early return.
+__device__ __forceinline__ void load_leap_table(uint32_t* s_leap) {
+  if (threadIdx.x < 32) s_leap[threadIdx.x] = c_leap[threadIdx.x];
+  __syncthreads();
+}
+
+__device__ __forceinline__ int warp_sum(int v) { return (int)__reduce_add_sync(kFull, (unsigned)v); }
+
 // get_legal_moves (chess_env.py:76-121).  Fills w.moves in the reference's
 // order and returns the count.
-// Phase A: work item = (own piece, direction) -> candidate list via an ordered
-// warp scan.  Phase B: 32 candidates per round through suicide(), ordered
-// compaction with ballot/popc.
-__device__ __forceinline__ int movegen(WarpSmem& w, Game& g) {
+// Phase A: work item = (own piece, direction) -> candidate list via an ordered warp scan.
+// Phase B: candidates that can change the king's safety (or all of them on irregular boards)
+// go through suicide() 32 per round; the others inherit the verdict of the position itself.
+// Ordered compaction with ballot/popc.
+__device__ __forceinline__ int movegen(WarpSmem& w, Game& g, const uint32_t* __restrict__ leap) {
   const int lane = lane_id();
   const unsigned lt = (1u << lane) - 1u;
   const int player = g.player;
@@ -468,7 +544,7 @@ __device__ __forceinline__ int movegen(WarpSmem& w, Game& g) {
   for (int base = 0; base < n_items; base += 32) {
     const int t = base + lane;
     Item it{0, 0, 0, -1, -1};
-    if (t < n_items) it = gen_item(w, player, w.own[t >> 2], t & 3);
+    if (t < n_items) it = gen_item(w, leap, player, w.own[t >> 2], t & 3);
     const int cnt = it.empties + (it.e1 >= 0) + (it.e2 >= 0);
     int incl = cnt;
 #pragma unroll
@@ -483,29 +559,67 @@ __device__ __forceinline__ int movegen(WarpSmem& w, Game& g) {
     }
     int off = ncand + incl - cnt;
     ncand += total;
-    for (int k = 1; k <= it.empties; ++k, ++off) {
-      w.cf[off] = (uint8_t)it.from;
-      w.ct[off] = (uint8_t)(it.from + k * it.delta);
-    }
-    if (it.e1 >= 0) { w.cf[off] = (uint8_t)it.from; w.ct[off] = (uint8_t)it.e1; ++off; }
-    if (it.e2 >= 0) { w.cf[off] = (uint8_t)it.from; w.ct[off] = (uint8_t)it.e2; }
+    const int fs = it.from << 8;
+    for (int k = 1; k <= it.empties; ++k, ++off) w.cand[off] = (uint16_t)(fs | (it.from + k * it.delta));
+    if (it.e1 >= 0) w.cand[off++] = (uint16_t)(fs | it.e1);
+    if (it.e2 >= 0) w.cand[off] = (uint16_t)(fs | it.e2);
   }
   __syncwarp();
 
-  // Phase B
+  // Phase B.1: classify, build the worklist
+  const int kr = ownK >= 0 ? ownK / 9 : 0, kc = ownK >= 0 ? ownK - kr * 9 : 0;
+  int nwl = 0;
+  bool any_irrelevant = false;
+  for (int base = 0; base < ncand; base += 32) {
+    const int j = base + lane;
+    bool rel = false, valid = j < ncand;
+    if (valid) {
+      const int c = w.cand[j], from = c >> 8, to = c & 0x7f;
+      rel = exotic || from == ownK || touches(kr, kc, from) || touches(kr, kc, to);
+      if (!rel) w.cand[j] = (uint16_t)(c | kCandIrrelevant);
+    }
+    const unsigned m = __ballot_sync(kFull, rel);
+    if (rel) w.wl[nwl + __popc(m & lt)] = (uint16_t)j;
+    nwl += __popc(m);
+    any_irrelevant |= __ballot_sync(kFull, valid && !rel) != 0;
+  }
+  if (any_irrelevant && lane == 0) w.wl[nwl] = kWlSentinel;  // nwl < ncand <= XQ_CAND_CAP here
+  nwl += any_irrelevant ? 1 : 0;
+  __syncwarp();
+
+  // Phase B.2: full legality test of the worklist (:118)
+  bool cur_bad = false;
+  for (int base = 0; base < nwl; base += 32) {
+    const int i = base + lane;
+    bool is_cur = false, bad = false;
+    if (i < nwl) {
+      const int item = w.wl[i];
+      is_cur = item == kWlSentinel;
+      if (is_cur) {
+        bad = suicide(w, g, -1, -1, exotic);
+      } else {
+        const int c = w.cand[item];
+        bad = suicide(w, g, c >> 8, c & 0x7f, exotic);
+        if (bad) w.cand[item] = (uint16_t)(c | kCandIllegal);
+      }
+    }
+    cur_bad |= __ballot_sync(kFull, is_cur && bad) != 0;
+  }
+  __syncwarp();
+
+  // Phase B.3: ordered compaction
   int n_legal = 0;
   for (int base = 0; base < ncand; base += 32) {
     const int j = base + lane;
     bool ok = false;
-    int from = 0, to = 0;
+    int c = 0;
     if (j < ncand) {
-      from = w.cf[j];
-      to = w.ct[j];
-      ok = !suicide(w, g, from, to, exotic);  // :118
+      c = w.cand[j];
+      ok = (c & kCandIrrelevant) ? !cur_bad : !(c & kCandIllegal);
     }
     const unsigned m = __ballot_sync(kFull, ok);
     const int idx = n_legal + __popc(m & lt);
-    if (ok && idx < XQ_MAX_MOVES) w.moves[idx] = (int16_t)(from * 90 + to);
+    if (ok && idx < XQ_MAX_MOVES) w.moves[idx] = (int16_t)(((c >> 8) & 0x7f) * 90 + (c & 0x7f));
     n_legal += __popc(m);
   }
   if (n_legal > XQ_MAX_MOVES) {
@@ -514,6 +628,15 @@ __device__ __forceinline__ int movegen(WarpSmem& w, Game& g) {
   }
   __syncwarp();
   return n_legal;
+}
+
+// _is_in_check(player) with one lane per probe direction (chess_env.py:506-548).
+__device__ __forceinline__ bool in_check_warp(const WarpSmem& w, const Game& g, int player) {
+  const int K = player == 1 ? g.red_king : g.black_king;
+  if (K < 0) return false;  // :517 (warp-uniform)
+  const int lane = lane_id();
+  const bool hit = lane < 8 ? attacked_dir(w, K, -player, g.player, lane) : false;
+  return __any_sync(kFull, hit);
 }
 #endif  // __CUDACC__
 
@@ -551,9 +674,10 @@ struct StepOut {
   uint64_t key_next;  // position key of the new board ‖ new side to move
 };
 
-// make_move (chess_env.py:253-406).  hist: this game's position_history row.
-__device__ __forceinline__ StepOut step(WarpSmem& w, Game& g, int move, uint64_t* __restrict__ hist,
-                                        int hist_cap) {
+// make_move part 1 (chess_env.py:253-349): apply, caches, capture/check/positional reward,
+// history appends, side switch.  o.done is set only by a king capture (:292-297).
+__device__ __forceinline__ StepOut step_apply(WarpSmem& w, Game& g, int move,
+                                              uint64_t* __restrict__ hist, int hist_cap) {
   const int lane = lane_id();
   const int from = move / 90, to = move - from * 90;
   const int captured = w.sq[to], moving = w.sq[from];  // :265-266
@@ -571,6 +695,15 @@ __device__ __forceinline__ StepOut step(WarpSmem& w, Game& g, int move, uint64_t
       w.rows[tr] &= ~(1u << tc);
       w.cols[tc] &= ~(1u << tr);
     }
+  }
+  {  // incremental position key: three (piece, square) keys on three lanes
+    uint64_t x = 0;
+    if (lane == 0 && moving != 0) x = piece_key(moving, from);
+    if (lane == 1 && moving != 0) x = piece_key(moving, to);
+    if (lane == 2 && captured != 0) x = piece_key(captured, to);
+    x ^= __shfl_xor_sync(kFull, x, 1);
+    x ^= __shfl_xor_sync(kFull, x, 2);
+    g.bkey ^= __shfl_sync(kFull, x, 0);
   }
   __syncwarp();
 
@@ -597,8 +730,8 @@ __device__ __forceinline__ StepOut step(WarpSmem& w, Game& g, int move, uint64_t
     if (acap == ADVISOR || acap == BISHOP) reward = xq_dadd(reward, 3.0);
   }
 
-  const bool checking = in_check(w, g, -g.player);  // :317, geometry = mover
-  if (!done && checking) {                           // :318-327
+  const bool checking = in_check_warp(w, g, -g.player);  // :317, geometry = mover
+  if (!done && checking) {                                // :318-327
     if (g.cchecks == 0) { reward = xq_dadd(reward, 15.0); is_int = 0; }
     else if (g.cchecks == 1) { reward = xq_dadd(reward, 10.0); is_int = 0; }
     else if (g.cchecks == 2) { reward = xq_dadd(reward, 5.0); is_int = 0; }
@@ -613,9 +746,8 @@ __device__ __forceinline__ StepOut step(WarpSmem& w, Game& g, int move, uint64_t
     }
   }
 
-  const uint64_t bkey = board_key(w);
   if (g.hist_len < hist_cap) {  // :338, stored with the MOVER's side byte
-    if (lane == 0) hist[g.hist_len] = bkey ^ side_key(g.player);
+    if (lane == 0) hist[g.hist_len] = g.bkey ^ side_key(g.player);
     g.hist_len += 1;
   } else {
     g.flags |= XQ_F_OVERFLOW;
@@ -625,51 +757,65 @@ __device__ __forceinline__ StepOut step(WarpSmem& w, Game& g, int move, uint64_t
 
   g.player = -g.player;  // :348-349
   g.move_count += 1;
-  o.key_next = bkey ^ side_key(g.player);
+  o.key_next = g.bkey ^ side_key(g.player);
   o.n_next = -1;
-
-  if (!done) {  // :352-397
-    __syncwarp();
-    const int n_legal = movegen(w, g);
-    o.n_next = n_legal;
-    const bool chk_now = n_legal == 0 ? in_check(w, g, g.player) : false;
-    if (n_legal == 0 && chk_now) {  // :354, :614-628
-      done = 1; reward = 200.0; is_int = 1;
-      g.winner = -g.player;
-      g.reason = XQ_REASON_CHECKMATE;
-    } else {
-      int cnt = 0;  // :362, :598-605 — query uses the NEW side byte (quirk A.7)
-      for (int i = lane; i < g.hist_len; i += 32) cnt += hist[i] == o.key_next;
-#pragma unroll
-      for (int s = 16; s > 0; s >>= 1) cnt += __shfl_xor_sync(kFull, cnt, s);
-      if (cnt >= 3) {
-        done = 1; reward = 0.0; is_int = 1;
-        g.winner = 0;
-        g.reason = XQ_REASON_REPETITION;
-      } else if (g.no_capture >= 100) {  // :369, :612
-        done = 1; reward = 0.0; is_int = 1;
-        g.winner = 0;
-        g.reason = XQ_REASON_FIFTY;
-      } else if (n_legal == 0) {  // :376, :630-644
-        done = 1; reward = 100.0; is_int = 1;
-        g.winner = -g.player;
-        g.reason = XQ_REASON_STALEMATE;
-      } else if (g.check_len >= 12 && __popc(g.check_bits & 0xFFFu) >= 10) {  // :384, :646-662
-        done = 1; reward = -10.0; is_int = 1;
-        g.winner = -g.player;
-        g.reason = XQ_REASON_PERPETUAL_CHECK;
-      }  // :392 perpetual chase never fires (:674)
-    }
-  }
-  if (!done && g.move_count >= 70) {  // :400-404
-    done = 1; reward = -2.0; is_int = 1;
-    g.winner = 0;
-    g.reason = XQ_REASON_MOVE_CAP;
-  }
-  if (done) g.done = 1;
   o.reward = reward;
   o.is_int = is_int;
   o.done = done;
+  if (done) g.done = 1;
+  __syncwarp();
+  return o;
+}
+
+// make_move part 2 (chess_env.py:352-404): terminal chain for the side now to move, given its
+// legal-move count (the one movegen that also serves the next ply), then the 70-ply cap.
+__device__ __forceinline__ void step_finish(const WarpSmem& w, Game& g, StepOut& o, int n_legal,
+                                            const uint64_t* __restrict__ hist) {
+  const int lane = lane_id();
+  o.n_next = n_legal;
+  const bool chk_now = n_legal == 0 ? in_check_warp(w, g, g.player) : false;
+  if (n_legal == 0 && chk_now) {  // :354, :614-628
+    o.done = 1; o.reward = 200.0; o.is_int = 1;
+    g.winner = -g.player;
+    g.reason = XQ_REASON_CHECKMATE;
+  } else {
+    int cnt = 0;  // :362, :598-605 — query uses the NEW side byte (quirk A.7)
+    for (int i = lane; i < g.hist_len; i += 32) cnt += hist[i] == o.key_next;
+    cnt = warp_sum(cnt);
+    if (cnt >= 3) {
+      o.done = 1; o.reward = 0.0; o.is_int = 1;
+      g.winner = 0;
+      g.reason = XQ_REASON_REPETITION;
+    } else if (g.no_capture >= 100) {  // :369, :612
+      o.done = 1; o.reward = 0.0; o.is_int = 1;
+      g.winner = 0;
+      g.reason = XQ_REASON_FIFTY;
+    } else if (n_legal == 0) {  // :376, :630-644
+      o.done = 1; o.reward = 100.0; o.is_int = 1;
+      g.winner = -g.player;
+      g.reason = XQ_REASON_STALEMATE;
+    } else if (g.check_len >= 12 && __popc(g.check_bits & 0xFFFu) >= 10) {  // :384, :646-662
+      o.done = 1; o.reward = -10.0; o.is_int = 1;
+      g.winner = -g.player;
+      g.reason = XQ_REASON_PERPETUAL_CHECK;
+    }  // :392 perpetual chase never fires (:674)
+  }
+  if (!o.done && g.move_count >= 70) {  // :400-404
+    o.done = 1; o.reward = -2.0; o.is_int = 1;
+    g.winner = 0;
+    g.reason = XQ_REASON_MOVE_CAP;
+  }
+  if (o.done) g.done = 1;
+}
+
+// make_move (chess_env.py:253-406).  hist: this game's position_history row.
+__device__ __forceinline__ StepOut step(WarpSmem& w, Game& g, int move, uint64_t* __restrict__ hist,
+                                        int hist_cap, const uint32_t* __restrict__ leap) {
+  StepOut o = step_apply(w, g, move, hist, hist_cap);
+  if (!o.done) {  // :352
+    const int n_legal = movegen(w, g, leap);
+    step_finish(w, g, o, n_legal, hist);
+  }
   return o;
 }
 

@@ -509,21 +509,21 @@ static inline uint64_t dbits(double d) {
   return u;
 }
 
-/* Digest of one ply; order-sensitive inside the move list but a plain sum
- * across items so a warp can compute it lane-parallel. */
+/* Digest of one ply: position-weighted 32-bit sum of the ordered move
+ * list, packed with n / picked move / ply, then combined with the reward bits, the outcome
+ * flags and the key of the resulting position by odd 64-bit multipliers.  The chain is
+ * digest = mix64(digest ^ word). */
 static uint64_t ply_digest(int ply, const int16_t *moves, int n, int pick_move,
                            const xqo_state *after, const xqo_step_result *r) {
-  uint64_t w = 0;
-  for (int i = 0; i < n; ++i)
-    w += mix64(((uint64_t)(ply + 1) << 40) | ((uint64_t)(i + 1) << 20) |
-               (uint64_t)(uint16_t)moves[i]);
-  w += mix64(0xA5A5000000000000ULL ^ ((uint64_t)n << 16) ^ (uint64_t)pick_move);
-  w += xqo_position_hash(after->board, after->player);
-  w += mix64(dbits(r->reward));
-  w += mix64(0x5151000000000000ULL | (uint64_t)(r->done & 1) |
-             ((uint64_t)(after->winner + 2) << 8) | ((uint64_t)after->reason << 16) |
-             ((uint64_t)(r->reward_is_int & 1) << 24));
-  return w;
+  uint32_t lsum = 0;
+  for (int i = 0; i < n; ++i) lsum += (uint32_t)(moves[i] + 1) * (uint32_t)(2 * i + 1);
+  uint64_t a = (uint64_t)lsum | ((uint64_t)n << 32) | ((uint64_t)pick_move << 40) |
+               ((uint64_t)(ply + 1) << 54);
+  uint64_t c = (uint64_t)(r->done & 1) | ((uint64_t)(after->winner + 2) << 8) |
+               ((uint64_t)after->reason << 16) | ((uint64_t)(r->reward_is_int & 1) << 24);
+  return a * 0x9E3779B97F4A7C15ULL + dbits(r->reward) * 0xC2B2AE3D27D4EB4FULL +
+         c * 0x165667B19E3779F9ULL +
+         xqo_position_hash(after->board, after->player) * 0x27D4EB2F165667C5ULL;
 }
 
 void xqo_playout(xqo_state *s, uint64_t seed, uint32_t game_id, int max_plies,
@@ -541,7 +541,7 @@ void xqo_playout(xqo_state *s, uint64_t seed, uint32_t game_id, int max_plies,
     xqo_step_result r;
     xqo_make_move(s, moves[idx], &r);
     res->reward_sum += r.reward;
-    res->digest = mix64(res->digest + ply_digest(ply, moves, n, moves[idx], s, &r));
+    res->digest = mix64(res->digest ^ ply_digest(ply, moves, n, moves[idx], s, &r));
     if (trace_moves) memcpy(trace_moves + (size_t)ply * XQO_MAX_MOVES, moves, n * sizeof(int16_t));
     if (trace_n) trace_n[ply] = (int16_t)n;
     if (trace_pick) trace_pick[ply] = moves[idx];

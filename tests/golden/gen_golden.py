@@ -105,16 +105,14 @@ def dbits(x: float) -> int:
 
 def ply_digest(ply, packed, pick_move, board_after, player_after, reward, done, winner, reason,
                is_int):
-    w = 0
+    lsum = 0
     for i, m in enumerate(packed):
-        w += mix64(((ply + 1) << 40) | ((i + 1) << 20) | (m & 0xFFFF))
-    w += mix64(0xA5A5000000000000 ^ (len(packed) << 16) ^ pick_move)
-    w += pos_hash(board_after, player_after)
-    w += mix64(dbits(reward))
+        lsum = (lsum + (m + 1) * (2 * i + 1)) & 0xFFFFFFFF
+    a = lsum | (len(packed) << 32) | (pick_move << 40) | ((ply + 1) << 54)
     wn = 2 if winner is None else winner
-    w += mix64(0x5151000000000000 | (1 if done else 0) | ((wn + 2) << 8) | (reason << 16) |
-               ((1 if is_int else 0) << 24))
-    return w & M64
+    c = (1 if done else 0) | ((wn + 2) << 8) | (reason << 16) | ((1 if is_int else 0) << 24)
+    return (a * 0x9E3779B97F4A7C15 + dbits(reward) * 0xC2B2AE3D27D4EB4F + c * 0x165667B19E3779F9 +
+            pos_hash(board_after, player_after) * 0x27D4EB2F165667C5) & M64
 
 
 def import_reference():
@@ -180,9 +178,9 @@ def play_one(args):
         rc = reason_code(ref.end_reason)
         wn = 2 if ref.winner is None else ref.winner
         rec["reward_sum"] += float(reward)
-        rec["digest"] = mix64((rec["digest"] + ply_digest(
+        rec["digest"] = mix64(rec["digest"] ^ ply_digest(
             ply, packed, packed[idx], ref.board, ref.current_player, float(reward), done,
-            ref.winner, rc, is_int)) & M64)
+            ref.winner, rc, is_int))
         if full:
             rec["moves"].append(packed)
             rec["boards"].append(ref.board.reshape(90).copy())

@@ -19,8 +19,12 @@ static void stage(WarpSmem& w, const int8_t* board) {
       }
 }
 
+static const uint32_t h_leap[32] = XQ_LEAPER_TABLE_INIT;
+
+// mode 0: every candidate through suicide(); mode 1: the kernel's Phase B (relevance filter,
+// sentinel "no move" evaluation, flag bits) executed sequentially.
 extern "C" int xqh_legal_moves(const int8_t* board, int player, int red_king, int black_king,
-                               int16_t* moves, int* ncand_out) {
+                               int16_t* moves, int* ncand_out, int mode) {
   WarpSmem w;
   stage(w, board);
   Game g{};
@@ -38,24 +42,67 @@ extern "C" int xqh_legal_moves(const int8_t* board, int player, int red_king, in
   exotic = exotic || !regular_king(w, player, ownK, n_kings);
   int ncand = 0;
   for (int t = 0; t < n_own * 4; ++t) {
-    const Item it = gen_item(w, player, w.own[t >> 2], t & 3);
+    const Item it = gen_item(w, h_leap, player, w.own[t >> 2], t & 3);
     const int cnt = it.empties + (it.e1 >= 0) + (it.e2 >= 0);
     if (ncand + cnt > XQ_CAND_CAP) return -1;
-    for (int k = 1; k <= it.empties; ++k, ++ncand) {
-      w.cf[ncand] = (uint8_t)it.from;
-      w.ct[ncand] = (uint8_t)(it.from + k * it.delta);
-    }
-    if (it.e1 >= 0) { w.cf[ncand] = (uint8_t)it.from; w.ct[ncand] = (uint8_t)it.e1; ++ncand; }
-    if (it.e2 >= 0) { w.cf[ncand] = (uint8_t)it.from; w.ct[ncand] = (uint8_t)it.e2; ++ncand; }
+    for (int k = 1; k <= it.empties; ++k) w.cand[ncand++] = (uint16_t)((it.from << 8) | (it.from + k * it.delta));
+    if (it.e1 >= 0) w.cand[ncand++] = (uint16_t)((it.from << 8) | it.e1);
+    if (it.e2 >= 0) w.cand[ncand++] = (uint16_t)((it.from << 8) | it.e2);
   }
   if (ncand_out) *ncand_out = ncand;
   int n = 0;
-  for (int j = 0; j < ncand; ++j)
-    if (!suicide(w, g, w.cf[j], w.ct[j], exotic)) {
-      if (n < XQ_MAX_MOVES) moves[n] = (int16_t)(w.cf[j] * 90 + w.ct[j]);
+  if (mode == 0) {
+    for (int j = 0; j < ncand; ++j)
+      if (!suicide(w, g, w.cand[j] >> 8, w.cand[j] & 0x7f, true)) {
+        if (n < XQ_MAX_MOVES) moves[n] = (int16_t)((w.cand[j] >> 8) * 90 + (w.cand[j] & 0x7f));
+        ++n;
+      }
+    return n;
+  }
+  const int kr = ownK >= 0 ? ownK / 9 : 0, kc = ownK >= 0 ? ownK - kr * 9 : 0;
+  int nwl = 0;
+  bool any_irrelevant = false;
+  for (int j = 0; j < ncand; ++j) {
+    const int c = w.cand[j], from = c >> 8, to = c & 0x7f;
+    const bool rel = exotic || from == ownK || touches(kr, kc, from) || touches(kr, kc, to);
+    if (rel) w.wl[nwl++] = (uint16_t)j;
+    else {
+      w.cand[j] = (uint16_t)(c | kCandIrrelevant);
+      any_irrelevant = true;
+    }
+  }
+  if (any_irrelevant) w.wl[nwl++] = kWlSentinel;
+  bool cur_bad = false;
+  for (int i = 0; i < nwl; ++i) {
+    const int item = w.wl[i];
+    if (item == kWlSentinel) {
+      cur_bad = suicide(w, g, -1, -1, exotic);
+    } else {
+      const int c = w.cand[item];
+      if (suicide(w, g, c >> 8, c & 0x7f, exotic)) w.cand[item] = (uint16_t)(c | kCandIllegal);
+    }
+  }
+  for (int j = 0; j < ncand; ++j) {
+    const int c = w.cand[j];
+    const bool ok = (c & kCandIrrelevant) ? !cur_bad : !(c & kCandIllegal);
+    if (ok) {
+      if (n < XQ_MAX_MOVES) moves[n] = (int16_t)(((c >> 8) & 0x7f) * 90 + (c & 0x7f));
       ++n;
     }
+  }
   return n;
+}
+
+// OR of the 8 per-direction probes (what in_check_warp computes with 8 lanes)
+extern "C" int xqh_in_check_dirs(const int8_t* board, int player, int current_player, int red_king,
+                                 int black_king) {
+  WarpSmem w;
+  stage(w, board);
+  const int K = player == 1 ? red_king : black_king;
+  if (K < 0) return 0;
+  bool hit = false;
+  for (int d = 0; d < 8; ++d) hit |= attacked_dir(w, K, -player, current_player, d);
+  return hit ? 1 : 0;
 }
 
 // _is_in_check(player) with geometry of `current_player` (chess_env.py:506-548)

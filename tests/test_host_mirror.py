@@ -11,19 +11,26 @@ import pytest
 def hm():
     from tests.host_mirror.build import build
     lib = C.CDLL(build())
-    lib.xqh_legal_moves.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.xqh_legal_moves.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
     lib.xqh_in_check.argtypes = [C.c_void_p] + [C.c_int] * 4
+    lib.xqh_in_check_dirs.argtypes = [C.c_void_p] + [C.c_int] * 4
     lib.xqh_position_change.argtypes = [C.c_int] * 5
     lib.xqh_position_change.restype = C.c_double
     return lib
 
 
 def _legal(hm, board, player, red, black):
+    """Kernel Phase B (mode 1) must agree with the test-everything path (mode 0)."""
     b = np.ascontiguousarray(board, np.int8).reshape(90)
-    mv = np.zeros(128, np.int16)
-    nc = C.c_int(0)
-    n = hm.xqh_legal_moves(b.ctypes.data, int(player), int(red), int(black), mv.ctypes.data, C.byref(nc))
-    return mv[:n].copy(), nc.value
+    out = []
+    for mode in (0, 1):
+        mv = np.zeros(128, np.int16)
+        nc = C.c_int(0)
+        n = hm.xqh_legal_moves(b.ctypes.data, int(player), int(red), int(black), mv.ctypes.data,
+                               C.byref(nc), mode)
+        out.append(mv[:n].copy())
+    assert np.array_equal(out[0], out[1]), "relevance filter changed the legal list"
+    return out[1], nc.value
 
 
 def test_golden_positions(hm, golden):
@@ -36,6 +43,9 @@ def test_golden_positions(hm, golden):
         pl = int(P["player"][i])
         assert hm.xqh_in_check(b.ctypes.data, pl, pl, int(P["red"][i]), int(P["black"][i])) == P["chk_self"][i], i
         assert hm.xqh_in_check(b.ctypes.data, -pl, pl, int(P["red"][i]), int(P["black"][i])) == P["chk_opp"][i], i
+        for who in (pl, -pl):
+            assert hm.xqh_in_check_dirs(b.ctypes.data, who, pl, int(P["red"][i]), int(P["black"][i])) == \
+                hm.xqh_in_check(b.ctypes.data, who, pl, int(P["red"][i]), int(P["black"][i])), i
 
 
 @pytest.mark.parametrize("bias", [0, 200])
@@ -52,6 +62,8 @@ def test_fuzz_playouts_vs_oracle(hm, xo, bias):
             b = np.ascontiguousarray(e.board.reshape(90))
             for who in (1, -1):
                 assert hm.xqh_in_check(b.ctypes.data, who, e.s.player, e.s.red_king, e.s.black_king) == \
+                    int(e.is_in_check(who)), (g, ply, who)
+                assert hm.xqh_in_check_dirs(b.ctypes.data, who, e.s.player, e.s.red_king, e.s.black_king) == \
                     int(e.is_in_check(who)), (g, ply, who)
             if len(lm) == 0:
                 break
