@@ -88,8 +88,6 @@ __global__ void __launch_bounds__(kThreads)
                        int16_t* __restrict__ moves, int16_t* __restrict__ n_moves,
                        uint8_t* __restrict__ in_check_out, int n_games) {
   __shared__ WarpSmem slab[kWarpsPerCta];
-  __shared__ uint32_t s_leap[32];
-  load_leap_table(s_leap);
   const int g = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   if (g >= n_games) return;
   WarpSmem& w = slab[threadIdx.x >> 5];
@@ -98,7 +96,7 @@ __global__ void __launch_bounds__(kThreads)
   build_masks(w);
   Game G = load_meta(meta + g);
   const int flags0 = G.flags;
-  const int n = movegen(w, G, s_leap);
+  const int n = movegen(w, G, g_leap);
   int16_t* row = moves + (size_t)g * XQ_MAX_MOVES;
   for (int i = lane; i < n; i += 32) row[i] = w.moves[i];
   if (lane == 0) {
@@ -147,8 +145,6 @@ __global__ void __launch_bounds__(kThreads)
                 double* __restrict__ reward, uint8_t* __restrict__ flags,
                 int16_t* __restrict__ next_moves, int16_t* __restrict__ next_n, int n_games) {
   __shared__ WarpSmem slab[kWarpsPerCta];
-  __shared__ uint32_t s_leap[32];
-  load_leap_table(s_leap);
   const int g = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   if (g >= n_games) return;
   WarpSmem& w = slab[threadIdx.x >> 5];
@@ -167,7 +163,7 @@ __global__ void __launch_bounds__(kThreads)
   build_masks(w);
   Game G = load_meta(meta + g);
   G.bkey = board_key(w);
-  const StepOut o = step(w, G, mv, pos_hist + (size_t)g * hist_cap, hist_cap, s_leap);
+  const StepOut o = step(w, G, mv, pos_hist + (size_t)g * hist_cap, hist_cap, g_leap);
   store_board(w, board + (size_t)g * XQ_BOARD_STRIDE);
   store_meta(meta + g, G);
   if (lane == 0) {
@@ -223,8 +219,6 @@ __global__ void __launch_bounds__(kThreads, MINB)
                    double* __restrict__ tr_reward, uint8_t* __restrict__ tr_flags,
                    int8_t* __restrict__ tr_boards, int n_games) {
   __shared__ WarpSmem slab[kWarpsPerCta];
-  __shared__ uint32_t s_leap[32];
-  load_leap_table(s_leap);
   const int g = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   if (g >= n_games) return;
   WarpSmem& w = slab[threadIdx.x >> 5];
@@ -266,7 +260,7 @@ __global__ void __launch_bounds__(kThreads, MINB)
   // One movegen site per iteration: it closes the previous make_move (:354,:376 need the new
   // side's move count) and is the get_legal_moves of the next ply (self_play.py:205).
   for (;;) {
-    const int n = movegen(w, G, s_leap);
+    const int n = movegen(w, G, g_leap);
     if (pending) {
       step_finish(w, G, o, n, hist);
       pending = false;
@@ -278,6 +272,7 @@ __global__ void __launch_bounds__(kThreads, MINB)
     const int idx = pick_index(w, n, seed, gid, (uint32_t)ply, capture_bias);
     const int mv = w.moves[idx];
     unsigned lsum = 0;
+#pragma unroll 1
     for (int i = lane; i < n; i += 32) lsum += (unsigned)((int)w.moves[i] + 1) * (unsigned)(2 * i + 1);
     lsum = __reduce_add_sync(kFull, lsum);
     word_a = (uint64_t)lsum | ((uint64_t)n << 32) | ((uint64_t)mv << 40) | ((uint64_t)(ply + 1) << 54);

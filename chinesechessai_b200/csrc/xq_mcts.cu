@@ -182,8 +182,6 @@ __global__ void __launch_bounds__(kThreadsM, 4)
                        int8_t* __restrict__ leaf_player, int16_t* __restrict__ leaf_moves,
                        int16_t* __restrict__ leaf_n, int16_t* __restrict__ leaf_mult, int n_games) {
   __shared__ WarpSmem slab[kWarpsPerCta];
-  __shared__ uint32_t s_leap[32];
-  load_leap_table(s_leap);
   const int g = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   if (g >= n_games) return;
   WarpSmem& w = slab[threadIdx.x >> 5];
@@ -211,7 +209,7 @@ __global__ void __launch_bounds__(kThreadsM, 4)
           load_board(w, t.board(0));
           build_masks(w);
           G = load_meta(t.meta(0));
-          n_legal = movegen(w, G, s_leap);  // :123
+          n_legal = movegen(w, G, g_leap);  // :123
         } else {
           const int ps = t.nodes[nd.parent].state;
           slot = h.n_states;  // scratch until proven non-terminal
@@ -223,7 +221,7 @@ __global__ void __launch_bounds__(kThreadsM, 4)
           const uint64_t* hp = t.hist(ps);
           for (int i = lane; i < G.hist_len; i += 32) hs[i] = hp[i];
           __syncwarp();
-          const StepOut o = step(w, G, nd.move, hs, d.hist_cap, s_leap);  // :119
+          const StepOut o = step(w, G, nd.move, hs, d.hist_cap, g_leap);  // :119
           n_legal = o.n_next < 0 ? 0 : o.n_next;
           if (o.n_next < 0 && G.winner == XQ_WINNER_NONE) n_legal = 0;
         }

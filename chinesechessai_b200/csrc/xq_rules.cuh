@@ -223,132 +223,104 @@ __device__ __forceinline__ void build_masks(WarpSmem& w) {
 // Is square K a pseudo-target of any piece of sign `es` (the attackers), with
 // K/A/B/P geometry taken from side `geo` (chess_env.py:506-548 — the reference
 // regenerates attackers' moves with self.current_player's geometry, quirk A.3)?
-// The candidate (from,to,mover) is applied as an override (from<0: none).
-// `exotic` enables the K/A/B probes (warp-uniform hint; always safe to pass true).
-XQ_HD bool attacked(const WarpSmem& w, int K, int es, int geo, int from,
-                                         int to, int mover, bool exotic, unsigned* colm_out) {
-  const int kr = K / 9, kc = K - kr * 9;
-  unsigned rowm = w.rows[kr], colm = w.cols[kc];
+// A candidate (from,to,mover) can be applied as an override (from<0: none).
+// The test is 8 probes from K outward: 4 rays (first piece = rook / adjacent pawn / adjacent
+// king; second piece = cannon) and 4 diagonal neighbours (knight legs :182-197, bishop eyes
+// :161-174, advisors :149-152).  Probes are written once and looped (code size matters: the
+// fused playout loop must stay inside the 32 KB L1.5 instruction cache).
+struct Probe {
+  int K, kr, kc, es, geo, from, to, mover;
+  unsigned rowm, colm;  // occupancy of K's row / column with the override applied
+  bool kocc, in_pal;
+};
+
+XQ_HD Probe make_probe(const WarpSmem& w, int K, int es, int geo, int from, int to, int mover) {
+  Probe p;
+  p.K = K; p.es = es; p.geo = geo; p.from = from; p.to = to; p.mover = mover;
+  p.kr = K / 9;
+  p.kc = K - p.kr * 9;
+  p.rowm = w.rows[p.kr];
+  p.colm = w.cols[p.kc];
   if (from >= 0) {
     const int fr = from / 9, fc = from - fr * 9, tr = to / 9, tc = to - tr * 9;
-    if (fr == kr) rowm &= ~(1u << fc);
-    if (fc == kc) colm &= ~(1u << fr);
-    if (tr == kr) rowm |= 1u << tc;
-    if (tc == kc) colm |= 1u << tr;
+    if (fr == p.kr) p.rowm &= ~(1u << fc);
+    if (fc == p.kc) p.colm &= ~(1u << fr);
+    if (tr == p.kr) p.rowm |= 1u << tc;
+    if (tc == p.kc) p.colm |= 1u << tr;
   }
-  if (colm_out) *colm_out = colm;
-  auto pc = [&](int s) -> int { return s == to ? mover : (s == from ? 0 : (int)w.sq[s]); };
-  const bool kocc = (rowm >> kc) & 1u;
-  const int rook = es * ROOK, cannon = es * CANNON, pawn = es * PAWN, king = es * KING;
-  const bool in_pal = (kc >= 3 && kc <= 5) && (geo == 1 ? kr >= 7 : kr <= 2);  // :127-131
-  const bool side_ok = geo == 1 ? kr < 5 : kr >= 5;                             // :242,:247
-  bool hit = false;
+  p.kocc = (p.rowm >> p.kc) & 1u;
+  p.in_pal = (p.kc >= 3 && p.kc <= 5) && (geo == 1 ? p.kr >= 7 : p.kr <= 2);  // :127-131
+  return p;
+}
 
-  // rays: first piece = rook / adjacent pawn / adjacent king; cannon over one screen
-  {  // (0,+1)
-    unsigned a = rowm >> (kc + 1);
-    if (a) {
-      int d1 = xq_ffs(a), q = pc(K + d1);
-      hit |= (q == rook) | (q == cannon && !kocc) |
-             (d1 == 1 && ((q == pawn && side_ok) | (q == king && in_pal)));
-      unsigned a2 = a & (a - 1);
-      if (kocc && a2) hit |= pc(K + xq_ffs(a2)) == cannon;
-    }
+XQ_HD int probe_piece(const WarpSmem& w, const Probe& p, int s) {
+  return s == p.to ? p.mover : (s == p.from ? 0 : (int)w.sq[s]);
+}
+
+// dir 0..3 = rays (0,+1),(0,-1),(+1,0),(-1,0).  The mask is mirrored for the backward rays so
+// "ahead" is always toward higher bits.
+XQ_HD bool probe_ray(const WarpSmem& w, const Probe& p, int dir) {
+  const bool horiz = dir < 2, fwd = (dir & 1) == 0;
+  const int len = horiz ? 9 : 10;
+  unsigned m = horiz ? p.rowm : p.colm;
+  int x = horiz ? p.kc : p.kr;
+  if (!fwd) {
+    m = xq_brev(m) >> (32 - len);
+    x = len - 1 - x;
   }
-  {  // (0,-1)
-    unsigned b = rowm & ((1u << kc) - 1u);
-    if (b) {
-      int hb = 31 - xq_clz(b), q = pc(kr * 9 + hb);
-      hit |= (q == rook) | (q == cannon && !kocc) |
-             (kc - hb == 1 && ((q == pawn && side_ok) | (q == king && in_pal)));
-      unsigned b2 = b & ~(1u << hb);
-      if (kocc && b2) hit |= pc(kr * 9 + 31 - xq_clz(b2)) == cannon;
-    }
-  }
-  {  // (+1,0): a pawn below K attacks it iff pawns move toward smaller rows (geo==1, :241)
-    unsigned a = colm >> (kr + 1);
-    if (a) {
-      int d1 = xq_ffs(a), q = pc(K + 9 * d1);
-      hit |= (q == rook) | (q == cannon && !kocc) |
-             (d1 == 1 && ((q == pawn && geo == 1) | (q == king && in_pal)));
-      unsigned a2 = a & (a - 1);
-      if (kocc && a2) hit |= pc(K + 9 * xq_ffs(a2)) == cannon;
-    }
-  }
-  {  // (-1,0)
-    unsigned b = colm & ((1u << kr) - 1u);
-    if (b) {
-      int hb = 31 - xq_clz(b), q = pc(hb * 9 + kc);
-      hit |= (q == rook) | (q == cannon && !kocc) |
-             (kr - hb == 1 && ((q == pawn && geo == -1) | (q == king && in_pal)));
-      unsigned b2 = b & ~(1u << hb);
-      if (kocc && b2) hit |= pc((31 - xq_clz(b2)) * 9 + kc) == cannon;
-    }
-  }
-  // diagonal neighbours: knight legs (:182-197), bishop eyes (:161-174), advisors (:149-152)
-  const int knight = es * KNIGHT, bishop = es * BISHOP, advisor = es * ADVISOR;
-  const bool bside = geo == 1 ? kr >= 5 : kr <= 3;  // :159,:167-170 (black river = 4: rows 0..3)
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int a = (i & 2) ? 1 : -1, b = (i & 1) ? 1 : -1;
-    const int lr = kr + a, lc = kc + b;
-    if (lr < 0 || lr > 9 || lc < 0 || lc > 8) continue;
-    const int ql = pc(lr * 9 + lc);
-    if (ql == 0) {
-      const int r2 = kr + 2 * a, c2 = kc + 2 * b;
-      const bool r2ok = r2 >= 0 && r2 <= 9, c2ok = c2 >= 0 && c2 <= 8;
-      if (r2ok) hit |= pc(r2 * 9 + lc) == knight;
-      if (c2ok) hit |= pc(lr * 9 + c2) == knight;
-      if (exotic && bside && r2ok && c2ok) hit |= pc(r2 * 9 + c2) == bishop;
-    } else if (exotic && in_pal && ql == advisor) {
-      hit = true;
-    }
-  }
+  const unsigned a = m >> (x + 1);
+  if (!a) return false;
+  const int delta = (horiz ? 1 : 9) * (fwd ? 1 : -1);
+  const int d1 = xq_ffs(a), q = probe_piece(w, p, p.K + d1 * delta);
+  // adjacent pawn: sideways only from a crossed row (:242,:247); vertically only if it moves
+  // toward K under `geo` (a pawn below K attacks iff pawns move to smaller rows, geo==1, :241)
+  const bool pawn_dir = horiz ? (p.geo == 1 ? p.kr < 5 : p.kr >= 5) : (p.geo == (fwd ? 1 : -1));
+  bool hit = (q == p.es * ROOK) | (q == p.es * CANNON && !p.kocc) |
+             (d1 == 1 && ((q == p.es * PAWN && pawn_dir) | (q == p.es * KING && p.in_pal)));
+  const unsigned a2 = a & (a - 1);
+  if (p.kocc && a2) hit |= probe_piece(w, p, p.K + xq_ffs(a2) * delta) == p.es * CANNON;
   return hit;
 }
 
-// One of the 8 probes of attacked() on the staged board without an override: dir 0..3 =
-// rays (0,+1),(0,-1),(+1,0),(-1,0); dir 4..7 = the diagonal neighbours.  The OR over the
-// 8 directions equals attacked(w, K, es, geo, -1, -1, 0, true) — one lane per direction
-// gives the warp-parallel check test of make_move (:317).
-XQ_HD bool attacked_dir(const WarpSmem& w, int K, int es, int geo, int dir) {
-  const int kr = K / 9, kc = K - kr * 9;
-  const bool in_pal = (kc >= 3 && kc <= 5) && (geo == 1 ? kr >= 7 : kr <= 2);
-  if (dir < 4) {
-    const bool horiz = dir < 2, fwd = (dir & 1) == 0;
-    const int len = horiz ? 9 : 10;
-    unsigned m = horiz ? w.rows[kr] : w.cols[kc];
-    int x = horiz ? kc : kr;
-    const bool kocc = (m >> x) & 1u;
-    if (!fwd) {
-      m = xq_brev(m) >> (32 - len);
-      x = len - 1 - x;
-    }
-    const int delta = (horiz ? 1 : 9) * (fwd ? 1 : -1);
-    const unsigned a = m >> (x + 1);
-    if (!a) return false;
-    const int d1 = xq_ffs(a), q = w.sq[K + d1 * delta];
-    const bool pawn_dir = horiz ? (geo == 1 ? kr < 5 : kr >= 5) : (geo == (fwd ? 1 : -1));
-    bool hit = (q == es * ROOK) | (q == es * CANNON && !kocc) |
-               (d1 == 1 && ((q == es * PAWN && pawn_dir) | (q == es * KING && in_pal)));
-    const unsigned a2 = a & (a - 1);
-    if (kocc && a2) hit |= w.sq[K + xq_ffs(a2) * delta] == es * CANNON;
-    return hit;
-  }
-  const int i = dir - 4;
+// i 0..3 = diagonal neighbour (a,b) in {-1,+1}^2.
+XQ_HD bool probe_diag(const WarpSmem& w, const Probe& p, int i, bool exotic) {
   const int a = (i & 2) ? 1 : -1, b = (i & 1) ? 1 : -1;
-  const int lr = kr + a, lc = kc + b;
+  const int lr = p.kr + a, lc = p.kc + b;
   if (lr < 0 || lr > 9 || lc < 0 || lc > 8) return false;
-  const int ql = w.sq[lr * 9 + lc];
-  if (ql != 0) return in_pal && ql == es * ADVISOR;
-  const int r2 = kr + 2 * a, c2 = kc + 2 * b;
+  const int ql = probe_piece(w, p, lr * 9 + lc);
+  if (ql != 0) return exotic && p.in_pal && ql == p.es * ADVISOR;
+  const int r2 = p.kr + 2 * a, c2 = p.kc + 2 * b;
   const bool r2ok = r2 >= 0 && r2 <= 9, c2ok = c2 >= 0 && c2 <= 8;
-  const bool bside = geo == 1 ? kr >= 5 : kr <= 3;
+  const bool bside = p.geo == 1 ? p.kr >= 5 : p.kr <= 3;  // :159,:167-170 (black river = 4)
   bool hit = false;
-  if (r2ok) hit |= w.sq[r2 * 9 + lc] == es * KNIGHT;
-  if (c2ok) hit |= w.sq[lr * 9 + c2] == es * KNIGHT;
-  if (bside && r2ok && c2ok) hit |= w.sq[r2 * 9 + c2] == es * BISHOP;
+  if (r2ok) hit |= probe_piece(w, p, r2 * 9 + lc) == p.es * KNIGHT;
+  if (c2ok) hit |= probe_piece(w, p, lr * 9 + c2) == p.es * KNIGHT;
+  if (exotic && bside && r2ok && c2ok) hit |= probe_piece(w, p, r2 * 9 + c2) == p.es * BISHOP;
   return hit;
+}
+
+// `exotic` enables the K/A/B diagonal probes (warp-uniform hint; always safe to pass true).
+XQ_HD bool attacked(const WarpSmem& w, int K, int es, int geo, int from, int to, int mover,
+                    bool exotic, unsigned* colm_out) {
+  const Probe p = make_probe(w, K, es, geo, from, to, mover);
+  if (colm_out) *colm_out = p.colm;
+  bool hit = false;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  for (int d = 0; d < 4; ++d) hit |= probe_ray(w, p, d);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  for (int i = 0; i < 4; ++i) hit |= probe_diag(w, p, i, exotic);
+  return hit;
+}
+
+// One of the 8 probes of attacked() on the staged board without an override (dir 4..7 = the
+// diagonals).  One lane per direction gives the warp-parallel check test of make_move (:317).
+XQ_HD bool attacked_dir(const WarpSmem& w, int K, int es, int geo, int dir) {
+  const Probe p = make_probe(w, K, es, geo, -1, -1, 0);
+  return dir < 4 ? probe_ray(w, p, dir) : probe_diag(w, p, dir - 4, true);
 }
 
 // _is_in_check(player) on the staged board (chess_env.py:506-548), single-lane form.
@@ -401,31 +373,15 @@ struct Item {
   int from, empties, delta, e1, e2;
 };
 
-// Leaper table, entry [piece_type*4 + d]: byte0/byte1 = targets, byte2 = square that must be
-// empty (knight leg :189-195, bishop eye :171-174), each (dr+2)|(dc+2)<<3 or 0xFF = none;
-// byte3 = zone: 0 on-board, 1 palace of the side to move (:127-131,:143-147), 2 own side of
-// the river (:159-170), 3 pawn forward (dr is multiplied by the side, :241,:246), 4 pawn
-// sideways (needs a crossed pawn, :242,:247).
-#define XQ_OFF(dr, dc) (uint32_t)(((dr) + 2) | (((dc) + 2) << 3))
-#define XQ_LEAP(t1, t2, bk, zone) ((t1) | ((t2) << 8) | ((bk) << 16) | ((uint32_t)(zone) << 24))
-#define XQ_NONE 0xFFu
-#define XQ_LEAPER_TABLE_INIT                                                                      \
-  {0, 0, 0, 0, /* KING */                                                                         \
-   XQ_LEAP(XQ_OFF(0, 1), XQ_NONE, XQ_NONE, 1), XQ_LEAP(XQ_OFF(0, -1), XQ_NONE, XQ_NONE, 1),       \
-   XQ_LEAP(XQ_OFF(1, 0), XQ_NONE, XQ_NONE, 1), XQ_LEAP(XQ_OFF(-1, 0), XQ_NONE, XQ_NONE, 1),       \
-   /* ADVISOR */                                                                                  \
-   XQ_LEAP(XQ_OFF(1, 1), XQ_NONE, XQ_NONE, 1), XQ_LEAP(XQ_OFF(1, -1), XQ_NONE, XQ_NONE, 1),       \
-   XQ_LEAP(XQ_OFF(-1, 1), XQ_NONE, XQ_NONE, 1), XQ_LEAP(XQ_OFF(-1, -1), XQ_NONE, XQ_NONE, 1),     \
-   /* BISHOP */                                                                                   \
-   XQ_LEAP(XQ_OFF(2, 2), XQ_NONE, XQ_OFF(1, 1), 2), XQ_LEAP(XQ_OFF(2, -2), XQ_NONE, XQ_OFF(1, -1), 2),     \
-   XQ_LEAP(XQ_OFF(-2, 2), XQ_NONE, XQ_OFF(-1, 1), 2), XQ_LEAP(XQ_OFF(-2, -2), XQ_NONE, XQ_OFF(-1, -1), 2), \
-   /* KNIGHT: offset pairs sharing a leg (:182-187) */                                            \
-   XQ_LEAP(XQ_OFF(2, 1), XQ_OFF(2, -1), XQ_OFF(1, 0), 0), XQ_LEAP(XQ_OFF(-2, 1), XQ_OFF(-2, -1), XQ_OFF(-1, 0), 0), \
-   XQ_LEAP(XQ_OFF(1, 2), XQ_OFF(-1, 2), XQ_OFF(0, 1), 0), XQ_LEAP(XQ_OFF(1, -2), XQ_OFF(-1, -2), XQ_OFF(0, -1), 0), \
-   0, 0, 0, 0, /* ROOK */ 0, 0, 0, 0, /* CANNON */                                                \
-   /* PAWN: forward, left, right (:241-249) */                                                    \
-   XQ_LEAP(XQ_OFF(-1, 0), XQ_NONE, XQ_NONE, 3), XQ_LEAP(XQ_OFF(0, -1), XQ_NONE, XQ_NONE, 4),      \
-   XQ_LEAP(XQ_OFF(0, 1), XQ_NONE, XQ_NONE, 4), XQ_LEAP(XQ_NONE, XQ_NONE, XQ_NONE, 0)}
+// Leaper table (generated, xq_leap_table.inc): entry [side][piece type][from][d] =
+// t1 | t2<<8 | blocker<<16, each a square or 0xFF: the targets of generator slot d that are
+// on-board and inside the zone the generator enforces (palace :127-147, own river side
+// :159-170, pawn direction/crossing :240-249) and the square that must be empty (knight leg
+// :189-195, bishop eye :171-174).  23 KB, read through the L1/read-only path.
+constexpr int kLeapEntries = 2 * 8 * 90 * 4;
+XQ_HD int leap_index(int player, int pt, int from, int d) {
+  return ((player == 1 ? 0 : 8) + pt) * 360 + from * 4 + d;
+}
 
 XQ_HD Item gen_item(const WarpSmem& w, const uint32_t* __restrict__ leap, int player, int from, int d) {
   Item it{from, 0, 0, -1, -1};
@@ -457,29 +413,16 @@ XQ_HD Item gen_item(const WarpSmem& w, const uint32_t* __restrict__ leap, int pl
     return it;
   }
   if (pt < KING || pt > PAWN) return it;
-  const uint32_t e = leap[pt * 4 + d];
-  const int zone = (int)(e >> 24);
+#if defined(__CUDA_ARCH__)
+  const uint32_t e = __ldg(leap + leap_index(player, pt, from, d));
+#else
+  const uint32_t e = leap[leap_index(player, pt, from, d)];
+#endif
   const uint32_t bk = (e >> 16) & 0xFFu;
-  bool ok = true;
-  if (bk != XQ_NONE) {
-    const int br = r + (int)(bk & 7u) - 2, bc = c + (int)((bk >> 3) & 7u) - 2;
-    ok = br >= 0 && br <= 9 && bc >= 0 && bc <= 8 && w.sq[br * 9 + bc] == 0;
-  }
-  if (zone == 4) ok = player == 1 ? r < 5 : r >= 5;
-  const int sgn = zone == 3 ? player : 1;
-#pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const uint32_t t = (e >> (8 * k)) & 0xFFu;
-    if (!ok || t == XQ_NONE) continue;
-    const int nr = r + ((int)(t & 7u) - 2) * sgn, nc = c + (int)((t >> 3) & 7u) - 2;
-    bool good = nr >= 0 && nr <= 9 && nc >= 0 && nc <= 8;
-    if (zone == 1) good = good && nc >= 3 && nc <= 5 && (player == 1 ? nr >= 7 : nr <= 2);
-    if (zone == 2) good = good && (player == 1 ? nr >= 5 : nr <= 3);
-    if (good && (int)w.sq[nr * 9 + nc] * player <= 0) {
-      if (k == 0) it.e1 = nr * 9 + nc;
-      else it.e2 = nr * 9 + nc;
-    }
-  }
+  if (bk != 0xFFu && w.sq[bk] != 0) return it;  // blocked leg / eye
+  const uint32_t t1 = e & 0xFFu, t2 = (e >> 8) & 0xFFu;
+  if (t1 != 0xFFu && (int)w.sq[t1] * player <= 0) it.e1 = (int)t1;  // :116
+  if (t2 != 0xFFu && (int)w.sq[t2] * player <= 0) it.e2 = (int)t2;
   return it;
 }
 
@@ -498,14 +441,9 @@ XQ_HD bool regular_king(const WarpSmem& w, int player, int own_king, int n_own_k
 }
 
 #if defined(__CUDACC__)
-static __constant__ uint32_t c_leap[32] = XQ_LEAPER_TABLE_INIT;
-
-// Copies the leaper table into shared memory (divergent lookups from constant memory would
-// serialise).  Must be called by every thread of the CTA before any early return.
-__device__ __forceinline__ void load_leap_table(uint32_t* s_leap) {
-  if (threadIdx.x < 32) s_leap[threadIdx.x] = c_leap[threadIdx.x];
-  __syncthreads();
-}
+static __device__ const uint32_t g_leap[kLeapEntries] = {
+#include "xq_leap_table.inc"
+};
 
 __device__ __forceinline__ int warp_sum(int v) { return (int)__reduce_add_sync(kFull, (unsigned)v); }
 
@@ -560,6 +498,7 @@ __device__ __forceinline__ int movegen(WarpSmem& w, Game& g, const uint32_t* __r
     int off = ncand + incl - cnt;
     ncand += total;
     const int fs = it.from << 8;
+#pragma unroll 1
     for (int k = 1; k <= it.empties; ++k, ++off) w.cand[off] = (uint16_t)(fs | (it.from + k * it.delta));
     if (it.e1 >= 0) w.cand[off++] = (uint16_t)(fs | it.e1);
     if (it.e2 >= 0) w.cand[off] = (uint16_t)(fs | it.e2);
@@ -595,13 +534,10 @@ __device__ __forceinline__ int movegen(WarpSmem& w, Game& g, const uint32_t* __r
     if (i < nwl) {
       const int item = w.wl[i];
       is_cur = item == kWlSentinel;
-      if (is_cur) {
-        bad = suicide(w, g, -1, -1, exotic);
-      } else {
-        const int c = w.cand[item];
-        bad = suicide(w, g, c >> 8, c & 0x7f, exotic);
-        if (bad) w.cand[item] = (uint16_t)(c | kCandIllegal);
-      }
+      const int c = is_cur ? 0 : (int)w.cand[item];
+      // ONE call site: the sentinel lane evaluates the position itself (from = -1)
+      bad = suicide(w, g, is_cur ? -1 : (c >> 8), is_cur ? -1 : (c & 0x7f), exotic);
+      if (bad && !is_cur) w.cand[item] = (uint16_t)(c | kCandIllegal);
     }
     cur_bad |= __ballot_sync(kFull, is_cur && bad) != 0;
   }
@@ -696,11 +632,10 @@ __device__ __forceinline__ StepOut step_apply(WarpSmem& w, Game& g, int move,
       w.cols[tc] &= ~(1u << tr);
     }
   }
-  {  // incremental position key: three (piece, square) keys on three lanes
-    uint64_t x = 0;
-    if (lane == 0 && moving != 0) x = piece_key(moving, from);
-    if (lane == 1 && moving != 0) x = piece_key(moving, to);
-    if (lane == 2 && captured != 0) x = piece_key(captured, to);
+  {  // incremental position key: three (piece, square) keys on three lanes, one mix64 site
+    const int kp = lane == 2 ? captured : moving;
+    const int ks = lane == 0 ? from : to;
+    uint64_t x = (lane < 3 && kp != 0) ? piece_key(kp, ks) : 0ULL;
     x ^= __shfl_xor_sync(kFull, x, 1);
     x ^= __shfl_xor_sync(kFull, x, 2);
     g.bkey ^= __shfl_sync(kFull, x, 0);
@@ -780,6 +715,7 @@ __device__ __forceinline__ void step_finish(const WarpSmem& w, Game& g, StepOut&
     g.reason = XQ_REASON_CHECKMATE;
   } else {
     int cnt = 0;  // :362, :598-605 — query uses the NEW side byte (quirk A.7)
+#pragma unroll 1
     for (int i = lane; i < g.hist_len; i += 32) cnt += hist[i] == o.key_next;
     cnt = warp_sum(cnt);
     if (cnt >= 3) {
@@ -839,31 +775,39 @@ __device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+// Capture-biased pick (diagnostic workloads only): kept out of line so that the uniform-pick
+// hot loop does not carry its code.
+static __device__ __noinline__ int pick_capture(const WarpSmem* wp, int n, uint32_t x0) {
+  const WarpSmem& w = *wp;
+  const int lane = lane_id();
+  unsigned masks[XQ_MAX_MOVES / 32];
+  int ncap = 0;
+#pragma unroll
+  for (int k = 0; k < XQ_MAX_MOVES / 32; ++k) {
+    const int i = k * 32 + lane;
+    const bool cap = i < n && w.sq[(int)w.moves[i] % 90] != 0;
+    masks[k] = __ballot_sync(kFull, cap);
+    ncap += __popc(masks[k]);
+  }
+  if (ncap == 0) return -1;
+  int k = (int)(x0 % (uint32_t)ncap);
+#pragma unroll
+  for (int r = 0; r < XQ_MAX_MOVES / 32; ++r) {
+    const int c = __popc(masks[r]);
+    if (k < c) return r * 32 + (int)__fns(masks[r], 0, k + 1);
+    k -= c;
+  }
+  return -1;
+}
+
 // Index into w.moves[0..n) chosen by the shared pick rule.
 __device__ __forceinline__ int pick_index(const WarpSmem& w, int n, uint64_t seed, uint32_t game_id,
                                           uint32_t ply, int capture_bias) {
   uint32_t x[4];
   philox4x32(game_id, ply, 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), x);
   if (capture_bias > 0 && (int)(x[1] & 0xFFu) < capture_bias) {
-    const int lane = lane_id();
-    unsigned masks[XQ_MAX_MOVES / 32];
-    int ncap = 0;
-#pragma unroll
-    for (int k = 0; k < XQ_MAX_MOVES / 32; ++k) {
-      const int i = k * 32 + lane;
-      const bool cap = i < n && w.sq[(int)w.moves[i] % 90] != 0;
-      masks[k] = __ballot_sync(kFull, cap);
-      ncap += __popc(masks[k]);
-    }
-    if (ncap > 0) {
-      int k = (int)(x[0] % (uint32_t)ncap);
-#pragma unroll
-      for (int r = 0; r < XQ_MAX_MOVES / 32; ++r) {
-        const int c = __popc(masks[r]);
-        if (k >= 0 && k < c) return r * 32 + (int)__fns(masks[r], 0, k + 1);
-        k -= c;
-      }
-    }
+    const int idx = pick_capture(&w, n, x[0]);
+    if (idx >= 0) return idx;
   }
   return (int)(x[0] % (uint32_t)n);
 }

@@ -8,8 +8,9 @@ SO = os.path.join(HERE, "_build", "libxq_host_mirror.so")
 
 def build() -> str:
     src = os.path.join(HERE, "xq_host_mirror.cpp")
-    hdr = os.path.join(HERE, "..", "..", "chinesechessai_b200", "csrc", "xq_rules.cuh")
-    if not os.path.exists(SO) or max(os.path.getmtime(src), os.path.getmtime(hdr)) > os.path.getmtime(SO):
+    csrc = os.path.join(HERE, "..", "..", "chinesechessai_b200", "csrc")
+    deps = [src, os.path.join(csrc, "xq_rules.cuh"), os.path.join(csrc, "xq_leap_table.inc")]
+    if not os.path.exists(SO) or max(os.path.getmtime(d) for d in deps) > os.path.getmtime(SO):
         os.makedirs(os.path.dirname(SO), exist_ok=True)
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-x", "c++", "-fPIC", "-shared",
                                "-ffp-contract=off", "-Wall", "-o", SO, src])

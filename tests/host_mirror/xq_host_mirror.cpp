@@ -19,7 +19,9 @@ static void stage(WarpSmem& w, const int8_t* board) {
       }
 }
 
-static const uint32_t h_leap[32] = XQ_LEAPER_TABLE_INIT;
+static const uint32_t h_leap[kLeapEntries] = {
+#include "../../chinesechessai_b200/csrc/xq_leap_table.inc"
+};
 
 // mode 0: every candidate through suicide(); mode 1: the kernel's Phase B (relevance filter,
 // sentinel "no move" evaluation, flag bits) executed sequentially.
