@@ -35,8 +35,8 @@ BYTES_PER_STEP_LAUNCH_MODE = 352
 #   fused playout: (board+meta in 128, out 128, result 40) / 70 plies + one 8-byte history append
 BYTES_PER_STEP_FUSED = (128 + 128 + 40) / 70.0 + 8.0
 # warp-instructions per board-step of playout_kernel<false>, from ncu smsp__inst_executed.sum /
-# plies of the same launch (profiles/r1/playout_v1_ncu_summary.txt); refreshed with every capture
-WARP_INST_PER_STEP = 2534.0
+# plies of the same launch (profiles/r1/playout_v3_ncu_summary.txt); refreshed with every capture
+WARP_INST_PER_STEP = 2404.0
 FLOP_PER_LEAF_EVAL = 263_209_216          # ChessNet.forward, SURVEY.md §8d
 MCTS_GAMES, MCTS_SIMS, MCTS_OPENING_PLIES = 4096, 15, 4
 METRIC = "board-steps/sec (legal movegen+step)"

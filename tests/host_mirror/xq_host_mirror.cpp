@@ -74,6 +74,7 @@ extern "C" int xqh_legal_moves(const int8_t* board, int player, int red_king, in
     }
   }
   if (any_irrelevant) w.wl[nwl++] = kWlSentinel;
+  if (ncand_out) ncand_out[1] = nwl, ncand_out[2] = exotic;
   bool cur_bad = false;
   for (int i = 0; i < nwl; ++i) {
     const int item = w.wl[i];
