@@ -37,13 +37,49 @@ class HashEvaluator:
         return pri, val
 
 
+class _FoldedNet(torch.nn.Module):
+    """Inference copy of ChessNet: eval-mode BatchNorm folded into the preceding conv
+    (exact algebra, torch.nn.utils.fusion), weights cast to ``dtype``, channels-last."""
+
+    def __init__(self, net: torch.nn.Module, dtype: torch.dtype):
+        super().__init__()
+        import copy
+        from torch.nn.utils.fusion import fuse_conv_bn_eval
+        n = copy.deepcopy(net).eval()
+        self.stem = fuse_conv_bn_eval(n.conv1, n.bn1)
+        self.blocks = torch.nn.ModuleList(
+            torch.nn.ModuleList([fuse_conv_bn_eval(b.conv1, b.bn1), fuse_conv_bn_eval(b.conv2, b.bn2)])
+            for b in n.res_blocks)
+        self.policy_conv = fuse_conv_bn_eval(n.policy_conv, n.policy_bn)
+        self.value_conv = fuse_conv_bn_eval(n.value_conv, n.value_bn)
+        self.policy_fc, self.value_fc1, self.value_fc2 = n.policy_fc, n.value_fc1, n.value_fc2
+        self.to(dtype=dtype, memory_format=torch.channels_last)
+
+    def forward(self, x):
+        x = torch.relu(self.stem(x))
+        for c1, c2 in self.blocks:
+            x = torch.relu(c2(torch.relu(c1(x))) + x)
+        p = self.policy_fc(torch.relu(self.policy_conv(x)).flatten(1))  # NCHW-order flatten
+        v = torch.relu(self.value_conv(x)).flatten(1)
+        v = torch.tanh(self.value_fc2(torch.relu(self.value_fc1(v))))
+        return p, v
+
+
 class NetEvaluator:
     """encode_board -> ChessNet.forward -> gather+softmax, all on device
-    (neural_network.py:96-126 without the per-sample D2H of :120-124)."""
+    (neural_network.py:96-126 without the per-sample D2H of :120-124).
+
+    ``dtype=float32`` runs the module as given (the reference's precision).  A lower-precision
+    dtype builds a folded inference copy (BN folded, ``dtype`` weights, channels-last); call
+    ``refresh()`` after the weights change (once per training iteration)."""
 
     def __init__(self, net: torch.nn.Module, dtype: torch.dtype = torch.float32):
         self.net = net
         self.dtype = dtype
+        self._fast = None
+
+    def refresh(self) -> None:
+        self._fast = None
 
     @torch.no_grad()
     def __call__(self, leaf_board, leaf_player, leaf_moves, leaf_n):
@@ -51,8 +87,9 @@ class NetEvaluator:
         if self.dtype == torch.float32:
             logits, value = self.net(planes)
         else:
-            with torch.autocast("cuda", dtype=self.dtype):
-                logits, value = self.net(planes)
+            if self._fast is None:
+                self._fast = _FoldedNet(self.net, self.dtype)
+            logits, value = self._fast(planes.contiguous(memory_format=torch.channels_last))
         logits = logits.contiguous()
         if logits.dtype not in (torch.float32, torch.bfloat16):
             logits = logits.float()
