@@ -35,8 +35,10 @@ BYTES_PER_STEP_LAUNCH_MODE = 352
 #   fused playout: (board+meta in 128, out 128, result 40) / 70 plies + one 8-byte history append
 BYTES_PER_STEP_FUSED = (128 + 128 + 40) / 70.0 + 8.0
 # warp-instructions per board-step of playout_kernel<false>, from ncu smsp__inst_executed.sum /
-# plies of the same launch (profiles/r1/playout_v3_ncu_summary.txt); refreshed with every capture
-WARP_INST_PER_STEP = 2404.0
+# plies of the same launch (profiles/r1/playout_v6_ncu_summary.txt); refreshed with every capture
+WARP_INST_PER_STEP = 2303.0
+# dram__bytes_read.sum + dram__bytes_write.sum of one playout launch in the same capture
+DRAM_TRAFFIC_PER_LAUNCH = 23.14e6 + 19.48e6
 FLOP_PER_LEAF_EVAL = 263_209_216          # ChessNet.forward, SURVEY.md §8d
 MCTS_GAMES, MCTS_SIMS, MCTS_OPENING_PLIES = 4096, 15, 4
 METRIC = "board-steps/sec (legal movegen+step)"
@@ -170,9 +172,11 @@ def measure_step_per_launch(torch, BoardBatch, n, first_id, steps, flush):
     return plies / (ms * 1e-3), ms / steps, 2 * PLIES + 2
 
 
-def measure_mcts(torch, dev, plies_timed=6):
+def measure_mcts(torch, dev, plies_timed=6, games=MCTS_GAMES, sims=MCTS_SIMS, label="cfg3"):
     """cfg 3: 4,096 concurrent self-play games, 15 sims/move (2 waves of 8+7), random-init ChessNet
-    (torch.manual_seed(0)), temperature 1.0; games diversified by 4 random opening plies."""
+    (torch.manual_seed(0)), temperature 1.0; games diversified by 4 random opening plies.
+    cfg 4 (per GPU): 16,384 games, 50 sims/move (7 waves)."""
+    MCTS_GAMES, MCTS_SIMS = games, sims
     from chinesechessai_b200.neural_network import ChessNet
     from chinesechessai_b200.self_play import BatchedSelfPlay
     torch.manual_seed(0)
@@ -194,7 +198,7 @@ def measure_mcts(torch, dev, plies_timed=6):
     waves = (MCTS_SIMS + 7) // 8
     evals = played * waves
     return {"metric": "MCTS sims/sec", "value": sims / (ms * 1e-3), "unit": "sims/s",
-            "config": {"workload": f"cfg3: {MCTS_GAMES} concurrent games, {MCTS_SIMS} sims/move, "
+            "config": {"workload": f"{label}: {MCTS_GAMES} concurrent games, {MCTS_SIMS} sims/move, "
                                    f"random-init ChessNet, T=1.0, {MCTS_OPENING_PLIES} random opening plies",
                        "plies_timed": plies_timed, "nn_dtype": "bf16 autocast (reference: fp32)"},
             "ms_per_ply": ms / plies_timed, "unique_leaf_evals_per_s": evals / (ms * 1e-3),
@@ -330,7 +334,11 @@ def run_ours(args):
                 "api": "xq_playout_host (pinned host buffers)"},
         "gpu_launches": int(launches + e2e_launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / hbm_peak,
+                     "traffic": DRAM_TRAFFIC_PER_LAUNCH if n == BOARDS else None,
+                     "traffic_note": "ncu dram bytes read+write per launch (profiles/r1/playout_v6_ncu_summary.txt); "
+                                     "algorithmic bytes per launch = %.2e" % (BYTES_PER_STEP_FUSED * plies_per_launch),
+                     "peak_source": peak_src,
                      "kernel": "xq::playout_kernel<false>",
                      "bytes_per_board_step": BYTES_PER_STEP_FUSED,
                      "kernel_ms_per_launch": kern_ms / args.steps,
@@ -365,6 +373,11 @@ def run_ours(args):
         mc["roofline"]["frac"] = mc["roofline"]["achieved"] / tf_peak
         mc["gpu_launches"] = int(lib.xq_launch_count() - l0)
         out["mcts"] = mc
+        if not args.no_cfg4:
+            m4 = measure_mcts(torch, dev, plies_timed=2, games=16384, sims=50, label="cfg4 (one GPU's shard)")
+            m4["roofline"]["peak"] = tf_peak
+            m4["roofline"]["frac"] = m4["roofline"]["achieved"] / tf_peak
+            out["mcts_cfg4"] = m4
     # ---- CPU baseline: C port of the reference path on the host cores, bounded sample ------
     if world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
@@ -388,6 +401,7 @@ def main():
     ap.add_argument("--boards", type=int, default=BOARDS)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--fast", action="store_true", help="skip the step-per-launch and MCTS legs")
+    ap.add_argument("--no-cfg4", action="store_true", help="skip the 16,384-game x 50-sim MCTS leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(kThreads)
   for (int i = lane; i < n; i += 32) row[i] = w.moves[i];
   if (lane == 0) {
     n_moves[g] = (int16_t)n;
-    if (in_check_out) in_check_out[g] = in_check(w, G, G.player) ? 1 : 0;
+    if (in_check_out) in_check_out[g] = in_check_cold(&w, &G, G.player) ? 1 : 0;
     if (G.flags != flags0) reinterpret_cast<uint8_t*>(meta + g)[6] = (uint8_t)G.flags;
   }
 }
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(kThreads)
 // Fused random playout: state stays in shared memory / registers for all plies.
 __device__ __forceinline__ uint64_t dbits(double d) { return (uint64_t)__double_as_longlong(d); }
 
-template <bool TRACE, int MINB>
+template <bool TRACE, int MINB, bool SYNC>
 __global__ void __launch_bounds__(kThreads, MINB)
     playout_kernel(int8_t* __restrict__ board, xq_meta* __restrict__ meta,
                    uint64_t* __restrict__ pos_hist, int hist_cap, uint64_t seed,
@@ -219,8 +219,10 @@ __global__ void __launch_bounds__(kThreads, MINB)
                    double* __restrict__ tr_reward, uint8_t* __restrict__ tr_flags,
                    int8_t* __restrict__ tr_boards, int n_games) {
   __shared__ WarpSmem slab[kWarpsPerCta];
-  const int g = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-  if (g >= n_games) return;
+  const int g_raw = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  const bool valid = g_raw < n_games;
+  if (!SYNC && !valid) return;
+  const int g = valid ? g_raw : n_games - 1;  // SYNC: surplus warps idle through the barriers
   WarpSmem& w = slab[threadIdx.x >> 5];
   const int lane = lane_id();
   load_board(w, board + (size_t)g * XQ_BOARD_STRIDE);
@@ -259,15 +261,18 @@ __global__ void __launch_bounds__(kThreads, MINB)
   };
   // One movegen site per iteration: it closes the previous make_move (:354,:376 need the new
   // side's move count) and is the get_legal_moves of the next ply (self_play.py:205).
-  for (;;) {
-    const int n = movegen(w, G, g_leap);
-    if (pending) {
-      step_finish(w, G, o, n, hist);
+  // Returns false when the game is over.
+  bool kingcap = false;  // the applied move captured a king: no movegen, no terminal chain (:352)
+  auto one_ply = [&]() -> bool {
+    bool checking = false;
+    const int n = kingcap ? -1 : movegen(w, G, g_leap, pending ? &checking : nullptr);
+    if (pending) {  // single finish/account site (code size)
+      step_finish(w, G, o, n, checking, hist);
       pending = false;
       account();
-      if (o.done) break;
+      if (o.done) return false;
     }
-    if (ply >= max_plies || n == 0) break;  // self_play.py:203,207
+    if (ply >= max_plies || n == 0) return false;  // self_play.py:203,207
     max_legal = max(max_legal, n);
     const int idx = pick_index(w, n, seed, gid, (uint32_t)ply, capture_bias);
     const int mv = w.moves[idx];
@@ -287,11 +292,21 @@ __global__ void __launch_bounds__(kThreads, MINB)
     }
     __syncwarp();
     o = step_apply(w, G, mv, hist, hist_cap);
-    if (o.done) {  // king capture: make_move skips the terminal chain (:352)
-      account();
-      break;
-    }
+    kingcap = o.done != 0;
     pending = true;
+    return true;
+  };
+  if (SYNC) {
+    // Phase-aligned variant: the 8 warps of a CTA start every ply together, so they fetch the
+    // same part of the (larger than L1.5) loop body at about the same time.
+    bool alive = valid;
+    while (__syncthreads_or(alive ? 1 : 0)) {
+      if (alive) alive = one_ply();
+    }
+    if (!valid) return;
+  } else {
+    while (one_ply()) {
+    }
   }
   const uint64_t fkey = G.bkey ^ side_key(G.player);
   store_board(w, board + (size_t)g * XQ_BOARD_STRIDE);
@@ -472,16 +487,22 @@ int xq_playout(int8_t* board, xq_meta* meta, uint64_t* pos_hist, int hist_cap, u
   }();
   const dim3 grid(ctas_for(n_games)), block(kThreads);
   const cudaStream_t st = (cudaStream_t)stream;
-#define XQ_LAUNCH_PLAYOUT(T, M)                                                                  \
-  playout_kernel<T, M><<<grid, block, 0, st>>>(board, meta, pos_hist, hist_cap, seed,            \
-                                               first_game_id, max_plies, capture_bias, results, \
-                                               tr_moves, tr_n, tr_pick, tr_reward, tr_flags,     \
-                                               tr_boards, n_games)
-  if (trace) XQ_LAUNCH_PLAYOUT(true, 4);
-  else if (minb == 2) XQ_LAUNCH_PLAYOUT(false, 2);
-  else if (minb == 3) XQ_LAUNCH_PLAYOUT(false, 3);
-  else if (minb == 5) XQ_LAUNCH_PLAYOUT(false, 5);
-  else XQ_LAUNCH_PLAYOUT(false, 4);
+#define XQ_LAUNCH_PLAYOUT(T, M, S)                                                               \
+  playout_kernel<T, M, S><<<grid, block, 0, st>>>(board, meta, pos_hist, hist_cap, seed,         \
+                                                  first_game_id, max_plies, capture_bias,        \
+                                                  results, tr_moves, tr_n, tr_pick, tr_reward,   \
+                                                  tr_flags, tr_boards, n_games)
+  static const bool sync_plies = [] {
+    const char* e = getenv("XQ_PLAYOUT_SYNC");
+    return e ? atoi(e) != 0 : false;
+  }();
+  if (trace) XQ_LAUNCH_PLAYOUT(true, 4, false);
+  else if (sync_plies && minb == 3) XQ_LAUNCH_PLAYOUT(false, 3, true);
+  else if (sync_plies) XQ_LAUNCH_PLAYOUT(false, 4, true);
+  else if (minb == 2) XQ_LAUNCH_PLAYOUT(false, 2, false);
+  else if (minb == 3) XQ_LAUNCH_PLAYOUT(false, 3, false);
+  else if (minb == 5) XQ_LAUNCH_PLAYOUT(false, 5, false);
+  else XQ_LAUNCH_PLAYOUT(false, 4, false);
 #undef XQ_LAUNCH_PLAYOUT
   return check_launch("xq_playout");
 }

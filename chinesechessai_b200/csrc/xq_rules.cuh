@@ -363,6 +363,149 @@ XQ_HD bool touches(int kr, int kc, int s) {
   return dr == 0 || dc == 0 || (dr <= 2 && dc <= 2 && dr + dc <= 3);
 }
 
+// ---- fast legality test for regular positions -----------------------------------
+// Regular = exactly one own king on its cached square and no enemy K/A/B within 3 rows of it
+// (every position reachable in play).  Then only R, C, N and P can attack the king, the king
+// square is occupied, and for a NON-king move the test reduces to bit operations on masks that
+// are computed once per position: occupancy of the king's row/column, the enemy rooks / cannons
+// / pawns on them, the enemy knights on the 8 knight squares and the 4 leg squares.
+struct FastCtx {
+  int K, kr, kc, geo;
+  unsigned rowm, colm;              // occupancy of K's row (bit = column) / column (bit = row)
+  unsigned er_row, ec_row, ep_row;  // enemy rooks / cannons / pawns on K's row
+  unsigned er_col, ec_col, ep_col;  // ... on K's column
+  unsigned ekn;                     // bit 2*diag+t: enemy knight on K+(2a,b) [t=0] / K+(a,2b) [t=1]
+  unsigned legocc;                  // bit diag: leg K+(a,b) occupied or off-board
+  unsigned between;                 // rows strictly between the two cached kings (same file)
+  bool same_file, side_ok;
+};
+
+// diag index of probe_diag: bit1 = (dr>0), bit0 = (dc>0)
+XQ_HD int diag_index(int dr, int dc) { return (dr > 0 ? 2 : 0) + (dc > 0 ? 1 : 0); }
+
+// Sequential construction (host mirror); the kernel builds the same masks with ballots.
+XQ_HD FastCtx make_fast_ctx(const WarpSmem& w, const Game& g) {
+  FastCtx f{};
+  const int player = g.player, es = -player;
+  f.K = player == 1 ? g.red_king : g.black_king;
+  f.kr = f.K / 9;
+  f.kc = f.K - f.kr * 9;
+  f.geo = player;
+  f.rowm = w.rows[f.kr];
+  f.colm = w.cols[f.kc];
+  for (int c = 0; c < 9; ++c) {
+    const int q = w.sq[f.kr * 9 + c];
+    f.er_row |= (q == es * ROOK ? 1u : 0u) << c;
+    f.ec_row |= (q == es * CANNON ? 1u : 0u) << c;
+    f.ep_row |= (q == es * PAWN ? 1u : 0u) << c;
+  }
+  for (int r = 0; r < 10; ++r) {
+    const int q = w.sq[r * 9 + f.kc];
+    f.er_col |= (q == es * ROOK ? 1u : 0u) << r;
+    f.ec_col |= (q == es * CANNON ? 1u : 0u) << r;
+    f.ep_col |= (q == es * PAWN ? 1u : 0u) << r;
+  }
+  for (int d = 0; d < 4; ++d) {
+    const int a = (d & 2) ? 1 : -1, b = (d & 1) ? 1 : -1;
+    const int lr = f.kr + a, lc = f.kc + b;
+    const bool lon = lr >= 0 && lr <= 9 && lc >= 0 && lc <= 8;
+    if (!lon || w.sq[lr * 9 + lc] != 0) f.legocc |= 1u << d;
+    const int r2 = f.kr + 2 * a, c2 = f.kc + 2 * b;
+    if (lon && r2 >= 0 && r2 <= 9 && w.sq[r2 * 9 + lc] == es * KNIGHT) f.ekn |= 1u << (2 * d);
+    if (lon && c2 >= 0 && c2 <= 8 && w.sq[lr * 9 + c2] == es * KNIGHT) f.ekn |= 1u << (2 * d + 1);
+  }
+  f.side_ok = player == 1 ? f.kr < 5 : f.kr >= 5;
+  const int ek = player == 1 ? g.black_king : g.red_king;
+  if (ek >= 0 && ek % 9 == f.kc) {
+    const int er = ek / 9, lo = xq_min(er, f.kr), hi = xq_max(er, f.kr);
+    f.same_file = true;
+    f.between = ((1u << hi) - 1u) & ~((2u << lo) - 1u);
+  }
+  return f;
+}
+
+// Kings-facing verdict for a move of the own king to `to` (chess_env.py:448-451,:466-495);
+// p = probe built at the king's NEW square with the move applied.
+XQ_HD bool king_move_facing(const Game& g, const Probe& p, int to) {
+  const int ek = g.player == 1 ? g.black_king : g.red_king;
+  if (ek < 0) return false;
+  const int er = ek / 9, ec = ek - er * 9;
+  if (ec != p.kc) return false;
+  const int lo = xq_min(er, p.kr), hi = xq_max(er, p.kr);
+  const unsigned between = ((1u << hi) - 1u) & ~((2u << lo) - 1u);
+  (void)to;
+  return (p.colm & between) == 0;
+}
+
+// isolate the lowest / highest set bit (0 if none)
+XQ_HD unsigned low_bit(unsigned x) { return x & (0u - x); }
+XQ_HD unsigned high_bit(unsigned x) { return x ? 0x80000000u >> xq_clz(x) : 0u; }
+
+// _is_move_suicide for a non-king move of the side to move in a regular position
+// (from < 0: the position itself).  Same verdict as suicide(); pure register arithmetic.
+XQ_HD bool suicide_fast(const FastCtx& f, int from, int to) {
+  unsigned rowm = f.rowm, colm = f.colm;
+  unsigned er_row = f.er_row, ec_row = f.ec_row, ep_row = f.ep_row;
+  unsigned er_col = f.er_col, ec_col = f.ec_col, ep_col = f.ep_col;
+  unsigned ekn = f.ekn, legocc = f.legocc;
+  if (from >= 0) {
+    const int fr = from / 9, fc = from - fr * 9, tr = to / 9, tc = to - tr * 9;
+    if (fr == f.kr) rowm &= ~(1u << fc);
+    if (fc == f.kc) colm &= ~(1u << fr);
+    if (tr == f.kr) {  // own piece lands on the row: occupied, whatever stood there is gone
+      const unsigned b = 1u << tc;
+      rowm |= b; er_row &= ~b; ec_row &= ~b; ep_row &= ~b;
+    }
+    if (tc == f.kc) {
+      const unsigned b = 1u << tr;
+      colm |= b; er_col &= ~b; ec_col &= ~b; ep_col &= ~b;
+    }
+    const int fdr = fr - f.kr, fdc = fc - f.kc, tdr = tr - f.kr, tdc = tc - f.kc;
+    const int afr = xq_abs(fdr), afc = xq_abs(fdc), atr = xq_abs(tdr), atc = xq_abs(tdc);
+    if (afr == 1 && afc == 1) legocc &= ~(1u << diag_index(fdr, fdc));
+    if (atr == 1 && atc == 1) legocc |= 1u << diag_index(tdr, tdc);
+    if (atr + atc == 3 && atr != 0 && atc != 0)  // lands on a knight square: that knight is gone
+      ekn &= ~(1u << (2 * diag_index(tdr, tdc) + (atr == 1 ? 1 : 0)));
+  }
+  bool hit = false;
+  {  // (0,+1): nearest piece toward higher columns
+    const unsigned a = rowm >> (f.kc + 1), first = low_bit(a), second = low_bit(a ^ first);
+    hit |= (first & (er_row >> (f.kc + 1))) != 0;
+    hit |= (second & (ec_row >> (f.kc + 1))) != 0;
+    hit |= f.side_ok && (1u & a & (ep_row >> (f.kc + 1))) != 0;
+  }
+  {  // (0,-1)
+    const unsigned lowm = (1u << f.kc) - 1u;
+    const unsigned b = rowm & lowm, first = high_bit(b), second = high_bit(b ^ first);
+    hit |= (first & er_row) != 0;
+    hit |= (second & ec_row) != 0;
+    hit |= f.side_ok && f.kc > 0 && ((b & ep_row) >> (f.kc - 1)) & 1u;
+  }
+  {  // (+1,0): a pawn below K attacks iff pawns move to smaller rows (geo==1), chess_env.py:241
+    const unsigned a = colm >> (f.kr + 1), first = low_bit(a), second = low_bit(a ^ first);
+    hit |= (first & (er_col >> (f.kr + 1))) != 0;
+    hit |= (second & (ec_col >> (f.kr + 1))) != 0;
+    hit |= f.geo == 1 && (1u & a & (ep_col >> (f.kr + 1))) != 0;
+  }
+  {  // (-1,0)
+    const unsigned lowm = (1u << f.kr) - 1u;
+    const unsigned b = colm & lowm, first = high_bit(b), second = high_bit(b ^ first);
+    hit |= (first & er_col) != 0;
+    hit |= (second & ec_col) != 0;
+    hit |= f.geo == -1 && f.kr > 0 && ((b & ep_col) >> (f.kr - 1)) & 1u;
+  }
+  // knights: a free leg exposes the two knight squares behind it (:182-197)
+  const unsigned knpair = (ekn | (ekn >> 1)) & 0x55u;  // bit 2*diag: a knight on either square
+  const unsigned freeleg = ~legocc & 0xFu;
+  hit |= (((freeleg & 1u) ? knpair : 0u) & 0x01u) != 0;
+  hit |= (((freeleg & 2u) ? knpair : 0u) & 0x04u) != 0;
+  hit |= (((freeleg & 4u) ? knpair : 0u) & 0x10u) != 0;
+  hit |= (((freeleg & 8u) ? knpair : 0u) & 0x40u) != 0;
+  // kings facing (:466-495): caches are unchanged by a non-king move
+  hit |= f.same_file && (colm & f.between) == 0;
+  return hit;
+}
+
 // ---- move generation --------------------------------------------------------
 // One work item of candidate generation: (own piece at `from`, direction d of
 // the reference's per-piece generator order).  Produces, in generator order,
@@ -445,6 +588,26 @@ static __device__ const uint32_t g_leap[kLeapEntries] = {
 #include "xq_leap_table.inc"
 };
 
+// Cold paths are kept out of line: the fused loop's hot code has to stay small enough for the
+// L1.5 instruction cache (profiles/r1: v2 72 KB -> no_instruction 3.0 stalls per issue).
+static __device__ __noinline__ bool in_check_cold(const WarpSmem* wp, const Game* gp, int player) {
+  return in_check(*wp, *gp, player);
+}
+
+// Irregular (poked) boards — several kings, stale or missing cache, enemy K/A/B near the
+// king: every candidate through the general suicide() (:118).  Cold path.
+static __device__ __noinline__ void legality_generic(WarpSmem* wp, const Game* gp, int ncand) {
+  WarpSmem& w = *wp;
+  const int lane = threadIdx.x & 31;
+  for (int base = 0; base < ncand; base += 32) {
+    const int j = base + lane;
+    if (j < ncand) {
+      const int c = w.cand[j];
+      if (suicide(w, *gp, c >> 8, c & 0x7f, true)) w.cand[j] = (uint16_t)(c | kCandIllegal);
+    }
+  }
+}
+
 __device__ __forceinline__ int warp_sum(int v) { return (int)__reduce_add_sync(kFull, (unsigned)v); }
 
 // get_legal_moves (chess_env.py:76-121).  Fills w.moves in the reference's
@@ -453,7 +616,8 @@ __device__ __forceinline__ int warp_sum(int v) { return (int)__reduce_add_sync(k
 // Phase B: candidates that can change the king's safety (or all of them on irregular boards)
 // go through suicide() 32 per round; the others inherit the verdict of the position itself.
 // Ordered compaction with ballot/popc.
-__device__ __forceinline__ int movegen(WarpSmem& w, Game& g, const uint32_t* __restrict__ leap) {
+__device__ __forceinline__ int movegen(WarpSmem& w, Game& g, const uint32_t* __restrict__ leap,
+                                       bool* checked_out = nullptr) {
   const int lane = lane_id();
   const unsigned lt = (1u << lane) - 1u;
   const int player = g.player;
@@ -479,6 +643,7 @@ __device__ __forceinline__ int movegen(WarpSmem& w, Game& g, const uint32_t* __r
   // Phase A
   int ncand = 0;
   const int n_items = n_own * 4;
+#pragma unroll 1
   for (int base = 0; base < n_items; base += 32) {
     const int t = base + lane;
     Item it{0, 0, 0, -1, -1};
@@ -505,46 +670,133 @@ __device__ __forceinline__ int movegen(WarpSmem& w, Game& g, const uint32_t* __r
   }
   __syncwarp();
 
-  // Phase B.1: classify, build the worklist
-  const int kr = ownK >= 0 ? ownK / 9 : 0, kc = ownK >= 0 ? ownK - kr * 9 : 0;
-  int nwl = 0;
-  bool any_irrelevant = false;
-  for (int base = 0; base < ncand; base += 32) {
-    const int j = base + lane;
-    bool rel = false, valid = j < ncand;
-    if (valid) {
-      const int c = w.cand[j], from = c >> 8, to = c & 0x7f;
-      rel = exotic || from == ownK || touches(kr, kc, from) || touches(kr, kc, to);
-      if (!rel) w.cand[j] = (uint16_t)(c | kCandIrrelevant);
-    }
-    const unsigned m = __ballot_sync(kFull, rel);
-    if (rel) w.wl[nwl + __popc(m & lt)] = (uint16_t)j;
-    nwl += __popc(m);
-    any_irrelevant |= __ballot_sync(kFull, valid && !rel) != 0;
-  }
-  if (any_irrelevant && lane == 0) w.wl[nwl] = kWlSentinel;  // nwl < ncand <= XQ_CAND_CAP here
-  nwl += any_irrelevant ? 1 : 0;
-  __syncwarp();
-
-  // Phase B.2: full legality test of the worklist (:118)
   bool cur_bad = false;
-  for (int base = 0; base < nwl; base += 32) {
-    const int i = base + lane;
-    bool is_cur = false, bad = false;
-    if (i < nwl) {
-      const int item = w.wl[i];
-      is_cur = item == kWlSentinel;
-      const int c = is_cur ? 0 : (int)w.cand[item];
-      // ONE call site: the sentinel lane evaluates the position itself (from = -1)
-      bad = suicide(w, g, is_cur ? -1 : (c >> 8), is_cur ? -1 : (c & 0x7f), exotic);
-      if (bad && !is_cur) w.cand[item] = (uint16_t)(c | kCandIllegal);
+  int kfirst = 0, kcount = 0;  // the own king's candidates (contiguous, <= 4) on regular boards
+  if (!exotic) {
+    // ---- regular position: bitmask legality (suicide_fast) + one probe round for king moves
+    FastCtx f;
+    {
+      const int es = -player;
+      f.K = ownK; f.kr = ownK / 9; f.kc = ownK - f.kr * 9; f.geo = player;
+      f.rowm = w.rows[f.kr];
+      f.colm = w.cols[f.kc];
+      int q = 0;  // lanes 0..8: the king's row; lanes 16..25: the king's column
+      if (lane < 9) q = w.sq[f.kr * 9 + lane];
+      else if (lane >= 16 && lane < 26) q = w.sq[(lane - 16) * 9 + f.kc];
+      const unsigned br = __ballot_sync(kFull, q == es * ROOK);
+      const unsigned bc = __ballot_sync(kFull, q == es * CANNON);
+      const unsigned bp = __ballot_sync(kFull, q == es * PAWN);
+      f.er_row = br & 0x1FFu; f.ec_row = bc & 0x1FFu; f.ep_row = bp & 0x1FFu;
+      f.er_col = (br >> 16) & 0x3FFu; f.ec_col = (bc >> 16) & 0x3FFu; f.ep_col = (bp >> 16) & 0x3FFu;
+      bool flag = false;  // lanes 0..7: knight squares; lanes 8..11: legs
+      if (lane < 12) {
+        const int d = lane < 8 ? lane >> 1 : lane - 8;
+        const int a = (d & 2) ? 1 : -1, b = (d & 1) ? 1 : -1;
+        const int lr = f.kr + a, lc = f.kc + b;
+        const bool lon = lr >= 0 && lr <= 9 && lc >= 0 && lc <= 8;
+        if (lane >= 8) {
+          flag = !lon || w.sq[lr * 9 + lc] != 0;
+        } else if (lon) {
+          const int r2 = (lane & 1) ? lr : f.kr + 2 * a, c2 = (lane & 1) ? f.kc + 2 * b : lc;
+          flag = r2 >= 0 && r2 <= 9 && c2 >= 0 && c2 <= 8 && w.sq[r2 * 9 + c2] == es * KNIGHT;
+        }
+      }
+      const unsigned b2 = __ballot_sync(kFull, flag);
+      f.ekn = b2 & 0xFFu;
+      f.legocc = (b2 >> 8) & 0xFu;
+      f.side_ok = player == 1 ? f.kr < 5 : f.kr >= 5;
+      const int ek = player == 1 ? g.black_king : g.red_king;
+      f.same_file = false;
+      f.between = 0;
+      if (ek >= 0 && ek % 9 == f.kc) {
+        const int er = ek / 9, lo = min(er, f.kr), hi = max(er, f.kr);
+        f.same_file = true;
+        f.between = ((1u << hi) - 1u) & ~((2u << lo) - 1u);
+      }
     }
-    cur_bad |= __ballot_sync(kFull, is_cur && bad) != 0;
+    // B.1: classify — king move / touches the king's lines / cannot matter
+    int nwl = 0;
+    bool any_irrelevant = false;
+#pragma unroll 1
+    for (int base = 0; base < ncand; base += 32) {
+      const int j = base + lane;
+      bool rel = false, isk = false;
+      const bool valid = j < ncand;
+      if (valid) {
+        const int c = w.cand[j], from = c >> 8, to = c & 0x7f;
+        isk = from == ownK;
+        rel = !isk && (touches(f.kr, f.kc, from) || touches(f.kr, f.kc, to));
+        if (!rel && !isk) w.cand[j] = (uint16_t)(c | kCandIrrelevant);
+      }
+      const unsigned m = __ballot_sync(kFull, rel), mk = __ballot_sync(kFull, isk);
+      if (rel) w.wl[nwl + __popc(m & lt)] = (uint16_t)j;
+      nwl += __popc(m);
+      if (mk && kcount == 0) kfirst = base + __ffs(mk) - 1;
+      kcount += __popc(mk);
+      any_irrelevant |= __ballot_sync(kFull, valid && !rel && !isk) != 0;
+    }
+    if (any_irrelevant && lane == 0) w.wl[nwl] = kWlSentinel;
+    nwl += any_irrelevant ? 1 : 0;
+    __syncwarp();
+    // B.2a: bitmask test of the worklist (the sentinel evaluates the position itself)
+#pragma unroll 1
+    for (int base = 0; base < nwl; base += 32) {
+      const int i = base + lane;
+      bool is_cur = false, bad = false;
+      if (i < nwl) {
+        const int item = w.wl[i];
+        is_cur = item == kWlSentinel;
+        const int c = is_cur ? 0 : (int)w.cand[item];
+        bad = suicide_fast(f, is_cur ? -1 : (c >> 8), is_cur ? -1 : (c & 0x7f));
+        if (bad && !is_cur) w.cand[item] = (uint16_t)(c | kCandIllegal);
+      }
+      cur_bad |= __ballot_sync(kFull, is_cur && bad) != 0;
+    }
+  } else {
+    legality_generic(&w, &g, ncand);
+  }
+  // Probe round — ONE inlined copy of the 8-probe attack test per kernel.  Item 0: is this
+  // side's king attacked under the PREVIOUS mover's geometry, i.e. make_move's is_checking
+  // (:317; evaluated here because it needs the same post-move board).  Items 1..kcount: the own
+  // king's moves on regular boards (8 probes at the new square + kings facing, :448-451).
+  {
+    const bool want_check = checked_out != nullptr && ownK >= 0;
+    const int n_it = 1 + kcount;
+    bool checked = false;
+#pragma unroll 1
+    for (int base = 0; base < n_it * 8; base += 32) {
+      const int idx = base + lane, it = idx >> 3, pr = idx & 7;
+      bool active = it < n_it, hit = false;
+      int K = ownK, geo = -player, from = -1, to = -1, mover = 0;
+      if (it == 0) {
+        active = want_check;
+      } else if (active) {
+        to = w.cand[kfirst + it - 1] & 0x7f;
+        K = to; geo = player; from = ownK; mover = player * KING;
+      }
+      if (active) {
+        const Probe p = make_probe(w, K, -player, geo, from, to, mover);
+        hit = pr < 4 ? probe_ray(w, p, pr) : probe_diag(w, p, pr - 4, it == 0);
+        if (it > 0 && pr == 0) {  // kings facing after the king's own move
+          const int ek = player == 1 ? g.black_king : g.red_king;
+          if (ek >= 0 && ek % 9 == p.kc) {
+            const int er = ek / 9, lo = min(er, p.kr), hi = max(er, p.kr);
+            hit |= (p.colm & (((1u << hi) - 1u) & ~((2u << lo) - 1u))) == 0;
+          }
+        }
+      }
+      const unsigned bal = __ballot_sync(kFull, active && hit);
+      if (base == 0) checked = (bal & 0xFFu) != 0;
+      if (active && it > 0 && pr == 0 && ((bal >> (lane & 24)) & 0xFFu))
+        w.cand[kfirst + it - 1] |= kCandIllegal;
+    }
+    if (checked_out) *checked_out = checked;
   }
   __syncwarp();
 
   // Phase B.3: ordered compaction
   int n_legal = 0;
+#pragma unroll 1
   for (int base = 0; base < ncand; base += 32) {
     const int j = base + lane;
     bool ok = false;
@@ -566,14 +818,6 @@ __device__ __forceinline__ int movegen(WarpSmem& w, Game& g, const uint32_t* __r
   return n_legal;
 }
 
-// _is_in_check(player) with one lane per probe direction (chess_env.py:506-548).
-__device__ __forceinline__ bool in_check_warp(const WarpSmem& w, const Game& g, int player) {
-  const int K = player == 1 ? g.red_king : g.black_king;
-  if (K < 0) return false;  // :517 (warp-uniform)
-  const int lane = lane_id();
-  const bool hit = lane < 8 ? attacked_dir(w, K, -player, g.player, lane) : false;
-  return __any_sync(kFull, hit);
-}
 #endif  // __CUDACC__
 
 // ---- step -------------------------------------------------------------------
@@ -608,10 +852,13 @@ struct StepOut {
   int done;
   int n_next;     // legal moves of the new side to move (in w.moves) or -1 if not generated
   uint64_t key_next;  // position key of the new board ‖ new side to move
+  int from, to, moving, captured;  // the applied move (for the deferred positional reward)
 };
 
-// make_move part 1 (chess_env.py:253-349): apply, caches, capture/check/positional reward,
-// history appends, side switch.  o.done is set only by a king capture (:292-297).
+// make_move part 1 (chess_env.py:253-314,:338,:348-349): apply, caches, capture reward,
+// position-history append, side switch.  o.done is set only by a king capture (:292-297).
+// The check test (:317) needs the post-move board too and is evaluated by the movegen that
+// follows (one probe round serves both); its consequences (:318-345) are in step_finish.
 __device__ __forceinline__ StepOut step_apply(WarpSmem& w, Game& g, int move,
                                               uint64_t* __restrict__ hist, int hist_cap) {
   const int lane = lane_id();
@@ -649,66 +896,66 @@ __device__ __forceinline__ StepOut step_apply(WarpSmem& w, Game& g, int move,
   g.no_capture = captured != 0 ? 0 : g.no_capture + 1;  // :282-285
 
   StepOut o;
-  double reward = 0.0;
-  int is_int = 1, done = 0;
+  o.from = from; o.to = to; o.moving = moving; o.captured = captured;
+  o.reward = 0.0;
+  o.is_int = 1;
+  o.done = 0;
   const int acap = captured < 0 ? -captured : captured;
   if (acap == KING) {  // :292-297
     g.winner = g.player;
-    reward = 100.0;
-    done = 1;
+    o.reward = 100.0;
+    o.done = 1;
     g.reason = XQ_REASON_KING_CAPTURE;
+    g.done = 1;
   } else if (captured != 0) {  // :300-314
     const double base = acap == ROOK ? 9.0 : acap == CANNON ? 4.5 : acap == KNIGHT ? 4.0
                         : (acap == BISHOP || acap == ADVISOR) ? 2.0 : acap == PAWN ? 1.0 : 0.0;
-    reward = xq_dmul(base, 2.0);
-    is_int = 0;
-    if (acap == ADVISOR || acap == BISHOP) reward = xq_dadd(reward, 3.0);
+    o.reward = xq_dmul(base, 2.0);
+    o.is_int = 0;
+    if (acap == ADVISOR || acap == BISHOP) o.reward = xq_dadd(o.reward, 3.0);
   }
-
-  const bool checking = in_check_warp(w, g, -g.player);  // :317, geometry = mover
-  if (!done && checking) {                                // :318-327
-    if (g.cchecks == 0) { reward = xq_dadd(reward, 15.0); is_int = 0; }
-    else if (g.cchecks == 1) { reward = xq_dadd(reward, 10.0); is_int = 0; }
-    else if (g.cchecks == 2) { reward = xq_dadd(reward, 5.0); is_int = 0; }
-    g.cchecks += 1;
-  } else {  // :328-335
-    g.cchecks = 0;
-    if (captured == 0 && !done) {
-      const int ek = g.player == 1 ? g.black_king : g.red_king;
-      const double pcg = position_change(moving < 0 ? -moving : moving, g.player, from, to, ek);
-      reward = xq_dadd(reward, xq_dmul(pcg, 0.01));
-      is_int = 0;
-    }
-  }
-
   if (g.hist_len < hist_cap) {  // :338, stored with the MOVER's side byte
     if (lane == 0) hist[g.hist_len] = g.bkey ^ side_key(g.player);
     g.hist_len += 1;
   } else {
     g.flags |= XQ_F_OVERFLOW;
   }
-  g.check_bits = (g.check_bits << 1) | (checking ? 1u : 0u);  // :341
-  g.check_len += 1;
-
   g.player = -g.player;  // :348-349
   g.move_count += 1;
   o.key_next = g.bkey ^ side_key(g.player);
   o.n_next = -1;
-  o.reward = reward;
-  o.is_int = is_int;
-  o.done = done;
-  if (done) g.done = 1;
   __syncwarp();
   return o;
 }
 
-// make_move part 2 (chess_env.py:352-404): terminal chain for the side now to move, given its
-// legal-move count (the one movegen that also serves the next ply), then the 70-ply cap.
+// make_move part 2.  `checking` = is_checking of :317 (false after a king capture, whose cache
+// is None): check bonus / consecutive_checks / positional reward (:318-335), check_history
+// append (:341); then, unless the king was captured, the terminal chain for the side now to
+// move given its legal-move count (:352-397) and the 70-ply cap (:400-404).
 __device__ __forceinline__ void step_finish(const WarpSmem& w, Game& g, StepOut& o, int n_legal,
-                                            const uint64_t* __restrict__ hist) {
+                                            bool checking, const uint64_t* __restrict__ hist) {
   const int lane = lane_id();
+  const int mover = -g.player;
+  if (!o.done && checking) {  // :318-327
+    if (g.cchecks == 0) { o.reward = xq_dadd(o.reward, 15.0); o.is_int = 0; }
+    else if (g.cchecks == 1) { o.reward = xq_dadd(o.reward, 10.0); o.is_int = 0; }
+    else if (g.cchecks == 2) { o.reward = xq_dadd(o.reward, 5.0); o.is_int = 0; }
+    g.cchecks += 1;
+  } else {  // :328-335
+    g.cchecks = 0;
+    if (o.captured == 0 && !o.done) {
+      const int ek = mover == 1 ? g.black_king : g.red_king;
+      const double pcg = position_change(o.moving < 0 ? -o.moving : o.moving, mover, o.from, o.to, ek);
+      o.reward = xq_dadd(o.reward, xq_dmul(pcg, 0.01));
+      o.is_int = 0;
+    }
+  }
+  g.check_bits = (g.check_bits << 1) | (checking ? 1u : 0u);  // :341
+  g.check_len += 1;
+  if (o.done) return;  // king capture: no terminal chain (:352), no move cap (:400 "not done")
+
   o.n_next = n_legal;
-  const bool chk_now = n_legal == 0 ? in_check_warp(w, g, g.player) : false;
+  const bool chk_now = n_legal == 0 ? in_check_cold(&w, &g, g.player) : false;
   if (n_legal == 0 && chk_now) {  // :354, :614-628
     o.done = 1; o.reward = 200.0; o.is_int = 1;
     g.winner = -g.player;
@@ -748,10 +995,10 @@ __device__ __forceinline__ void step_finish(const WarpSmem& w, Game& g, StepOut&
 __device__ __forceinline__ StepOut step(WarpSmem& w, Game& g, int move, uint64_t* __restrict__ hist,
                                         int hist_cap, const uint32_t* __restrict__ leap) {
   StepOut o = step_apply(w, g, move, hist, hist_cap);
-  if (!o.done) {  // :352
-    const int n_legal = movegen(w, g, leap);
-    step_finish(w, g, o, n_legal, hist);
-  }
+  bool checking = false;
+  int n_legal = -1;
+  if (!o.done) n_legal = movegen(w, g, leap, &checking);  // :317 + :354/:376 in one pass
+  step_finish(w, g, o, n_legal, checking, hist);
   return o;
 }
 

@@ -62,6 +62,31 @@ extern "C" int xqh_legal_moves(const int8_t* board, int player, int red_king, in
     return n;
   }
   const int kr = ownK >= 0 ? ownK / 9 : 0, kc = ownK >= 0 ? ownK - kr * 9 : 0;
+  if (mode == 2 && !exotic) {  // the kernel's regular-position path: bitmask test + king probes
+    const FastCtx f = make_fast_ctx(w, g);
+    const bool cur_bad = suicide_fast(f, -1, -1);
+    if (ncand_out) ncand_out[1] = 0, ncand_out[2] = 0;
+    for (int j = 0; j < ncand; ++j) {
+      const int from = w.cand[j] >> 8, to = w.cand[j] & 0x7f;
+      bool bad;
+      if (from == ownK) {  // king move: 8 probes at the new square + facing, as the king round does
+        const Probe p = make_probe(w, to, -player, player, from, to, w.sq[from]);
+        bad = false;
+        for (int d = 0; d < 4; ++d) bad |= probe_ray(w, p, d);
+        for (int d = 0; d < 4; ++d) bad |= probe_diag(w, p, d, false);
+        bad |= king_move_facing(g, p, to);
+      } else if (touches(kr, kc, from) || touches(kr, kc, to)) {
+        bad = suicide_fast(f, from, to);
+      } else {
+        bad = cur_bad;
+      }
+      if (!bad) {
+        if (n < XQ_MAX_MOVES) moves[n] = (int16_t)(from * 90 + to);
+        ++n;
+      }
+    }
+    return n;
+  }
   int nwl = 0;
   bool any_irrelevant = false;
   for (int j = 0; j < ncand; ++j) {

@@ -23,13 +23,14 @@ def _legal(hm, board, player, red, black):
     """Kernel Phase B (mode 1) must agree with the test-everything path (mode 0)."""
     b = np.ascontiguousarray(board, np.int8).reshape(90)
     out = []
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         mv = np.zeros(128, np.int16)
         nc = C.c_int(0)
         n = hm.xqh_legal_moves(b.ctypes.data, int(player), int(red), int(black), mv.ctypes.data,
                                C.byref(nc), mode)
         out.append(mv[:n].copy())
     assert np.array_equal(out[0], out[1]), "relevance filter changed the legal list"
+    assert np.array_equal(out[0], out[2]), "regular-position fast path changed the legal list"
     return out[1], nc.value
 
 
