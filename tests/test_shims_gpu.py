@@ -223,3 +223,26 @@ def test_network_predict_batch_surface(pkg):
     planes = net.encode_board(env.board, 1)
     assert planes.shape == (15, 10, 9) and planes.dtype == np.float32 and planes[14].all()
     assert net.predict(env.board, 1, lm)[0].keys() == out[0][0].keys()
+
+
+def test_device_training_tensors_match_materialised_samples(pkg):
+    """§8f: the device sample path reproduces the host tuples of materialise() exactly."""
+    import torch
+    _, self_play = pkg
+    from chinesechessai_b200 import samples
+    from chinesechessai_b200.mcts import HashEvaluator
+    for red_only in (False, True):
+        sp = self_play.BatchedSelfPlay(HashEvaluator(), 40, 15, temperature=1.0, seed=11)
+        sp.play()
+        host = sp.materialise(red_only=red_only)
+        dev = samples.training_tensors(sp, red_only=red_only)
+        boards = np.concatenate([np.stack([b.reshape(90) for b, _, _ in gd]) for gd, _, _ in host if gd])
+        rewards = np.array([r for gd, _, _ in host for _, _, r in gd], np.float64)
+        assert np.array_equal(dev["board"].cpu().numpy(), boards)
+        assert np.array_equal(dev["reward"].cpu().numpy().view(np.uint64), rewards.view(np.uint64))
+        idx = torch.arange(0, len(rewards), 7, device=dev["board"].device)
+        states, target = samples.training_batch(dev, idx)
+        net = _Net()
+        want = np.stack([net.encode_board(boards[i].reshape(10, 9), 1) for i in idx.cpu().tolist()[:5]])
+        assert np.array_equal(states[:5].cpu().numpy(), want)
+        assert target.shape == (len(idx), 1) and target.dtype == torch.float32
