@@ -32,6 +32,9 @@ int check_launch(const char* what) {
 
 static inline int ctas_for(int n_games) { return (n_games + kWarpsPerCta - 1) / kWarpsPerCta; }
 constexpr int kThreads = kWarpsPerCta * 32;
+#ifndef XQ_DEFAULT_LPB
+#define XQ_DEFAULT_LPB 32
+#endif
 
 // ---------------------------------------------------------------------------
 // reset (chess_env.py:14-67): one thread per 4 squares.
@@ -75,10 +78,10 @@ __global__ void __launch_bounds__(kThreads)
   const int g = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   if (g >= n_games) return;
   WarpSmem& w = slab[threadIdx.x >> 5];
-  load_board(w, board + (size_t)g * XQ_BOARD_STRIDE);
+  load_board<32>(w, board + (size_t)g * XQ_BOARD_STRIDE);
   const Game G = load_meta(meta + g);
-  const uint64_t k = board_key(w) ^ side_key(G.player);
-  if (lane_id() == 0) out[g] = k;
+  const uint64_t k = board_key<32>(w) ^ side_key(G.player);
+  if ((threadIdx.x & 31) == 0) out[g] = k;
 }
 
 // ---------------------------------------------------------------------------
@@ -91,12 +94,12 @@ __global__ void __launch_bounds__(kThreads)
   const int g = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   if (g >= n_games) return;
   WarpSmem& w = slab[threadIdx.x >> 5];
-  const int lane = lane_id();
-  load_board(w, board + (size_t)g * XQ_BOARD_STRIDE);
-  build_masks(w);
+  const int lane = (threadIdx.x & 31);
+  load_board<32>(w, board + (size_t)g * XQ_BOARD_STRIDE);
+  build_masks<32>(w);
   Game G = load_meta(meta + g);
   const int flags0 = G.flags;
-  const int n = movegen(w, G, g_leap);
+  const int n = movegen<32>(w, G, g_leap);
   int16_t* row = moves + (size_t)g * XQ_MAX_MOVES;
   for (int i = lane; i < n; i += 32) row[i] = w.moves[i];
   if (lane == 0) {
@@ -115,10 +118,10 @@ __global__ void __launch_bounds__(kThreads)
   const int g = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   if (g >= n_games) return;
   WarpSmem& w = slab[threadIdx.x >> 5];
-  load_board(w, board + (size_t)g * XQ_BOARD_STRIDE);
-  build_masks(w);
+  load_board<32>(w, board + (size_t)g * XQ_BOARD_STRIDE);
+  build_masks<32>(w);
   const Game G = load_meta(meta + g);
-  if (lane_id() == 0) {
+  if ((threadIdx.x & 31) == 0) {
     bool facing = false;
     if (G.red_king >= 0 && G.black_king >= 0) {
       const int rr = G.red_king / 9, rc = G.red_king % 9, br = G.black_king / 9, bc = G.black_king % 9;
@@ -148,7 +151,7 @@ __global__ void __launch_bounds__(kThreads)
   const int g = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   if (g >= n_games) return;
   WarpSmem& w = slab[threadIdx.x >> 5];
-  const int lane = lane_id();
+  const int lane = (threadIdx.x & 31);
   const int mv = move[g];
   if (mv < 0) {  // frozen game
     if (lane == 0) {
@@ -159,13 +162,13 @@ __global__ void __launch_bounds__(kThreads)
     }
     return;
   }
-  load_board(w, board + (size_t)g * XQ_BOARD_STRIDE);
-  build_masks(w);
+  load_board<32>(w, board + (size_t)g * XQ_BOARD_STRIDE);
+  build_masks<32>(w);
   Game G = load_meta(meta + g);
-  G.bkey = board_key(w);
-  const StepOut o = step(w, G, mv, pos_hist + (size_t)g * hist_cap, hist_cap, g_leap);
-  store_board(w, board + (size_t)g * XQ_BOARD_STRIDE);
-  store_meta(meta + g, G);
+  G.bkey = board_key<32>(w);
+  const StepOut o = step<32>(w, G, mv, pos_hist + (size_t)g * hist_cap, hist_cap, g_leap);
+  store_board<32>(w, board + (size_t)g * XQ_BOARD_STRIDE);
+  store_meta<32>(meta + g, G);
   if (lane == 0) {
     reward[g] = o.reward;
     flags[g] = step_flags(G, o);
@@ -190,18 +193,18 @@ __global__ void __launch_bounds__(kThreads)
   const int g = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   if (g >= n_games) return;
   WarpSmem& w = slab[threadIdx.x >> 5];
-  const int lane = lane_id();
+  const int lane = (threadIdx.x & 31);
   const int n = n_moves[g];
   const int done = meta[g].done;
   if (n <= 0 || done) {
     if (lane == 0) picked[g] = -1;
     return;
   }
-  load_board(w, board + (size_t)g * XQ_BOARD_STRIDE);
+  load_board<32>(w, board + (size_t)g * XQ_BOARD_STRIDE);
   const int16_t* row = moves + (size_t)g * XQ_MAX_MOVES;
   for (int i = lane; i < n; i += 32) w.moves[i] = row[i];
   __syncwarp();
-  const int idx = pick_index(w, n, seed, first_game_id + (uint32_t)g, ply, capture_bias);
+  const int idx = pick_index<32>(w, n, seed, first_game_id + (uint32_t)g, ply, capture_bias);
   if (lane == 0) picked[g] = w.moves[idx];
 }
 
@@ -209,7 +212,7 @@ __global__ void __launch_bounds__(kThreads)
 // Fused random playout: state stays in shared memory / registers for all plies.
 __device__ __forceinline__ uint64_t dbits(double d) { return (uint64_t)__double_as_longlong(d); }
 
-template <bool TRACE, int MINB, bool SYNC>
+template <bool TRACE, int MINB, int L>
 __global__ void __launch_bounds__(kThreads, MINB)
     playout_kernel(int8_t* __restrict__ board, xq_meta* __restrict__ meta,
                    uint64_t* __restrict__ pos_hist, int hist_cap, uint64_t seed,
@@ -218,17 +221,17 @@ __global__ void __launch_bounds__(kThreads, MINB)
                    int16_t* __restrict__ tr_n, int16_t* __restrict__ tr_pick,
                    double* __restrict__ tr_reward, uint8_t* __restrict__ tr_flags,
                    int8_t* __restrict__ tr_boards, int n_games) {
-  __shared__ WarpSmem slab[kWarpsPerCta];
-  const int g_raw = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-  const bool valid = g_raw < n_games;
-  if (!SYNC && !valid) return;
-  const int g = valid ? g_raw : n_games - 1;  // SYNC: surplus warps idle through the barriers
-  WarpSmem& w = slab[threadIdx.x >> 5];
-  const int lane = lane_id();
-  load_board(w, board + (size_t)g * XQ_BOARD_STRIDE);
-  build_masks(w);
+  using T = Tile<L>;
+  constexpr int kBoards = kThreads / L;  // boards per CTA: one tile of L lanes each
+  __shared__ WarpSmem slab[kBoards];
+  const int g = blockIdx.x * kBoards + threadIdx.x / L;
+  if (g >= n_games) return;  // whole tiles leave; collectives use tile masks only
+  WarpSmem& w = slab[threadIdx.x / L];
+  const int lane = T::lane();
+  load_board<L>(w, board + (size_t)g * XQ_BOARD_STRIDE);
+  build_masks<L>(w);
   Game G = load_meta(meta + g);
-  G.bkey = board_key(w);
+  G.bkey = board_key<L>(w);
   uint64_t* hist = pos_hist + (size_t)g * hist_cap;
   const uint32_t gid = first_game_id + (uint32_t)g;
 
@@ -236,81 +239,64 @@ __global__ void __launch_bounds__(kThreads, MINB)
   double rsum = 0.0;
   int max_legal = 0, ply = 0;
   bool pending = false;  // a move was applied; its terminal chain waits for the movegen below
+  bool kingcap = false;  // the applied move captured a king: no movegen, no terminal chain (:352)
   StepOut o;
   o.done = 0;
-  // Bookkeeping of one finished make_move: reward sum, digest chain, traces.
-  auto account = [&]() {
-    rsum = __dadd_rn(rsum, o.reward);
-    const uint64_t word_c = (uint64_t)(o.done & 1) | ((uint64_t)(G.winner + 2) << 8) |
-                            ((uint64_t)G.reason << 16) | ((uint64_t)(o.is_int & 1) << 24);
-    const uint64_t t = word_a * 0x9E3779B97F4A7C15ULL + dbits(o.reward) * 0xC2B2AE3D27D4EB4FULL +
-                       word_c * 0x165667B19E3779F9ULL + o.key_next * 0x27D4EB2F165667C5ULL;
-    digest = mix64(digest ^ t);
-    if (TRACE) {
-      const size_t tt = (size_t)g * max_plies + ply;
-      if (lane == 0) {
-        if (tr_reward) tr_reward[tt] = o.reward;
-        if (tr_flags) tr_flags[tt] = step_flags(G, o);
-      }
-      if (tr_boards) {
-        __syncwarp();
-        for (int s = lane; s < XQ_NSQ; s += 32) tr_boards[tt * XQ_NSQ + s] = w.sq[s];
-      }
-    }
-    ++ply;
-  };
   // One movegen site per iteration: it closes the previous make_move (:354,:376 need the new
   // side's move count) and is the get_legal_moves of the next ply (self_play.py:205).
-  // Returns false when the game is over.
-  bool kingcap = false;  // the applied move captured a king: no movegen, no terminal chain (:352)
-  auto one_ply = [&]() -> bool {
+  for (;;) {
     bool checking = false;
-    const int n = kingcap ? -1 : movegen(w, G, g_leap, pending ? &checking : nullptr);
+    const int n = kingcap ? -1 : movegen<L>(w, G, g_leap, pending ? &checking : nullptr);
     if (pending) {  // single finish/account site (code size)
-      step_finish(w, G, o, n, checking, hist);
+      step_finish<L>(w, G, o, n, checking, hist);
       pending = false;
-      account();
-      if (o.done) return false;
+      // bookkeeping of one finished make_move: reward sum, digest chain, traces
+      rsum = __dadd_rn(rsum, o.reward);
+      const uint64_t word_c = (uint64_t)(o.done & 1) | ((uint64_t)(G.winner + 2) << 8) |
+                              ((uint64_t)G.reason << 16) | ((uint64_t)(o.is_int & 1) << 24);
+      const uint64_t t = word_a * 0x9E3779B97F4A7C15ULL + dbits(o.reward) * 0xC2B2AE3D27D4EB4FULL +
+                         word_c * 0x165667B19E3779F9ULL + o.key_next * 0x27D4EB2F165667C5ULL;
+      digest = mix64(digest ^ t);
+      if (TRACE) {
+        const size_t tt = (size_t)g * max_plies + ply;
+        if (lane == 0) {
+          if (tr_reward) tr_reward[tt] = o.reward;
+          if (tr_flags) tr_flags[tt] = step_flags(G, o);
+        }
+        if (tr_boards) {
+          T::sync();
+          for (int s = lane; s < XQ_NSQ; s += L) tr_boards[tt * XQ_NSQ + s] = w.sq[s];
+        }
+      }
+      ++ply;
+      if (o.done) break;
     }
-    if (ply >= max_plies || n == 0) return false;  // self_play.py:203,207
+    if (ply >= max_plies || n == 0) break;  // self_play.py:203,207
     max_legal = max(max_legal, n);
-    const int idx = pick_index(w, n, seed, gid, (uint32_t)ply, capture_bias);
+    const int idx = pick_index<L>(w, n, seed, gid, (uint32_t)ply, capture_bias);
     const int mv = w.moves[idx];
     unsigned lsum = 0;
 #pragma unroll 1
-    for (int i = lane; i < n; i += 32) lsum += (unsigned)((int)w.moves[i] + 1) * (unsigned)(2 * i + 1);
-    lsum = __reduce_add_sync(kFull, lsum);
+    for (int i = lane; i < n; i += L) lsum += (unsigned)((int)w.moves[i] + 1) * (unsigned)(2 * i + 1);
+    lsum = T::sum(lsum);
     word_a = (uint64_t)lsum | ((uint64_t)n << 32) | ((uint64_t)mv << 40) | ((uint64_t)(ply + 1) << 54);
     if (TRACE) {
       const size_t tt = (size_t)g * max_plies + ply;
       if (tr_moves)
-        for (int i = lane; i < n; i += 32) tr_moves[tt * XQ_MAX_MOVES + i] = w.moves[i];
+        for (int i = lane; i < n; i += L) tr_moves[tt * XQ_MAX_MOVES + i] = w.moves[i];
       if (lane == 0) {
         if (tr_n) tr_n[tt] = (int16_t)n;
         if (tr_pick) tr_pick[tt] = (int16_t)mv;
       }
     }
-    __syncwarp();
-    o = step_apply(w, G, mv, hist, hist_cap);
+    T::sync();
+    o = step_apply<L>(w, G, mv, hist, hist_cap);
     kingcap = o.done != 0;
     pending = true;
-    return true;
-  };
-  if (SYNC) {
-    // Phase-aligned variant: the 8 warps of a CTA start every ply together, so they fetch the
-    // same part of the (larger than L1.5) loop body at about the same time.
-    bool alive = valid;
-    while (__syncthreads_or(alive ? 1 : 0)) {
-      if (alive) alive = one_ply();
-    }
-    if (!valid) return;
-  } else {
-    while (one_ply()) {
-    }
   }
   const uint64_t fkey = G.bkey ^ side_key(G.player);
-  store_board(w, board + (size_t)g * XQ_BOARD_STRIDE);
-  store_meta(meta + g, G);
+  store_board<L>(w, board + (size_t)g * XQ_BOARD_STRIDE);
+  store_meta<L>(meta + g, G);
   if (lane == 0) {
     xq_playout_result r;
     r.plies = ply;
@@ -354,7 +340,7 @@ __global__ void __launch_bounds__(kThreads)
                   const int16_t* __restrict__ n_moves, float* __restrict__ priors, int n) {
   const int g = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   if (g >= n) return;
-  const int lane = lane_id();
+  const int lane = (threadIdx.x & 31);
   const int cnt = min((int)n_moves[g], XQ_MAX_MOVES);
   const T* lg = logits + (size_t)g * XQ_POLICY;
   const int16_t* mv = moves + (size_t)g * moves_stride;
@@ -479,30 +465,40 @@ int xq_playout(int8_t* board, xq_meta* meta, uint64_t* pos_hist, int hist_cap, u
              "null pointer, negative size or hist_cap <= 0");
   XQ_REQUIRE(capture_bias >= 0 && capture_bias <= 256, "capture_bias out of [0,256]");
   const bool trace = tr_moves || tr_n || tr_pick || tr_reward || tr_flags || tr_boards;
-  // resident CTAs per SM the register allocation is bounded for (tuning knob; default 4 = 64 regs)
-  static const int minb = [] {
+  // Tuning knobs (defaults chosen on B200, profiles/): lanes per board and the number of
+  // resident CTAs per SM the register allocation is bounded for.
+  const int lpb = [] {
+    const char* e = getenv("XQ_PLAYOUT_LPB");
+    const int v = e ? atoi(e) : XQ_DEFAULT_LPB;
+    return (v == 8 || v == 16 || v == 32) ? v : XQ_DEFAULT_LPB;
+  }();
+  const int minb = [] {
     const char* e = getenv("XQ_PLAYOUT_MINB");
     const int v = e ? atoi(e) : 4;
-    return v >= 2 && v <= 5 ? v : 4;
+    return v >= 3 && v <= 5 ? v : 4;
   }();
-  const dim3 grid(ctas_for(n_games)), block(kThreads);
+  const dim3 block(kThreads), grid((n_games + (kThreads / lpb) - 1) / (kThreads / lpb));
   const cudaStream_t st = (cudaStream_t)stream;
-#define XQ_LAUNCH_PLAYOUT(T, M, S)                                                               \
-  playout_kernel<T, M, S><<<grid, block, 0, st>>>(board, meta, pos_hist, hist_cap, seed,         \
-                                                  first_game_id, max_plies, capture_bias,        \
-                                                  results, tr_moves, tr_n, tr_pick, tr_reward,   \
-                                                  tr_flags, tr_boards, n_games)
-  static const bool sync_plies = [] {
-    const char* e = getenv("XQ_PLAYOUT_SYNC");
-    return e ? atoi(e) != 0 : false;
-  }();
-  if (trace) XQ_LAUNCH_PLAYOUT(true, 4, false);
-  else if (sync_plies && minb == 3) XQ_LAUNCH_PLAYOUT(false, 3, true);
-  else if (sync_plies) XQ_LAUNCH_PLAYOUT(false, 4, true);
-  else if (minb == 2) XQ_LAUNCH_PLAYOUT(false, 2, false);
-  else if (minb == 3) XQ_LAUNCH_PLAYOUT(false, 3, false);
-  else if (minb == 5) XQ_LAUNCH_PLAYOUT(false, 5, false);
-  else XQ_LAUNCH_PLAYOUT(false, 4, false);
+#define XQ_LAUNCH_PLAYOUT(T, M, LL)                                                              \
+  playout_kernel<T, M, LL><<<dim3((n_games + (kThreads / LL) - 1) / (kThreads / LL)), block, 0,  \
+                             st>>>(board, meta, pos_hist, hist_cap, seed, first_game_id,         \
+                                   max_plies, capture_bias, results, tr_moves, tr_n, tr_pick,    \
+                                   tr_reward, tr_flags, tr_boards, n_games)
+#define XQ_LAUNCH_BY_MINB(LL)                          \
+  do {                                                 \
+    if (minb == 3) XQ_LAUNCH_PLAYOUT(false, 3, LL);    \
+    else if (minb == 5) XQ_LAUNCH_PLAYOUT(false, 5, LL); \
+    else XQ_LAUNCH_PLAYOUT(false, 4, LL);              \
+  } while (0)
+  (void)grid;
+  if (trace) {
+    if (lpb == 8) XQ_LAUNCH_PLAYOUT(true, 4, 8);
+    else if (lpb == 16) XQ_LAUNCH_PLAYOUT(true, 4, 16);
+    else XQ_LAUNCH_PLAYOUT(true, 4, 32);
+  } else if (lpb == 8) XQ_LAUNCH_BY_MINB(8);
+  else if (lpb == 16) XQ_LAUNCH_BY_MINB(16);
+  else XQ_LAUNCH_BY_MINB(32);
+#undef XQ_LAUNCH_BY_MINB
 #undef XQ_LAUNCH_PLAYOUT
   return check_launch("xq_playout");
 }

@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(kThreadsM)
                      int n_games) {
   const int g = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   if (g >= n_games) return;
-  const int lane = lane_id();
+  const int lane = threadIdx.x & 31;
   const TreeDims d = tree_dims(n_sims);
   Tree t = tree_at(trees, d, g);
   const bool on = active ? active[g] != 0 : true;
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(kThreadsM)
 
 // select_child (self_play.py:40-59): float32 PUCT, strict '>' => first max wins.
 __device__ __forceinline__ int puct_select(const Tree& t, int node) {
-  const int lane = lane_id();
+  const int lane = threadIdx.x & 31;
   const Node nd = t.nodes[node];
   const float sq = (float)sqrt((double)nd.visits);
   float best = -INFINITY;
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(kThreadsM, 4)
   const int g = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   if (g >= n_games) return;
   WarpSmem& w = slab[threadIdx.x >> 5];
-  const int lane = lane_id();
+  const int lane = threadIdx.x & 31;
   const TreeDims d = tree_dims(n_sims);
   Tree t = tree_at(trees, d, g);
   TreeHeader h = *t.h;
@@ -206,22 +206,22 @@ __global__ void __launch_bounds__(kThreadsM, 4)
         int slot;
         if (nd.parent < 0) {  // root: state 0 was written by init
           slot = 0;
-          load_board(w, t.board(0));
-          build_masks(w);
+          load_board<32>(w, t.board(0));
+          build_masks<32>(w);
           G = load_meta(t.meta(0));
-          n_legal = movegen(w, G, g_leap);  // :123
+          n_legal = movegen<32>(w, G, g_leap);  // :123
         } else {
           const int ps = t.nodes[nd.parent].state;
           slot = h.n_states;  // scratch until proven non-terminal
-          load_board(w, t.board(ps));
-          build_masks(w);
+          load_board<32>(w, t.board(ps));
+          build_masks<32>(w);
           G = load_meta(t.meta(ps));
-          G.bkey = board_key(w);
+          G.bkey = board_key<32>(w);
           uint64_t* hs = t.hist(slot);
           const uint64_t* hp = t.hist(ps);
           for (int i = lane; i < G.hist_len; i += 32) hs[i] = hp[i];
           __syncwarp();
-          const StepOut o = step(w, G, nd.move, hs, d.hist_cap, g_leap);  // :119
+          const StepOut o = step<32>(w, G, nd.move, hs, d.hist_cap, g_leap);  // :119
           n_legal = o.n_next < 0 ? 0 : o.n_next;
           if (o.n_next < 0 && G.winner == XQ_WINNER_NONE) n_legal = 0;
         }
@@ -230,8 +230,8 @@ __global__ void __launch_bounds__(kThreadsM, 4)
           tval = G.winner == G.player ? 1 : (G.winner == -G.player ? -1 : 0);
         } else {
           term = 1;
-          store_board(w, t.board(slot));
-          store_meta(t.meta(slot), G);
+          store_board<32>(w, t.board(slot));
+          store_meta<32>(t.meta(slot), G);
           if (slot != 0) h.n_states += 1;
           int16_t* lm = leaf_moves + (size_t)g * XQ_MAX_MOVES;
           for (int i = lane; i < n_legal; i += 32) lm[i] = w.moves[i];
@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(kThreadsM)
                        const V* __restrict__ values, int values_per_game, int n_games) {
   const int g = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   if (g >= n_games) return;
-  const int lane = lane_id();
+  const int lane = threadIdx.x & 31;
   const TreeDims d = tree_dims(n_sims);
   Tree t = tree_at(trees, d, g);
   TreeHeader h = *t.h;
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(kThreadsM)
                             int n_games) {
   const int g = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   if (g >= n_games) return;
-  const int lane = lane_id();
+  const int lane = threadIdx.x & 31;
   const TreeDims d = tree_dims(n_sims);
   Tree t = tree_at(const_cast<void*>(trees), d, g);
   const Node root = t.nodes[0];
@@ -356,10 +356,10 @@ __global__ void __launch_bounds__(kThreadsM)
   const int g = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   if (g >= n) return;
   WarpSmem& w = slab[threadIdx.x >> 5];
-  const int lane = lane_id();
+  const int lane = threadIdx.x & 31;
   for (int s = lane; s < XQ_NSQ; s += 32) w.sq[s] = board[(size_t)g * board_stride + s];
   __syncwarp();
-  const uint64_t hsh = board_key(w) ^ side_key(player[g]);
+  const uint64_t hsh = board_key<32>(w) ^ side_key(player[g]);
   const int cnt = n_moves[g];
   double wts[XQ_MAX_MOVES / 32];
   double sum = 0.0;

@@ -109,18 +109,36 @@ XQ_HD uint64_t mix64(uint64_t x) {
 }
 
 #if defined(__CUDACC__)
-__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
-
-__device__ __forceinline__ uint64_t warp_xor64(uint64_t v) {
+// A board (or tree) is owned by a TILE of L consecutive lanes, L in {8,16,32}: a warp carries
+// 32/L boards.  The per-board scalar work (make_move bookkeeping, pick, digest, loop control)
+// is then shared by 32/L boards per issued instruction.  Every collective uses the tile's own
+// member mask, so tiles of one warp may diverge freely.
+template <int L>
+struct Tile {
+  static_assert(L == 8 || L == 16 || L == 32, "tile width");
+  static __device__ __forceinline__ int lane() { return threadIdx.x & (L - 1); }
+  static __device__ __forceinline__ int shift() { return (threadIdx.x & 31) & ~(L - 1); }
+  static __device__ __forceinline__ unsigned lanes() { return L == 32 ? 0xffffffffu : ((1u << (L & 31)) - 1u); }
+  static __device__ __forceinline__ unsigned mask() { return L == 32 ? 0xffffffffu : lanes() << shift(); }
+  static __device__ __forceinline__ unsigned ballot(bool p) {
+    const unsigned b = __ballot_sync(mask(), p);
+    return L == 32 ? b : (b >> shift()) & lanes();
+  }
+  static __device__ __forceinline__ bool any(bool p) { return ballot(p) != 0; }
+  template <typename T>
+  static __device__ __forceinline__ T shfl(T v, int src) { return __shfl_sync(mask(), v, src, L); }
+  template <typename T>
+  static __device__ __forceinline__ T shfl_up(T v, int d) { return __shfl_up_sync(mask(), v, d, L); }
+  template <typename T>
+  static __device__ __forceinline__ T shfl_xor(T v, int d) { return __shfl_xor_sync(mask(), v, d, L); }
+  static __device__ __forceinline__ void sync() { __syncwarp(mask()); }
+  static __device__ __forceinline__ unsigned sum(unsigned v) { return __reduce_add_sync(mask(), v); }
+  static __device__ __forceinline__ uint64_t xor64(uint64_t v) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v ^= __shfl_xor_sync(kFull, v, o);
-  return v;
-}
-__device__ __forceinline__ uint64_t warp_add64(uint64_t v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-  return v;
-}
+    for (int o = L / 2; o > 0; o >>= 1) v ^= shfl_xor(v, o);
+    return v;
+  }
+};
 
 #endif  // __CUDACC__
 
@@ -132,32 +150,33 @@ XQ_HD uint64_t piece_key(int piece, int s) { return mix64((uint64_t)((piece + 8)
 #if defined(__CUDACC__)
 
 // Position key without the side byte: XOR of per-(piece,square) keys, computed
-// lane-parallel (3 squares per lane).  _get_position_hash, chess_env.py:497-504.
+// lane-parallel.  _get_position_hash, chess_env.py:497-504.
+template <int L>
 __device__ __forceinline__ uint64_t board_key(const WarpSmem& w) {
-  const int lane = lane_id();
   uint64_t h = 0;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    int s = lane + 32 * k;
-    int p = (s < XQ_NSQ) ? w.sq[s] : 0;
+#pragma unroll 1
+  for (int s = Tile<L>::lane(); s < XQ_NSQ; s += L) {
+    const int p = w.sq[s];
     if (p != 0) h ^= piece_key(p, s);
   }
-  return warp_xor64(h);
+  return Tile<L>::xor64(h);
 }
 
 // ---- state load / store ---------------------------------------------------
+template <int L>
 __device__ __forceinline__ void load_board(WarpSmem& w, const int8_t* __restrict__ board_row) {
-  const int lane = lane_id();
-  if (lane < XQ_BOARD_STRIDE / 4)
-    reinterpret_cast<uint32_t*>(w.sq)[lane] = reinterpret_cast<const uint32_t*>(board_row)[lane];
-  __syncwarp();
+#pragma unroll
+  for (int i = Tile<L>::lane(); i < XQ_BOARD_STRIDE / 4; i += L)
+    reinterpret_cast<uint32_t*>(w.sq)[i] = reinterpret_cast<const uint32_t*>(board_row)[i];
+  Tile<L>::sync();
 }
 
+template <int L>
 __device__ __forceinline__ void store_board(const WarpSmem& w, int8_t* __restrict__ board_row) {
-  const int lane = lane_id();
-  __syncwarp();
-  if (lane < XQ_BOARD_STRIDE / 4)
-    reinterpret_cast<uint32_t*>(board_row)[lane] = reinterpret_cast<const uint32_t*>(w.sq)[lane];
+  Tile<L>::sync();
+#pragma unroll
+  for (int i = Tile<L>::lane(); i < XQ_BOARD_STRIDE / 4; i += L)
+    reinterpret_cast<uint32_t*>(board_row)[i] = reinterpret_cast<const uint32_t*>(w.sq)[i];
 }
 
 __device__ __forceinline__ Game load_meta(const xq_meta* __restrict__ m) {
@@ -180,8 +199,9 @@ __device__ __forceinline__ Game load_meta(const xq_meta* __restrict__ m) {
   return g;
 }
 
+template <int L>
 __device__ __forceinline__ void store_meta(xq_meta* __restrict__ m, const Game& g) {
-  if (lane_id() == 0) {
+  if (Tile<L>::lane() == 0) {
     uint4 a, b;
     a.x = (uint32_t)(g.player & 0xff) | ((uint32_t)(g.winner & 0xff) << 8) |
           ((uint32_t)(g.reason & 0xff) << 16) | ((uint32_t)(g.done & 0xff) << 24);
@@ -199,22 +219,24 @@ __device__ __forceinline__ void store_meta(xq_meta* __restrict__ m, const Game& 
   }
 }
 
-// Row / column occupancy masks from the staged board.
+// Row / column occupancy masks from the staged board (19 tasks over the tile's lanes).
+template <int L>
 __device__ __forceinline__ void build_masks(WarpSmem& w) {
-  const int lane = lane_id();
-  if (lane < 10) {
+#pragma unroll 1
+  for (int t = Tile<L>::lane(); t < 19; t += L) {
     unsigned m = 0;
+    if (t < 10) {
 #pragma unroll
-    for (int c = 0; c < 9; ++c) m |= (w.sq[lane * 9 + c] != 0 ? 1u : 0u) << c;
-    w.rows[lane] = (uint16_t)m;
-  } else if (lane >= 16 && lane < 25) {
-    const int c = lane - 16;
-    unsigned m = 0;
+      for (int c = 0; c < 9; ++c) m |= (w.sq[t * 9 + c] != 0 ? 1u : 0u) << c;
+      w.rows[t] = (uint16_t)m;
+    } else {
+      const int c = t - 10;
 #pragma unroll
-    for (int r = 0; r < 10; ++r) m |= (w.sq[r * 9 + c] != 0 ? 1u : 0u) << r;
-    w.cols[c] = (uint16_t)m;
+      for (int r = 0; r < 10; ++r) m |= (w.sq[r * 9 + c] != 0 ? 1u : 0u) << r;
+      w.cols[c] = (uint16_t)m;
+    }
   }
-  __syncwarp();
+  Tile<L>::sync();
 }
 
 #endif  // __CUDACC__
@@ -596,29 +618,27 @@ static __device__ __noinline__ bool in_check_cold(const WarpSmem* wp, const Game
 
 // Irregular (poked) boards — several kings, stale or missing cache, enemy K/A/B near the
 // king: every candidate through the general suicide() (:118).  Cold path.
-static __device__ __noinline__ void legality_generic(WarpSmem* wp, const Game* gp, int ncand) {
+static __device__ __noinline__ void legality_generic(WarpSmem* wp, const Game* gp, int ncand,
+                                                     int lane, int stride) {
   WarpSmem& w = *wp;
-  const int lane = threadIdx.x & 31;
-  for (int base = 0; base < ncand; base += 32) {
-    const int j = base + lane;
-    if (j < ncand) {
-      const int c = w.cand[j];
-      if (suicide(w, *gp, c >> 8, c & 0x7f, true)) w.cand[j] = (uint16_t)(c | kCandIllegal);
-    }
+  for (int j = lane; j < ncand; j += stride) {
+    const int c = w.cand[j];
+    if (suicide(w, *gp, c >> 8, c & 0x7f, true)) w.cand[j] = (uint16_t)(c | kCandIllegal);
   }
 }
 
-__device__ __forceinline__ int warp_sum(int v) { return (int)__reduce_add_sync(kFull, (unsigned)v); }
-
-// get_legal_moves (chess_env.py:76-121).  Fills w.moves in the reference's
-// order and returns the count.
-// Phase A: work item = (own piece, direction) -> candidate list via an ordered warp scan.
-// Phase B: candidates that can change the king's safety (or all of them on irregular boards)
-// go through suicide() 32 per round; the others inherit the verdict of the position itself.
+// get_legal_moves (chess_env.py:76-121) by one tile of L lanes.  Fills w.moves in the
+// reference's order and returns the count.
+// Phase A: work item = (own piece, direction) -> candidate list via an ordered scan.
+// Phase B (regular boards): candidates that can change the king's safety go through the
+// bitmask test suicide_fast(), the others inherit the verdict of the position itself; king
+// moves and make_move's check test share one probe round.  Irregular boards: legality_generic.
 // Ordered compaction with ballot/popc.
+template <int L>
 __device__ __forceinline__ int movegen(WarpSmem& w, Game& g, const uint32_t* __restrict__ leap,
                                        bool* checked_out = nullptr) {
-  const int lane = lane_id();
+  using T = Tile<L>;
+  const int lane = T::lane();
   const unsigned lt = (1u << lane) - 1u;
   const int player = g.player;
 
@@ -626,37 +646,37 @@ __device__ __forceinline__ int movegen(WarpSmem& w, Game& g, const uint32_t* __r
   const int ownK = player == 1 ? g.red_king : g.black_king;
   int n_own = 0, n_kings = 0;
   bool ex = false;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    const int s = lane + 32 * k;
+#pragma unroll 1
+  for (int base = 0; base < XQ_BOARD_STRIDE; base += L) {
+    const int s = base + lane;
     const int p = s < XQ_NSQ ? (int)w.sq[s] : 0;
     const bool mine = p * player > 0;
-    const unsigned b = __ballot_sync(kFull, mine);
+    const unsigned b = T::ballot(mine);
     if (mine) w.own[n_own + __popc(b & lt)] = (uint8_t)s;
     n_own += __popc(b);
-    n_kings += __popc(__ballot_sync(kFull, p == player * KING));
+    n_kings += __popc(T::ballot(p == player * KING));
     ex |= exotic_piece(p, s, player, ownK < 0 ? 0 : ownK);
   }
-  const bool exotic = !regular_king(w, player, ownK, n_kings) || __any_sync(kFull, ex);
-  __syncwarp();
+  const bool exotic = !regular_king(w, player, ownK, n_kings) || T::any(ex);
+  T::sync();
 
   // Phase A
   int ncand = 0;
   const int n_items = n_own * 4;
 #pragma unroll 1
-  for (int base = 0; base < n_items; base += 32) {
+  for (int base = 0; base < n_items; base += L) {
     const int t = base + lane;
     Item it{0, 0, 0, -1, -1};
     if (t < n_items) it = gen_item(w, leap, player, w.own[t >> 2], t & 3);
     const int cnt = it.empties + (it.e1 >= 0) + (it.e2 >= 0);
     int incl = cnt;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int v = __shfl_up_sync(kFull, incl, o);
+    for (int o = 1; o < L; o <<= 1) {
+      const int v = T::shfl_up(incl, o);
       if (lane >= o) incl += v;
     }
-    const int total = __shfl_sync(kFull, incl, 31);
-    if (ncand + total > XQ_CAND_CAP) {  // warp-uniform; only on absurd poked boards
+    const int total = T::shfl(incl, L - 1);
+    if (ncand + total > XQ_CAND_CAP) {  // tile-uniform; only on absurd poked boards
       g.flags |= XQ_F_OVERFLOW;
       break;
     }
@@ -668,42 +688,55 @@ __device__ __forceinline__ int movegen(WarpSmem& w, Game& g, const uint32_t* __r
     if (it.e1 >= 0) w.cand[off++] = (uint16_t)(fs | it.e1);
     if (it.e2 >= 0) w.cand[off] = (uint16_t)(fs | it.e2);
   }
-  __syncwarp();
+  T::sync();
 
   bool cur_bad = false;
   int kfirst = 0, kcount = 0;  // the own king's candidates (contiguous, <= 4) on regular boards
   if (!exotic) {
-    // ---- regular position: bitmask legality (suicide_fast) + one probe round for king moves
+    // ---- regular position: bitmask legality (suicide_fast) for non-king moves
     FastCtx f;
     {
       const int es = -player;
       f.K = ownK; f.kr = ownK / 9; f.kc = ownK - f.kr * 9; f.geo = player;
       f.rowm = w.rows[f.kr];
       f.colm = w.cols[f.kc];
-      int q = 0;  // lanes 0..8: the king's row; lanes 16..25: the king's column
-      if (lane < 9) q = w.sq[f.kr * 9 + lane];
-      else if (lane >= 16 && lane < 26) q = w.sq[(lane - 16) * 9 + f.kc];
-      const unsigned br = __ballot_sync(kFull, q == es * ROOK);
-      const unsigned bc = __ballot_sync(kFull, q == es * CANNON);
-      const unsigned bp = __ballot_sync(kFull, q == es * PAWN);
-      f.er_row = br & 0x1FFu; f.ec_row = bc & 0x1FFu; f.ep_row = bp & 0x1FFu;
-      f.er_col = (br >> 16) & 0x3FFu; f.ec_col = (bc >> 16) & 0x3FFu; f.ep_col = (bp >> 16) & 0x3FFu;
-      bool flag = false;  // lanes 0..7: knight squares; lanes 8..11: legs
-      if (lane < 12) {
-        const int d = lane < 8 ? lane >> 1 : lane - 8;
-        const int a = (d & 2) ? 1 : -1, b = (d & 1) ? 1 : -1;
-        const int lr = f.kr + a, lc = f.kc + b;
-        const bool lon = lr >= 0 && lr <= 9 && lc >= 0 && lc <= 8;
-        if (lane >= 8) {
-          flag = !lon || w.sq[lr * 9 + lc] != 0;
-        } else if (lon) {
-          const int r2 = (lane & 1) ? lr : f.kr + 2 * a, c2 = (lane & 1) ? f.kc + 2 * b : lc;
-          flag = r2 >= 0 && r2 <= 9 && c2 >= 0 && c2 <= 8 && w.sq[r2 * 9 + c2] == es * KNIGHT;
-        }
+      f.er_row = f.ec_row = f.ep_row = f.er_col = f.ec_col = f.ep_col = 0;
+      // 9 row squares then 10 column squares of the king, L at a time
+#pragma unroll 1
+      for (int base = 0; base < 19; base += L) {
+        const int t = base + lane;
+        int q = 0;
+        if (t < 9) q = w.sq[f.kr * 9 + t];
+        else if (t < 19) q = w.sq[(t - 9) * 9 + f.kc];
+        const uint64_t br = (uint64_t)T::ballot(q == es * ROOK) << base;
+        const uint64_t bc = (uint64_t)T::ballot(q == es * CANNON) << base;
+        const uint64_t bp = (uint64_t)T::ballot(q == es * PAWN) << base;
+        f.er_row |= (unsigned)br & 0x1FFu; f.ec_row |= (unsigned)bc & 0x1FFu; f.ep_row |= (unsigned)bp & 0x1FFu;
+        f.er_col |= (unsigned)(br >> 9) & 0x3FFu; f.ec_col |= (unsigned)(bc >> 9) & 0x3FFu;
+        f.ep_col |= (unsigned)(bp >> 9) & 0x3FFu;
       }
-      const unsigned b2 = __ballot_sync(kFull, flag);
-      f.ekn = b2 & 0xFFu;
-      f.legocc = (b2 >> 8) & 0xFu;
+      // tasks 0..7: knight squares; 8..11: legs
+      f.ekn = f.legocc = 0;
+#pragma unroll 1
+      for (int base = 0; base < 12; base += L) {
+        const int t = base + lane;
+        bool flag = false;
+        if (t < 12) {
+          const int d = t < 8 ? t >> 1 : t - 8;
+          const int a = (d & 2) ? 1 : -1, b = (d & 1) ? 1 : -1;
+          const int lr = f.kr + a, lc = f.kc + b;
+          const bool lon = lr >= 0 && lr <= 9 && lc >= 0 && lc <= 8;
+          if (t >= 8) {
+            flag = !lon || w.sq[lr * 9 + lc] != 0;
+          } else if (lon) {
+            const int r2 = (t & 1) ? lr : f.kr + 2 * a, c2 = (t & 1) ? f.kc + 2 * b : lc;
+            flag = r2 >= 0 && r2 <= 9 && c2 >= 0 && c2 <= 8 && w.sq[r2 * 9 + c2] == es * KNIGHT;
+          }
+        }
+        const unsigned b2 = T::ballot(flag) << base;
+        f.ekn |= b2 & 0xFFu;
+        f.legocc |= (b2 >> 8) & 0xFu;
+      }
       f.side_ok = player == 1 ? f.kr < 5 : f.kr >= 5;
       const int ek = player == 1 ? g.black_king : g.red_king;
       f.same_file = false;
@@ -718,7 +751,7 @@ __device__ __forceinline__ int movegen(WarpSmem& w, Game& g, const uint32_t* __r
     int nwl = 0;
     bool any_irrelevant = false;
 #pragma unroll 1
-    for (int base = 0; base < ncand; base += 32) {
+    for (int base = 0; base < ncand; base += L) {
       const int j = base + lane;
       bool rel = false, isk = false;
       const bool valid = j < ncand;
@@ -728,19 +761,19 @@ __device__ __forceinline__ int movegen(WarpSmem& w, Game& g, const uint32_t* __r
         rel = !isk && (touches(f.kr, f.kc, from) || touches(f.kr, f.kc, to));
         if (!rel && !isk) w.cand[j] = (uint16_t)(c | kCandIrrelevant);
       }
-      const unsigned m = __ballot_sync(kFull, rel), mk = __ballot_sync(kFull, isk);
+      const unsigned m = T::ballot(rel), mk = T::ballot(isk);
       if (rel) w.wl[nwl + __popc(m & lt)] = (uint16_t)j;
       nwl += __popc(m);
       if (mk && kcount == 0) kfirst = base + __ffs(mk) - 1;
       kcount += __popc(mk);
-      any_irrelevant |= __ballot_sync(kFull, valid && !rel && !isk) != 0;
+      any_irrelevant |= T::any(valid && !rel && !isk);
     }
     if (any_irrelevant && lane == 0) w.wl[nwl] = kWlSentinel;
     nwl += any_irrelevant ? 1 : 0;
-    __syncwarp();
+    T::sync();
     // B.2a: bitmask test of the worklist (the sentinel evaluates the position itself)
 #pragma unroll 1
-    for (int base = 0; base < nwl; base += 32) {
+    for (int base = 0; base < nwl; base += L) {
       const int i = base + lane;
       bool is_cur = false, bad = false;
       if (i < nwl) {
@@ -750,10 +783,10 @@ __device__ __forceinline__ int movegen(WarpSmem& w, Game& g, const uint32_t* __r
         bad = suicide_fast(f, is_cur ? -1 : (c >> 8), is_cur ? -1 : (c & 0x7f));
         if (bad && !is_cur) w.cand[item] = (uint16_t)(c | kCandIllegal);
       }
-      cur_bad |= __ballot_sync(kFull, is_cur && bad) != 0;
+      cur_bad |= T::any(is_cur && bad);
     }
   } else {
-    legality_generic(&w, &g, ncand);
+    legality_generic(&w, &g, ncand, lane, L);
   }
   // Probe round — ONE inlined copy of the 8-probe attack test per kernel.  Item 0: is this
   // side's king attacked under the PREVIOUS mover's geometry, i.e. make_move's is_checking
@@ -764,7 +797,7 @@ __device__ __forceinline__ int movegen(WarpSmem& w, Game& g, const uint32_t* __r
     const int n_it = 1 + kcount;
     bool checked = false;
 #pragma unroll 1
-    for (int base = 0; base < n_it * 8; base += 32) {
+    for (int base = 0; base < n_it * 8; base += L) {
       const int idx = base + lane, it = idx >> 3, pr = idx & 7;
       bool active = it < n_it, hit = false;
       int K = ownK, geo = -player, from = -1, to = -1, mover = 0;
@@ -785,19 +818,19 @@ __device__ __forceinline__ int movegen(WarpSmem& w, Game& g, const uint32_t* __r
           }
         }
       }
-      const unsigned bal = __ballot_sync(kFull, active && hit);
+      const unsigned bal = T::ballot(active && hit);
       if (base == 0) checked = (bal & 0xFFu) != 0;
-      if (active && it > 0 && pr == 0 && ((bal >> (lane & 24)) & 0xFFu))
+      if (active && it > 0 && pr == 0 && ((bal >> (lane & ~7)) & 0xFFu))
         w.cand[kfirst + it - 1] |= kCandIllegal;
     }
     if (checked_out) *checked_out = checked;
   }
-  __syncwarp();
+  T::sync();
 
   // Phase B.3: ordered compaction
   int n_legal = 0;
 #pragma unroll 1
-  for (int base = 0; base < ncand; base += 32) {
+  for (int base = 0; base < ncand; base += L) {
     const int j = base + lane;
     bool ok = false;
     int c = 0;
@@ -805,7 +838,7 @@ __device__ __forceinline__ int movegen(WarpSmem& w, Game& g, const uint32_t* __r
       c = w.cand[j];
       ok = (c & kCandIrrelevant) ? !cur_bad : !(c & kCandIllegal);
     }
-    const unsigned m = __ballot_sync(kFull, ok);
+    const unsigned m = T::ballot(ok);
     const int idx = n_legal + __popc(m & lt);
     if (ok && idx < XQ_MAX_MOVES) w.moves[idx] = (int16_t)(((c >> 8) & 0x7f) * 90 + (c & 0x7f));
     n_legal += __popc(m);
@@ -814,10 +847,9 @@ __device__ __forceinline__ int movegen(WarpSmem& w, Game& g, const uint32_t* __r
     n_legal = XQ_MAX_MOVES;
     g.flags |= XQ_F_OVERFLOW;
   }
-  __syncwarp();
+  T::sync();
   return n_legal;
 }
-
 #endif  // __CUDACC__
 
 // ---- step -------------------------------------------------------------------
@@ -859,12 +891,14 @@ struct StepOut {
 // position-history append, side switch.  o.done is set only by a king capture (:292-297).
 // The check test (:317) needs the post-move board too and is evaluated by the movegen that
 // follows (one probe round serves both); its consequences (:318-345) are in step_finish.
+template <int L>
 __device__ __forceinline__ StepOut step_apply(WarpSmem& w, Game& g, int move,
                                               uint64_t* __restrict__ hist, int hist_cap) {
-  const int lane = lane_id();
+  using T = Tile<L>;
+  const int lane = T::lane();
   const int from = move / 90, to = move - from * 90;
   const int captured = w.sq[to], moving = w.sq[from];  // :265-266
-  __syncwarp();
+  T::sync();
   if (lane == 0) {
     w.sq[to] = (int8_t)moving;
     w.sq[from] = 0;
@@ -883,11 +917,11 @@ __device__ __forceinline__ StepOut step_apply(WarpSmem& w, Game& g, int move,
     const int kp = lane == 2 ? captured : moving;
     const int ks = lane == 0 ? from : to;
     uint64_t x = (lane < 3 && kp != 0) ? piece_key(kp, ks) : 0ULL;
-    x ^= __shfl_xor_sync(kFull, x, 1);
-    x ^= __shfl_xor_sync(kFull, x, 2);
-    g.bkey ^= __shfl_sync(kFull, x, 0);
+    x ^= T::shfl_xor(x, 1);
+    x ^= T::shfl_xor(x, 2);
+    g.bkey ^= T::shfl(x, 0);
   }
-  __syncwarp();
+  T::sync();
 
   if (moving == KING) g.red_king = to;  // :271-279
   else if (moving == -KING) g.black_king = to;
@@ -924,7 +958,7 @@ __device__ __forceinline__ StepOut step_apply(WarpSmem& w, Game& g, int move,
   g.move_count += 1;
   o.key_next = g.bkey ^ side_key(g.player);
   o.n_next = -1;
-  __syncwarp();
+  T::sync();
   return o;
 }
 
@@ -932,9 +966,11 @@ __device__ __forceinline__ StepOut step_apply(WarpSmem& w, Game& g, int move,
 // is None): check bonus / consecutive_checks / positional reward (:318-335), check_history
 // append (:341); then, unless the king was captured, the terminal chain for the side now to
 // move given its legal-move count (:352-397) and the 70-ply cap (:400-404).
+template <int L>
 __device__ __forceinline__ void step_finish(const WarpSmem& w, Game& g, StepOut& o, int n_legal,
                                             bool checking, const uint64_t* __restrict__ hist) {
-  const int lane = lane_id();
+  using T = Tile<L>;
+  const int lane = T::lane();
   const int mover = -g.player;
   if (!o.done && checking) {  // :318-327
     if (g.cchecks == 0) { o.reward = xq_dadd(o.reward, 15.0); o.is_int = 0; }
@@ -963,8 +999,8 @@ __device__ __forceinline__ void step_finish(const WarpSmem& w, Game& g, StepOut&
   } else {
     int cnt = 0;  // :362, :598-605 — query uses the NEW side byte (quirk A.7)
 #pragma unroll 1
-    for (int i = lane; i < g.hist_len; i += 32) cnt += hist[i] == o.key_next;
-    cnt = warp_sum(cnt);
+    for (int i = lane; i < g.hist_len; i += L) cnt += hist[i] == o.key_next;
+    cnt = (int)T::sum((unsigned)cnt);
     if (cnt >= 3) {
       o.done = 1; o.reward = 0.0; o.is_int = 1;
       g.winner = 0;
@@ -992,13 +1028,14 @@ __device__ __forceinline__ void step_finish(const WarpSmem& w, Game& g, StepOut&
 }
 
 // make_move (chess_env.py:253-406).  hist: this game's position_history row.
+template <int L>
 __device__ __forceinline__ StepOut step(WarpSmem& w, Game& g, int move, uint64_t* __restrict__ hist,
                                         int hist_cap, const uint32_t* __restrict__ leap) {
-  StepOut o = step_apply(w, g, move, hist, hist_cap);
+  StepOut o = step_apply<L>(w, g, move, hist, hist_cap);
   bool checking = false;
   int n_legal = -1;
-  if (!o.done) n_legal = movegen(w, g, leap, &checking);  // :317 + :354/:376 in one pass
-  step_finish(w, g, o, n_legal, checking, hist);
+  if (!o.done) n_legal = movegen<L>(w, g, leap, &checking);  // :317 + :354/:376 in one pass
+  step_finish<L>(w, g, o, n_legal, checking, hist);
   return o;
 }
 
@@ -1023,37 +1060,38 @@ __device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2
 }
 
 // Capture-biased pick (diagnostic workloads only): kept out of line so that the uniform-pick
-// hot loop does not carry its code.
-static __device__ __noinline__ int pick_capture(const WarpSmem* wp, int n, uint32_t x0) {
+// hot loop does not carry its code.  lane/stride/member mask describe the calling tile.
+static __device__ __noinline__ int pick_capture(const WarpSmem* wp, int n, uint32_t x0, int lane,
+                                                int stride, unsigned mask, int shift) {
   const WarpSmem& w = *wp;
-  const int lane = lane_id();
-  unsigned masks[XQ_MAX_MOVES / 32];
+  const unsigned lanes = stride == 32 ? 0xffffffffu : ((1u << stride) - 1u);
   int ncap = 0;
-#pragma unroll
-  for (int k = 0; k < XQ_MAX_MOVES / 32; ++k) {
-    const int i = k * 32 + lane;
+  for (int base = 0; base < n; base += stride) {
+    const int i = base + lane;
     const bool cap = i < n && w.sq[(int)w.moves[i] % 90] != 0;
-    masks[k] = __ballot_sync(kFull, cap);
-    ncap += __popc(masks[k]);
+    ncap += __popc((__ballot_sync(mask, cap) >> shift) & lanes);
   }
   if (ncap == 0) return -1;
   int k = (int)(x0 % (uint32_t)ncap);
-#pragma unroll
-  for (int r = 0; r < XQ_MAX_MOVES / 32; ++r) {
-    const int c = __popc(masks[r]);
-    if (k < c) return r * 32 + (int)__fns(masks[r], 0, k + 1);
+  for (int base = 0; base < n; base += stride) {
+    const int i = base + lane;
+    const bool cap = i < n && w.sq[(int)w.moves[i] % 90] != 0;
+    const unsigned m = (__ballot_sync(mask, cap) >> shift) & lanes;
+    const int c = __popc(m);
+    if (k < c) return base + (int)__fns(m, 0, k + 1);
     k -= c;
   }
   return -1;
 }
 
 // Index into w.moves[0..n) chosen by the shared pick rule.
+template <int L>
 __device__ __forceinline__ int pick_index(const WarpSmem& w, int n, uint64_t seed, uint32_t game_id,
                                           uint32_t ply, int capture_bias) {
   uint32_t x[4];
   philox4x32(game_id, ply, 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), x);
   if (capture_bias > 0 && (int)(x[1] & 0xFFu) < capture_bias) {
-    const int idx = pick_capture(&w, n, x[0]);
+    const int idx = pick_capture(&w, n, x[0], Tile<L>::lane(), L, Tile<L>::mask(), Tile<L>::shift());
     if (idx >= 0) return idx;
   }
   return (int)(x[0] % (uint32_t)n);

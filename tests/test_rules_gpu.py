@@ -187,6 +187,32 @@ def test_fused_playout_vs_oracle(eng, xo, bias, first):
     assert int(res["plies"].sum()) == total
 
 
+@pytest.mark.parametrize("lpb", [8, 16, 32])
+def test_fused_playout_tile_widths(eng, xo, lpb, monkeypatch):
+    """The fused kernel with 8, 16 or 32 lanes per board (XQ_PLAYOUT_LPB) is bit-exact, traces
+    included, for uniform and capture-biased games and ragged batch sizes."""
+    monkeypatch.setenv("XQ_PLAYOUT_LPB", str(lpb))
+    for n, bias, first in ((4099, 0, 77), (1500, 200, 123456)):
+        bb = eng.BoardBatch(n)
+        res = eng.results_host(bb.playout(SEED + lpb, 70, first_game_id=first, capture_bias=bias))
+        total, ref = xo.playout_many(n, SEED + lpb, first, 70, bias, n_threads=8)
+        _cmp_results(res, ref)
+    bb = eng.BoardBatch(37)
+    res, tr = bb.playout(SEED, 70, capture_bias=128, trace=True)
+    res = eng.results_host(res)
+    n_arr, moves = tr["n"].cpu().numpy(), tr["moves"].cpu().numpy()
+    rew, flags = tr["reward"].cpu().numpy(), tr["flags"].cpu().numpy()
+    for g in range(37):
+        e = xo.Env()
+        r, t = e.playout(SEED, g, 70, 128, trace=True)
+        assert res["plies"][g] == r.plies and res["digest"][g] == r.digest
+        assert np.array_equal(n_arr[g, :r.plies], t["n"][:r.plies])
+        assert np.array_equal(rew[g, :r.plies].view(np.uint64), t["reward"][:r.plies].view(np.uint64))
+        assert np.array_equal(flags[g, :r.plies], t["flags"][:r.plies])
+        for q in range(r.plies):
+            assert np.array_equal(moves[g, q, :n_arr[g, q]], t["moves"][q, :t["n"][q]])
+
+
 def test_step_per_launch_equals_fused(eng):
     import torch
     n, bias = 2048, 96
