@@ -35,10 +35,10 @@ BYTES_PER_STEP_LAUNCH_MODE = 352
 #   fused playout: (board+meta in 128, out 128, result 40) / 70 plies + one 8-byte history append
 BYTES_PER_STEP_FUSED = (128 + 128 + 40) / 70.0 + 8.0
 # warp-instructions per board-step of playout_kernel<false>, from ncu smsp__inst_executed.sum /
-# plies of the same launch (profiles/r1/playout_v6_ncu_summary.txt); refreshed with every capture
-WARP_INST_PER_STEP = 2303.0
+# plies of the same launch (profiles/r1/playout_v7_ncu_summary.txt); refreshed with every capture
+WARP_INST_PER_STEP = 2193.0
 # dram__bytes_read.sum + dram__bytes_write.sum of one playout launch in the same capture
-DRAM_TRAFFIC_PER_LAUNCH = 23.14e6 + 19.48e6
+DRAM_TRAFFIC_PER_LAUNCH = 17.20e6 + 13.79e6
 FLOP_PER_LEAF_EVAL = 263_209_216          # ChessNet.forward, SURVEY.md §8d
 MCTS_GAMES, MCTS_SIMS, MCTS_OPENING_PLIES = 4096, 15, 4
 METRIC = "board-steps/sec (legal movegen+step)"
@@ -336,7 +336,7 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak,
                      "traffic": DRAM_TRAFFIC_PER_LAUNCH if n == BOARDS else None,
-                     "traffic_note": "ncu dram bytes read+write per launch (profiles/r1/playout_v6_ncu_summary.txt); "
+                     "traffic_note": "ncu dram bytes read+write per launch (profiles/r1/playout_v7_ncu_summary.txt); "
                                      "algorithmic bytes per launch = %.2e" % (BYTES_PER_STEP_FUSED * plies_per_launch),
                      "peak_source": peak_src,
                      "kernel": "xq::playout_kernel<false>",
