@@ -119,3 +119,41 @@ def test_net_evaluator_runs(mods):
         v = vis.cpu().numpy()
         assert (nc.cpu().numpy() == 44).all() and (v.sum(1) == 7).all()
         assert ((v > 0).sum(1) == 1).all()  # delta on the arg-max-prior child (Appendix C.1)
+
+
+def test_search_cfg3_size_properties(mods, xo):
+    """cfg 3 size (4,096 trees x 15 sims) and a cfg 4 slice (2,048 x 50): determinism, the
+    n-8 visit law (B.4), and the oracle on a strided sample of trees."""
+    eng, mcts = mods
+    for n, n_sims, stride in ((4096, 15, 128), (2048, 50, 256)):
+        bb = eng.BoardBatch(n)
+        bb.playout(99, 9, capture_bias=40)          # diversify
+        s = mcts.BatchedMCTS(n, n_sims)
+        mv1, vis1, nc1 = [t.clone() for t in s.search(bb.board, bb.meta, mcts.HashEvaluator())]
+        mv2, vis2, nc2 = s.search(bb.board, bb.meta, mcts.HashEvaluator())
+        assert bool((vis1 == vis2).all()) and bool((mv1 == mv2).all()) and bool((nc1 == nc2).all())
+        v, c = vis1.cpu().numpy(), nc1.cpu().numpy()
+        live = c > 0
+        assert live.all()                             # nothing ends within 9 plies
+        assert (v.sum(1) == n_sims - 8).all()
+        boards, meta = bb.boards_host(), bb.meta_host()
+        pos = lambda q: None if q < 0 else (int(q) // 9, int(q) % 9)
+        for g in range(0, n, stride):
+            e = xo.Env().load(boards[g].reshape(10, 9), int(meta["player"][g]), int(meta["move_count"][g]),
+                              None, pos(meta["red_king"][g]), pos(meta["black_king"][g]),
+                              int(meta["no_capture"][g]))
+            om, ov, _ = xo.mcts_search(e, n_sims)
+            assert np.array_equal(mv1[g, :c[g]].cpu().numpy(), om) and np.array_equal(v[g, :c[g]], ov), g
+
+
+def test_opponent_mode_runs_and_records_red_only(mods):
+    import torch
+    eng, mcts = mods
+    from chinesechessai_b200.self_play import BatchedSelfPlay
+    sp = BatchedSelfPlay(mcts.HashEvaluator(False), 12, 15, temperature=1.0,
+                         opponent_network=mcts.HashEvaluator(True), seed=3)
+    sp.play(12)
+    out = sp.materialise(red_only=True)
+    assert len(out) == 12
+    for gd, winner, reason in out:
+        assert len(gd) == 6 and all((b != 0).sum() >= 30 for b, _, _ in gd)
