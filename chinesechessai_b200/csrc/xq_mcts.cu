@@ -346,6 +346,46 @@ __global__ void __launch_bounds__(kThreadsM)
   if (lane == 0) n_children[g] = (int16_t)n;
 }
 
+// Temperature sampling of the move to play (self_play.py:219-243), one thread per game.
+__global__ void __launch_bounds__(256)
+    sample_moves_kernel(const int32_t* __restrict__ visits, const int16_t* __restrict__ n_children,
+                        const uint8_t* __restrict__ active, double temperature, uint64_t seed,
+                        uint32_t first_game_id, uint32_t ply, int16_t* __restrict__ chosen,
+                        int n_games) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_games) return;
+  const int n = n_children[g];
+  if (n <= 0 || (active && !active[g])) {
+    chosen[g] = -1;
+    return;
+  }
+  const int32_t* v = visits + (size_t)g * XQ_MAX_MOVES;
+  uint32_t x[4];
+  philox4x32(first_game_id + (uint32_t)g, ply, 1u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), x);
+  int pick = 0;
+  if (temperature < 0.01) {  // :224-227, np.argmax = first maximum
+    int best = v[0];
+    for (int i = 1; i < n; ++i)
+      if (v[i] > best) { best = v[i]; pick = i; }
+  } else {
+    const double inv_t = 1.0 / temperature;
+    double total = 0.0;
+    for (int i = 0; i < n; ++i) total = __dadd_rn(total, pow((double)v[i], inv_t));
+    if (!(total > 0.0)) {  // all-zero counts (n_sims <= 8): the reference divides by zero here
+      pick = (int)(x[0] % (uint32_t)n);
+    } else {
+      const double u = (double)((((uint64_t)x[0] << 32) | x[1]) >> 11) * (1.0 / 9007199254740992.0);
+      double cdf = 0.0;
+      pick = n - 1;
+      for (int i = 0; i < n; ++i) {  // searchsorted(cumsum(p), u, side="right")
+        cdf = __dadd_rn(cdf, __ddiv_rn(pow((double)v[i], inv_t), total));
+        if (cdf > u) { pick = i; break; }
+      }
+    }
+  }
+  chosen[g] = (int16_t)pick;
+}
+
 // Mirror of the oracle's deterministic evaluator (order-independent arithmetic).
 __global__ void __launch_bounds__(kThreadsM)
     hash_eval_kernel(const int8_t* __restrict__ board, int board_stride,
@@ -450,6 +490,17 @@ int xq_mcts_root_visits(const void* trees, int num_simulations, int16_t* moves, 
   mcts_root_visits_kernel<<<ctas_m(n_games), kThreadsM, 0, (cudaStream_t)stream>>>(
       trees, num_simulations, moves, visits, n_children, n_games);
   return check_launch("xq_mcts_root_visits");
+}
+
+int xq_sample_moves(const int32_t* visits, const int16_t* n_children, const uint8_t* active,
+                    double temperature, uint64_t seed, uint32_t first_game_id, uint32_t ply,
+                    int16_t* chosen, int n_games, void* stream) {
+  if (n_games == 0) return 0;
+  XQM_REQUIRE(visits && n_children && chosen && n_games > 0, "null pointer or non-positive size");
+  XQM_REQUIRE(temperature >= 0.0, "negative temperature");
+  sample_moves_kernel<<<(n_games + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      visits, n_children, active, temperature, seed, first_game_id, ply, chosen, n_games);
+  return check_launch("xq_sample_moves");
 }
 
 int xq_hash_eval(const int8_t* board, int board_stride, const int8_t* player, const int16_t* moves,

@@ -16,10 +16,10 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import BOARD_STRIDE, MAX_MOVES, META_DTYPE
+from ._lib import BOARD_STRIDE, MAX_MOVES, META_DTYPE, check
 from .chess_env import ChineseChess, format_end_reason
 from .config import MAX_MOVES as MAX_PLIES, MCTS_SIMULATIONS
-from .engine import BoardBatch, pack_move, unpack_move
+from .engine import BoardBatch, _ptr, _stream, pack_move, unpack_move
 from .mcts import WAVE, BatchedMCTS, NetEvaluator
 
 Move = Tuple[int, int, int, int]
@@ -174,6 +174,7 @@ class BatchedSelfPlay:
         self.temperature = float(temperature)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         d = self.device
+        self.lib = _lib.load()
         self.boards = BoardBatch(self.n, device=d, hist_cap=MAX_PLIES + 2)
         self.mcts = BatchedMCTS(self.n, self.n_sims, device=d)
         self.eval_red = network if callable(network) and not isinstance(network, torch.nn.Module) \
@@ -182,8 +183,11 @@ class BatchedSelfPlay:
         if opponent_network is not None:
             self.eval_black = opponent_network if callable(opponent_network) and not isinstance(
                 opponent_network, torch.nn.Module) else NetEvaluator(opponent_network, net_dtype)
-        self.gen = torch.Generator(device=d)
-        self.gen.manual_seed(int(np.random.randint(0, 2**31 - 1)) if seed is None else int(seed) + first_game_id)
+        # move sampling is counter-based: (seed, game id, ply) -> uniform, so a game's trajectory
+        # does not depend on the batch or GPU it is played on
+        self.seed = int(np.random.randint(0, 2**31 - 1)) if seed is None else int(seed)
+        self.first_game_id = int(first_game_id)
+        self.chosen = torch.zeros((self.n,), dtype=torch.int16, device=d)
         P = MAX_PLIES
         self.rec_board = torch.zeros((P, self.n, 90), dtype=torch.int8, device=d)
         self.rec_player = torch.zeros((P, self.n), dtype=torch.int8, device=d)
@@ -191,6 +195,7 @@ class BatchedSelfPlay:
         self.rec_visits = torch.zeros((P, self.n, MAX_MOVES), dtype=torch.int32, device=d)
         self.rec_n = torch.zeros((P, self.n), dtype=torch.int16, device=d)
         self.rec_reward = torch.zeros((P, self.n), dtype=torch.float64, device=d)
+        self.rec_move = torch.full((P, self.n), -1, dtype=torch.int16, device=d)
         self.rec_played = torch.zeros((P, self.n), dtype=torch.bool, device=d)
         self.plies = 0
         self.done = torch.zeros(self.n, dtype=torch.bool, device=d)
@@ -221,21 +226,15 @@ class BatchedSelfPlay:
         per-ply "all games over?" host read (benchmarks that time a fixed number of plies)."""
         b = self.boards
         done = self.done
-        inv_t = 1.0 / self.temperature if self.temperature >= 0.01 else None
         for ply in range(self.plies, min(MAX_PLIES, self.plies + max_plies)):
             active = (~done).to(torch.uint8)
             mv, vis, nc = self._search(active)
-            live = (nc > 0) & ~done  # self_play.py:207,216: no legal move / empty search ends the game
-            counts = vis.to(torch.float64)
-            if inv_t is None:
-                idx = counts.argmax(dim=1)
-            else:
-                w = counts.pow(inv_t)
-                w = torch.where(live[:, None], w, torch.ones_like(w))  # keep multinomial well-defined
-                rowsum = w.sum(1, keepdim=True)
-                w = torch.where(rowsum > 0, w, torch.ones_like(w))
-                idx = torch.multinomial(w, 1, generator=self.gen).squeeze(1)
-            move = mv.gather(1, idx[:, None]).squeeze(1)
+            # self_play.py:219-243 on device; idx = -1: game over / no legal move / empty search
+            check(self.lib.xq_sample_moves(_ptr(vis), _ptr(nc), _ptr(active), self.temperature,
+                                           self.seed, self.first_game_id, ply, _ptr(self.chosen),
+                                           self.n, _stream()))
+            live = self.chosen >= 0
+            move = mv.gather(1, self.chosen.clamp(min=0).to(torch.int64)[:, None]).squeeze(1)
             move = torch.where(live, move, torch.full_like(move, -1))
             self.rec_board[ply].copy_(b.board[:, :90])
             self.rec_player[ply].copy_(b.meta[:, 0].view(torch.int8))
@@ -243,6 +242,7 @@ class BatchedSelfPlay:
             self.rec_visits[ply].copy_(vis)
             self.rec_n[ply].copy_(nc)
             self.rec_played[ply].copy_(live)
+            self.rec_move[ply].copy_(move)
             reward, flags = b.step(move.contiguous())
             self.rec_reward[ply].copy_(reward)
             done = done | ~live | ((flags & 1) != 0)

@@ -217,6 +217,17 @@ int xq_mcts_backup(void *trees, int num_simulations, const int16_t *leaf_moves, 
 int xq_mcts_root_visits(const void *trees, int num_simulations, int16_t *moves, int32_t *visits,
                         int16_t *n_children, int n_games, void *stream);
 
+/* Move choice of self_play_game (self_play.py:219-243) for a batch: p_i = visits_i^(1/T) /
+ * sum (float64), or a one-hot on the first maximum when T < 0.01 (:224-227); the index is drawn
+ * by inverse CDF with u = philox4x32-10(key=seed, ctr=(first_game_id+g, ply, 1, 0)) in [0,1),
+ * so a game's trajectory depends on (seed, game id) only — not on which GPU or batch plays it.
+ * (The reference draws from the process-global np.random stream; parity is defined on the
+ * visit counts)  chosen[g] = index into the root's move list, or -1 when the game
+ * is inactive or has no children.  active: optional uint8[n_games]. */
+int xq_sample_moves(const int32_t *visits, const int16_t *n_children, const uint8_t *active,
+                    double temperature, uint64_t seed, uint32_t first_game_id, uint32_t ply,
+                    int16_t *chosen, int n_games, void *stream);
+
 /* Deterministic test evaluator (hashed or flat priors, hashed value) identical
  * to the oracle's, so MCTS parity can be checked at batch scale without a net. */
 int xq_hash_eval(const int8_t *board, int board_stride, const int8_t *player,

@@ -503,6 +503,31 @@ int xqo_pick_move(const xqo_state *s, const int16_t *moves, int n,
   return (int)(x[0] % (uint32_t)n);
 }
 
+/* self_play.py:219-243: counts ** (1/T) / sum, np.random.choice by inverse CDF
+ * (searchsorted(cumsum(p), u, side="right")); u from the shared counter-based generator. */
+int xqo_sample_move(const int32_t *visits, int n, double temperature, uint64_t seed,
+                    uint32_t game_id, uint32_t ply) {
+  uint32_t x[4];
+  xqo_philox4x32(game_id, ply, 1u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), x);
+  if (n <= 0) return -1;
+  if (temperature < 0.01) {
+    int pick = 0;
+    for (int i = 1; i < n; ++i)
+      if (visits[i] > visits[pick]) pick = i;
+    return pick;
+  }
+  double inv_t = 1.0 / temperature, total = 0.0;
+  for (int i = 0; i < n; ++i) total += pow((double)visits[i], inv_t);
+  if (!(total > 0.0)) return (int)(x[0] % (uint32_t)n);
+  double u = (double)((((uint64_t)x[0] << 32) | x[1]) >> 11) * (1.0 / 9007199254740992.0);
+  double cdf = 0.0;
+  for (int i = 0; i < n; ++i) {
+    cdf += pow((double)visits[i], inv_t) / total;
+    if (cdf > u) return i;
+  }
+  return n - 1;
+}
+
 static inline uint64_t dbits(double d) {
   uint64_t u;
   memcpy(&u, &d, 8);

@@ -107,6 +107,11 @@ int64_t xqo_playout_many(int n_games, uint32_t first_game_id, uint64_t seed,
                          int max_plies, int capture_bias, int n_threads,
                          xqo_playout_result *results);
 
+/* Move choice of self_play_game (self_play.py:219-243) with the counter-based uniform the CUDA
+ * engine uses (philox ctr=(game_id, ply, 1, 0)); returns the index into the visit list. */
+int xqo_sample_move(const int32_t *visits, int n, double temperature, uint64_t seed,
+                    uint32_t game_id, uint32_t ply);
+
 /* --- evaluator glue (neural_network.py:128-169) --------------------------- */
 void xqo_encode_board(const int8_t *board, int player,
                       float *planes /* [15][10][9] */);

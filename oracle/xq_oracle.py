@@ -110,6 +110,8 @@ def lib():
         L.xqo_playout_many.argtypes = [C.c_int, C.c_uint32, C.c_uint64, C.c_int, C.c_int, C.c_int,
                                        C.c_void_p]
         L.xqo_playout_many.restype = C.c_int64
+        L.xqo_sample_move.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_uint64, C.c_uint32, C.c_uint32]
+        L.xqo_sample_move.restype = C.c_int
         L.xqo_encode_board.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.xqo_logits_to_priors.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.xqo_mcts_search.argtypes = [P(State), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -262,6 +264,11 @@ def philox(c0: int, c1: int, k0: int, k1: int) -> np.ndarray:
     out = np.zeros(4, np.uint32)
     lib().xqo_philox4x32(c0, c1, 0, 0, k0, k1, out.ctypes.data)
     return out
+
+
+def sample_move(visits, temperature: float, seed: int, game_id: int, ply: int) -> int:
+    v = np.ascontiguousarray(visits, dtype=np.int32)
+    return int(lib().xqo_sample_move(v.ctypes.data, len(v), float(temperature), seed, game_id, ply))
 
 
 def encode_board(board, player: int) -> np.ndarray:

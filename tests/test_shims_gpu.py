@@ -153,55 +153,66 @@ def test_self_play_game_vs_reference(pkg, xo):
             assert repr(float(reward)) == repr(gr)
 
 
-def test_parallel_self_play_batched(pkg, xo):
-    """Batched device loop: every recorded game must be a legal trajectory under the oracle and
-    its samples/rewards must follow self_play.py:262-310."""
+def test_batched_self_play_vs_oracle_game_loop(pkg, xo):
+    """The batched device game loop (search -> counter-based temperature sampling -> make_move)
+    against the same loop driven on the oracle: identical visit counts, chosen moves, rewards,
+    outcomes and shaped sample rewards (self_play.py:203-310) for every game and ply."""
+    _, self_play = pkg
+    from chinesechessai_b200.mcts import HashEvaluator
+    for n, n_sims, temp, seed, first in ((24, 15, 1.0, 5, 0), (10, 30, 0.5, 9, 1000), (6, 15, 0.001, 2, 7)):
+        sp = self_play.BatchedSelfPlay(HashEvaluator(), n, n_sims, temperature=temp, seed=seed,
+                                       first_game_id=first)
+        sp.play()
+        res = sp.materialise()
+        P = sp.plies
+        rm, rv, rn = (t[:P].cpu().numpy() for t in (sp.rec_moves, sp.rec_visits, sp.rec_n))
+        played, rmove = sp.rec_played[:P].cpu().numpy(), sp.rec_move[:P].cpu().numpy()
+        meta = sp.boards.meta_host()
+        for g, (data, winner, reason) in enumerate(res):
+            e = xo.Env()
+            rewards, boards = [], []
+            for p in range(70):
+                om, ov, _ = xo.mcts_search(e, n_sims)
+                if len(e.legal_moves_packed()) == 0 or len(om) == 0:
+                    break
+                assert played[p, g], (g, p)
+                k = int(rn[p, g])
+                assert np.array_equal(rm[p, g, :k], om) and np.array_equal(rv[p, g, :k], ov), (g, p)
+                idx = xo.sample_move(ov, temp, seed, first + g, p)
+                assert int(rmove[p, g]) == int(om[idx]), (g, p)
+                boards.append(e.board.copy())
+                rw, _, done = e.make_move(int(om[idx]))
+                rewards.append(rw)
+                if done:
+                    break
+            n_plies = len(rewards)
+            assert not played[n_plies:, g].any() and played[:n_plies, g].all(), g
+            w = 0 if e.winner is None else e.winner
+            assert winner == w and meta["reason"][g] == e.s.reason, g
+            assert len(data) == n_plies
+            for i, (b, probs, total) in enumerate(data):
+                assert np.array_equal(b, boards[i])
+                player = 1 if i % 2 == 0 else -1
+                assert repr(total) == repr(self_play.final_reward(w, player, n_plies) + rewards[i] * 0.01)
+                assert abs(sum(probs.values()) - 1.0) < 1e-9
+    out = self_play.parallel_self_play(_Net(), 4, temperature=1.0, num_simulations=15, num_workers=4)
+    assert len(out) == 4 and all(len(gd) > 0 and isinstance(r, str) for gd, w, r in out)
+
+
+def test_self_play_is_shard_invariant(pkg):
+    """A game's trajectory depends on (seed, game id) only: two half batches with game-id
+    offsets reproduce the full batch (what makes the multi-GPU shards verifiable)."""
     import torch
     _, self_play = pkg
     from chinesechessai_b200.mcts import HashEvaluator
-    n, n_sims = 24, 15
-    sp = self_play.BatchedSelfPlay(HashEvaluator(), n, n_sims, temperature=1.0, seed=5)
-    sp.play()
-    res = sp.materialise()
-    assert len(res) == n
-    rm = sp.rec_moves[:sp.plies].cpu().numpy()
-    rv = sp.rec_visits[:sp.plies].cpu().numpy()
-    rn = sp.rec_n[:sp.plies].cpu().numpy()
-    played = sp.rec_played[:sp.plies].cpu().numpy()
-    boards_after = sp.boards.boards_host()
-    for g, (data, winner, reason) in enumerate(res):
-        e = xo.Env()
-        rewards = []
-        for p in range(sp.plies):
-            if not played[p, g]:
-                break
-            om, ov, _ = xo.mcts_search(e, n_sims)
-            k = int(rn[p, g])
-            assert np.array_equal(rm[p, g, :k], om) and np.array_equal(rv[p, g, :k], ov), (g, p)
-            board_before = e.board.copy()
-            assert np.array_equal(data[p][0], board_before)
-            # the sampled move is the one that was applied: find it from the next recorded board
-            nxt = sp.rec_board[p + 1, g].cpu().numpy() if p + 1 < sp.plies and played[p + 1, g] else boards_after[g]
-            cand = [m for m in om.tolist() if ov[om.tolist().index(m)] > 0]
-            hit = None
-            for m in cand:
-                t = e.clone()
-                t.make_move(int(m))
-                if np.array_equal(t.board.reshape(90), nxt):
-                    hit = m
-                    break
-            assert hit is not None, (g, p)
-            rw, _, done = e.make_move(int(hit))
-            rewards.append(rw)
-        w = 0 if e.winner is None else e.winner
-        assert winner == w, g
-        L = len(data)
-        for i, (b, probs, total) in enumerate(data):
-            player = 1 if i % 2 == 0 else -1
-            assert repr(total) == repr(self_play.final_reward(w, player, L) + rewards[i] * 0.01), (g, i)
-            assert abs(sum(probs.values()) - 1.0) < 1e-9
-    out = self_play.parallel_self_play(_Net(), 4, temperature=1.0, num_simulations=15, num_workers=4)
-    assert len(out) == 4 and all(len(gd) > 0 and isinstance(r, str) for gd, w, r in out)
+    full = self_play.BatchedSelfPlay(HashEvaluator(), 32, 15, temperature=1.0, seed=77)
+    full.play(20)
+    for lo in (0, 16):
+        part = self_play.BatchedSelfPlay(HashEvaluator(), 16, 15, temperature=1.0, seed=77, first_game_id=lo)
+        part.play(20)
+        assert torch.equal(part.rec_move[:20], full.rec_move[:20, lo:lo + 16])
+        assert torch.equal(part.rec_visits[:20], full.rec_visits[:20, lo:lo + 16])
+        assert torch.equal(part.boards.board, full.boards.board[lo:lo + 16])
 
 
 def _Net():
