@@ -60,3 +60,26 @@ def gather_samples(samples: Dict[str, torch.Tensor], dst: int = 0) -> Optional[D
         if rank == dst:
             out[k] = torch.cat([b[:c] for b, c in zip(bufs, counts)])
     return out if rank == dst else None
+
+
+def distributed_self_play(evaluator, num_games: int, num_simulations: int, temperature: float = 1.0,
+                          seed: int = 0, network: Optional[torch.nn.Module] = None, dst: int = 0,
+                          opponent=None):
+    """One self-play phase on all ranks (one process per GPU): broadcast ``network``'s weights
+    from ``dst`` (if given), play this rank's block of game ids as one device batch, gather the
+    training samples on ``dst``.  Replaces parallel_self_play's process pool + pickles
+    (self_play.py:386-408); there is no collective inside the game loop.
+    Returns (samples dict on ``dst`` / None elsewhere, this rank's BatchedSelfPlay)."""
+    from .samples import training_tensors
+    from .self_play import BatchedSelfPlay
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    if network is not None:
+        broadcast_weights(network, src=dst)
+    lo, hi = shard_range(num_games, rank, world)
+    sp = BatchedSelfPlay(evaluator, hi - lo, num_simulations, temperature, opponent_network=opponent,
+                         seed=seed, first_game_id=lo)
+    sp.play()
+    mine = training_tensors(sp, red_only=opponent is not None)
+    mine["game"] = mine["game"] + lo
+    return gather_samples(mine, dst=dst), sp

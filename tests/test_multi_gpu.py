@@ -1,0 +1,61 @@
+"""GPU, world_size 2, NCCL: games sharded over two GPUs reproduce the single-GPU run of the same
+game ids (SURVEY §7 test plan item 6); weights are identical after the broadcast.
+Run with: gpurun --gpus 2 -- python -m pytest tests/test_multi_gpu.py -m gpu"""
+import os
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from chinesechessai_b200 import dist as xd
+    from chinesechessai_b200.mcts import HashEvaluator
+    from chinesechessai_b200.neural_network import ChessNet
+    from chinesechessai_b200.samples import training_tensors
+    from chinesechessai_b200.self_play import BatchedSelfPlay
+    torch.manual_seed(100 + rank)
+    net = ChessNet(num_channels=16).cuda()
+    samples, sp = xd.distributed_self_play(HashEvaluator(), 41, 15, 1.0, seed=5, network=net)
+    chk = torch.tensor([sum(float(p.double().sum()) for p in net.parameters())], device="cuda",
+                       dtype=torch.float64)
+    both = [torch.zeros_like(chk) for _ in range(world)]
+    dist.all_gather(both, chk)
+    ok = True
+    if rank == 0:
+        ref = BatchedSelfPlay(HashEvaluator(), 41, 15, 1.0, seed=5)
+        ref.play()
+        want = training_tensors(ref)
+        ok = all(torch.equal(samples[k], want[k]) for k in ("board", "player", "reward", "game", "ply"))
+        ok = ok and float(both[0]) == float(both[1]) and len(want["reward"]) > 41 * 10
+    else:
+        ok = samples is None
+    out.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gpu_shards_equal_single_gpu_run():
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 1000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == {0: True, 1: True}
