@@ -172,6 +172,49 @@ def measure_step_per_launch(torch, BoardBatch, n, first_id, steps, flush):
     return plies / (ms * 1e-3), ms / steps, 2 * PLIES + 2
 
 
+def measure_tree_only(torch, dev, games, sims):
+    """Search kernels alone (select / expand / backup + the hashed stand-in evaluator): sims/s of
+    the tree machinery without the network, and the same literal algorithm (self_play.py:89-154,
+    C port, hashed evaluator) on the host cores for a bounded sample."""
+    from concurrent.futures import ThreadPoolExecutor
+    from chinesechessai_b200.engine import BoardBatch
+    from chinesechessai_b200.mcts import BatchedMCTS, HashEvaluator
+    from oracle import xq_oracle as xo
+    bb = BoardBatch(games, device=dev)
+    bb.playout(SEED, MCTS_OPENING_PLIES)
+    m = BatchedMCTS(games, sims, device=dev)
+    ev = HashEvaluator()
+    m.search(bb.board, bb.meta, ev)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    a.record()
+    for _ in range(reps):
+        m.search(bb.board, bb.meta, ev)
+    b.record()
+    torch.cuda.synchronize()
+    gpu = games * sims * reps / (a.elapsed_time(b) * 1e-3)
+    threads = os.cpu_count() or 1
+    boards, meta = bb.boards_host(), bb.meta_host()
+    pos = lambda q: None if q < 0 else (int(q) // 9, int(q) % 9)
+    n_cpu = min(games, 64 * threads)
+
+    def one(g):
+        e = xo.Env().load(boards[g].reshape(10, 9), int(meta["player"][g]), int(meta["move_count"][g]),
+                          None, pos(meta["red_king"][g]), pos(meta["black_king"][g]),
+                          int(meta["no_capture"][g]))
+        xo.mcts_search(e, sims)
+    xo.mcts_search(xo.Env(), sims)
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(one, range(n_cpu)))
+    dt = time.perf_counter() - t0
+    return {"gpu_sims_per_s": gpu,
+            "cpu_baseline": {"value": n_cpu * sims / dt, "unit": "sims/s", "cores": threads, "kind": "port",
+                             "sample": f"{n_cpu} searches x {sims} sims, literal replay per simulation "
+                                       f"(oracle/xq_oracle.c via ctypes threads), {dt:.1f} s"}}
+
+
 def measure_mcts(torch, dev, plies_timed=6, games=MCTS_GAMES, sims=MCTS_SIMS, label="cfg3"):
     """cfg 3: 4,096 concurrent self-play games, 15 sims/move (2 waves of 8+7), random-init ChessNet
     (torch.manual_seed(0)), temperature 1.0; games diversified by 4 random opening plies.
@@ -371,6 +414,7 @@ def run_ours(args):
             tf_peak = 1400.0
         mc["roofline"]["peak"] = tf_peak
         mc["roofline"]["frac"] = mc["roofline"]["achieved"] / tf_peak
+        mc["tree_only"] = measure_tree_only(torch, dev, MCTS_GAMES, MCTS_SIMS)
         mc["gpu_launches"] = int(lib.xq_launch_count() - l0)
         out["mcts"] = mc
         if not args.no_cfg4:

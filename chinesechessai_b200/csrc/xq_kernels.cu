@@ -336,13 +336,14 @@ __global__ void __launch_bounds__(256)
 // _logits_to_move_probs (neural_network.py:148-169): warp per position.
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
-    priors_kernel(const T* __restrict__ logits, const int16_t* __restrict__ moves, int moves_stride,
+    priors_kernel(const T* __restrict__ logits, int logits_stride,
+                  const int16_t* __restrict__ moves, int moves_stride,
                   const int16_t* __restrict__ n_moves, float* __restrict__ priors, int n) {
   const int g = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   if (g >= n) return;
   const int lane = (threadIdx.x & 31);
   const int cnt = min((int)n_moves[g], XQ_MAX_MOVES);
-  const T* lg = logits + (size_t)g * XQ_POLICY;
+  const T* lg = logits + (size_t)g * logits_stride;
   const int16_t* mv = moves + (size_t)g * moves_stride;
   float v[XQ_MAX_MOVES / 32];
   float mx = -INFINITY;
@@ -588,17 +589,18 @@ int xq_encode_planes(const int8_t* board, int board_stride, const int8_t* player
   return check_launch("xq_encode_planes");
 }
 
-int xq_policy_priors(const void* logits, int logits_bf16, const int16_t* moves, int moves_stride,
-                     const int16_t* n_moves, float* priors, int n, void* stream) {
+int xq_policy_priors(const void* logits, int logits_bf16, int logits_stride, const int16_t* moves,
+                     int moves_stride, const int16_t* n_moves, float* priors, int n, void* stream) {
   if (n == 0) return 0;
-  XQ_REQUIRE(logits && moves && n_moves && priors && n >= 0 && moves_stride >= 1,
+  XQ_REQUIRE(logits && moves && n_moves && priors && n >= 0 && moves_stride >= 1 &&
+                 logits_stride >= XQ_POLICY,
              "null pointer or bad stride");
   if (logits_bf16)
     priors_kernel<__nv_bfloat16><<<ctas_for(n), kThreads, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)logits, moves, moves_stride, n_moves, priors, n);
+        (const __nv_bfloat16*)logits, logits_stride, moves, moves_stride, n_moves, priors, n);
   else
     priors_kernel<float><<<ctas_for(n), kThreads, 0, (cudaStream_t)stream>>>(
-        (const float*)logits, moves, moves_stride, n_moves, priors, n);
+        (const float*)logits, logits_stride, moves, moves_stride, n_moves, priors, n);
   return check_launch("xq_policy_priors");
 }
 

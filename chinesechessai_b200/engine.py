@@ -190,12 +190,12 @@ def policy_priors(logits: torch.Tensor, moves: torch.Tensor, n_moves: torch.Tens
     """ChessNet._logits_to_move_probs (neural_network.py:148-169) for a batch."""
     lib = _lib.load()
     n = logits.shape[0]
-    assert logits.is_contiguous() and logits.shape[1] == _lib.POLICY
+    assert logits.stride(1) == 1 and logits.shape[1] >= _lib.POLICY  # padded heads allowed
     assert logits.dtype in (torch.float32, torch.bfloat16)
     if out is None:
         out = torch.empty((n, MAX_MOVES), dtype=torch.float32, device=logits.device)
     with torch.cuda.device(logits.device):
         check(lib.xq_policy_priors(_ptr(logits), 1 if logits.dtype == torch.bfloat16 else 0,
-                                   _ptr(moves), moves.stride(0), _ptr(n_moves), _ptr(out), n,
-                                   _stream()))
+                                   logits.stride(0), _ptr(moves), moves.stride(0), _ptr(n_moves),
+                                   _ptr(out), n, _stream()))
     return out

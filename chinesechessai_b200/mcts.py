@@ -38,8 +38,14 @@ class HashEvaluator:
 
 
 class _FoldedNet(torch.nn.Module):
-    """Inference copy of ChessNet: eval-mode BatchNorm folded into the preceding conv
-    (exact algebra, torch.nn.utils.fusion), weights cast to ``dtype``, channels-last."""
+    """Inference copy of ChessNet for the search: eval-mode BatchNorm folded into the preceding
+    conv (exact algebra, torch.nn.utils.fusion), weights cast to ``dtype``, channels-last,
+    conv+bias+ReLU(+residual) issued as ONE cuDNN call each (torch.cudnn_convolution_relu /
+    _add_relu) instead of conv + separate bias-add / ReLU / add kernels, and the policy head
+    padded from 8100 to 8192 outputs so the GEMM takes an aligned tensor-core path (the prior
+    kernel reads the padded rows through its row stride).  Library calls only — no custom GEMM."""
+
+    POLICY_PAD = 8192
 
     def __init__(self, net: torch.nn.Module, dtype: torch.dtype):
         super().__init__()
@@ -52,16 +58,48 @@ class _FoldedNet(torch.nn.Module):
             for b in n.res_blocks)
         self.policy_conv = fuse_conv_bn_eval(n.policy_conv, n.policy_bn)
         self.value_conv = fuse_conv_bn_eval(n.value_conv, n.value_bn)
-        self.policy_fc, self.value_fc1, self.value_fc2 = n.policy_fc, n.value_fc1, n.value_fc2
+        fc = n.policy_fc
+        self.policy_fc = torch.nn.Linear(fc.in_features, self.POLICY_PAD, device=fc.weight.device)
+        with torch.no_grad():
+            self.policy_fc.weight.zero_()
+            self.policy_fc.bias.zero_()
+            self.policy_fc.weight[:fc.out_features].copy_(fc.weight)
+            self.policy_fc.bias[:fc.out_features].copy_(fc.bias)
+        self.value_fc1, self.value_fc2 = n.value_fc1, n.value_fc2
         self.to(dtype=dtype, memory_format=torch.channels_last)
+        self.fused = False
+        if next(self.parameters()).is_cuda:
+            try:  # probe the fused cuDNN entry points once
+                x = torch.zeros((2, 15, 10, 9), dtype=dtype, device=fc.weight.device).contiguous(
+                    memory_format=torch.channels_last)
+                self.fused = True
+                self.forward(x)
+                torch.cuda.synchronize()
+            except Exception:
+                self.fused = False
+
+    @staticmethod
+    def _cr(conv, x):
+        return torch.cudnn_convolution_relu(x, conv.weight, conv.bias, conv.stride, conv.padding,
+                                            conv.dilation, conv.groups)
 
     def forward(self, x):
-        x = torch.relu(self.stem(x))
-        for c1, c2 in self.blocks:
-            x = torch.relu(c2(torch.relu(c1(x))) + x)
-        p = self.policy_fc(torch.relu(self.policy_conv(x)).flatten(1))  # NCHW-order flatten
-        v = torch.relu(self.value_conv(x)).flatten(1)
-        v = torch.tanh(self.value_fc2(torch.relu(self.value_fc1(v))))
+        if self.fused:
+            x = self._cr(self.stem, x)
+            for c1, c2 in self.blocks:
+                y = self._cr(c1, x)
+                x = torch.cudnn_convolution_add_relu(y, c2.weight, x, 1.0, c2.bias, c2.stride,
+                                                     c2.padding, c2.dilation, c2.groups)
+            p = self._cr(self.policy_conv, x)
+            v = self._cr(self.value_conv, x)
+        else:
+            x = torch.relu(self.stem(x))
+            for c1, c2 in self.blocks:
+                x = torch.relu(c2(torch.relu(c1(x))) + x)
+            p = torch.relu(self.policy_conv(x))
+            v = torch.relu(self.value_conv(x))
+        p = self.policy_fc(p.flatten(1))  # NCHW-order flatten, as the reference's .view
+        v = torch.tanh(self.value_fc2(torch.relu(self.value_fc1(v.flatten(1)))))
         return p, v
 
 
@@ -90,7 +128,8 @@ class NetEvaluator:
             if self._fast is None:
                 self._fast = _FoldedNet(self.net, self.dtype)
             logits, value = self._fast(planes.contiguous(memory_format=torch.channels_last))
-        logits = logits.contiguous()
+        if logits.stride(1) != 1:
+            logits = logits.contiguous()
         if logits.dtype not in (torch.float32, torch.bfloat16):
             logits = logits.float()
         pri = policy_priors(logits, leaf_moves, leaf_n)

@@ -168,11 +168,12 @@ int xq_encode_planes(const int8_t *board, int board_stride, const int8_t *player
                      void *stream);
 
 /* ChessNet._logits_to_move_probs (neural_network.py:148-169): gather the
- * legal moves' logits and softmax in float32.  logits: float32 or bf16
- * [n][XQ_POLICY]; priors float32[n][XQ_MAX_MOVES]. */
-int xq_policy_priors(const void *logits, int logits_bf16, const int16_t *moves,
-                     int moves_stride, const int16_t *n_moves, float *priors,
-                     int n, void *stream);
+ * legal moves' logits and softmax in float32.  logits: float32 or bf16 rows of
+ * logits_stride >= XQ_POLICY elements (a padded policy head may be passed as is);
+ * priors float32[n][XQ_MAX_MOVES]. */
+int xq_policy_priors(const void *logits, int logits_bf16, int logits_stride,
+                     const int16_t *moves, int moves_stride, const int16_t *n_moves,
+                     float *priors, int n, void *stream);
 
 /* ---- MCTS: self_play.py:19-175 ------------------------------------------- */
 /* One flat node pool per game ("tree"), caller-allocated device memory of
