@@ -206,9 +206,13 @@ def measure_tree_only(torch, dev, games, sims):
         xo.mcts_search(e, sims)
     xo.mcts_search(xo.Env(), sims)
     t0 = time.perf_counter()
+    done = 0
     with ThreadPoolExecutor(threads) as ex:
-        list(ex.map(one, range(n_cpu)))
+        while time.perf_counter() - t0 < 4.0:       # bounded sample: ~4 s of host work
+            list(ex.map(one, range(n_cpu)))
+            done += n_cpu
     dt = time.perf_counter() - t0
+    n_cpu = done
     return {"gpu_sims_per_s": gpu,
             "cpu_baseline": {"value": n_cpu * sims / dt, "unit": "sims/s", "cores": threads, "kind": "port",
                              "sample": f"{n_cpu} searches x {sims} sims, literal replay per simulation "

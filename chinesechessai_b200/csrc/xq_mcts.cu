@@ -369,8 +369,13 @@ __global__ void __launch_bounds__(256)
       if (v[i] > best) { best = v[i]; pick = i; }
   } else {
     const double inv_t = 1.0 / temperature;
+    // counts ** (1/T): exact shortcuts for the reference's two temperatures (trainer.py:166)
+    auto weight = [&](int c) -> double {
+      const double x = (double)c;
+      return inv_t == 1.0 ? x : (inv_t == 2.0 ? __dmul_rn(x, x) : pow(x, inv_t));
+    };
     double total = 0.0;
-    for (int i = 0; i < n; ++i) total = __dadd_rn(total, pow((double)v[i], inv_t));
+    for (int i = 0; i < n; ++i) total = __dadd_rn(total, weight(v[i]));
     if (!(total > 0.0)) {  // all-zero counts (n_sims <= 8): the reference divides by zero here
       pick = (int)(x[0] % (uint32_t)n);
     } else {
@@ -378,7 +383,7 @@ __global__ void __launch_bounds__(256)
       double cdf = 0.0;
       pick = n - 1;
       for (int i = 0; i < n; ++i) {  // searchsorted(cumsum(p), u, side="right")
-        cdf = __dadd_rn(cdf, __ddiv_rn(pow((double)v[i], inv_t), total));
+        cdf = __dadd_rn(cdf, __ddiv_rn(weight(v[i]), total));
         if (cdf > u) { pick = i; break; }
       }
     }
