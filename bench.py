@@ -219,6 +219,55 @@ def measure_tree_only(torch, dev, games, sims):
                                        f"(oracle/xq_oracle.c via ctypes threads), {dt:.1f} s"}}
 
 
+def measure_mcts_multi(torch, dist, dev, world, rank, games=16384, sims=50, plies_timed=2):
+    """cfg 4: 16,384 games per GPU x 50 sims/move on every rank, weights broadcast by NCCL once
+    (the per-iteration collective), no collective inside the game loop.  All ranks call this."""
+    from chinesechessai_b200 import dist as xd
+    from chinesechessai_b200.neural_network import ChessNet
+    from chinesechessai_b200.self_play import BatchedSelfPlay
+    torch.manual_seed(rank)                       # different weights until the broadcast
+    net = ChessNet().to(dev).eval()
+    xd.broadcast_weights(net, src=0)              # warm-up (NCCL communicator setup)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    sent = xd.broadcast_weights(net, src=0)
+    b.record()
+    torch.cuda.synchronize()
+    bcast_ms = a.elapsed_time(b)
+    sp = BatchedSelfPlay(net, games, sims, temperature=1.0, device=dev, net_dtype=torch.bfloat16,
+                         seed=0, first_game_id=rank * games)
+    sp.boards.playout(SEED, MCTS_OPENING_PLIES, first_game_id=rank * games)
+    sp.play(2, check_done=False)
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    p0 = sp.plies
+    a.record()
+    sp.play(plies_timed, check_done=False)
+    b.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    t = torch.tensor([a.elapsed_time(b), bcast_ms], dtype=torch.float64, device=dev)
+    played = sp.rec_played[p0:sp.plies].sum().to(torch.int64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(played, op=dist.ReduceOp.SUM)
+    ms, played = float(t[0]), int(played)
+    waves = (sims + 7) // 8
+    return {"metric": "MCTS sims/sec", "value": played * sims / (ms * 1e-3), "unit": "sims/s",
+            "n_gpus": world, "scaling": "weak",
+            "config": {"workload": f"cfg4: {games} games per GPU x {world} GPUs, {sims} sims/move, random-init "
+                                   f"ChessNet broadcast from rank 0 by NCCL, T=1.0, {MCTS_OPENING_PLIES} random "
+                                   "opening plies", "plies_timed": plies_timed,
+                       "nn_dtype": "bf16 (BN folded, fused cuDNN conv+bias+ReLU; reference: fp32)"},
+            "ms_per_ply": ms / plies_timed,
+            "unique_leaf_evals_per_s": played * waves / (ms * 1e-3),
+            "weight_broadcast": {"ms": float(t[1]), "bytes": int(sent)},
+            "roofline": {"bound": "tensor", "unit": "TFLOP/s",
+                         "achieved": played * waves / (ms * 1e-3) * FLOP_PER_LEAF_EVAL / 1e12 / world,
+                         "note": "per GPU"}}
+
+
 def measure_mcts(torch, dev, plies_timed=6, games=MCTS_GAMES, sims=MCTS_SIMS, label="cfg3"):
     """cfg 3: 4,096 concurrent self-play games, 15 sims/move (2 waves of 8+7), random-init ChessNet
     (torch.manual_seed(0)), temperature 1.0; games diversified by 4 random opening plies.
@@ -355,6 +404,9 @@ def run_ours(args):
     e2e_value = int(ep) / float(et)
     # device result of step 0 == host-path result of step 0 (same seed): cheap self-check
     clk = clocks.stop() if rank == 0 else None
+    mc_multi = None
+    if world > 1 and not args.fast:
+        mc_multi = measure_mcts_multi(torch, dist, dev, world, rank)
 
     if rank != 0:
         if world > 1:
@@ -400,6 +452,14 @@ def run_ours(args):
                     "unit": "warp-inst/s", "frac": kern_steps_per_s * WARP_INST_PER_STEP / issue_peak,
                     "warp_inst_per_board_step": WARP_INST_PER_STEP,
                     "source": "ncu smsp__inst_executed.sum / plies (profiles/), peak = 148 SM x 4 x f_SM"}
+    if mc_multi is not None:
+        try:
+            tfp = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"])
+        except Exception:
+            tfp = 1400.0
+        mc_multi["roofline"]["peak"] = tfp
+        mc_multi["roofline"]["frac"] = mc_multi["roofline"]["achieved"] / tfp
+        out["mcts_cfg4"] = mc_multi
     if world == 1 and not args.fast:
         v, ms, launches_per_step = measure_step_per_launch(torch, BoardBatch, n, first_id, 2, flush)
         out["step_per_launch"] = {

@@ -334,3 +334,23 @@ def test_encode_planes_and_priors(eng, xo):
         np.testing.assert_allclose(pri[i, :k], ref, rtol=2e-6, atol=1e-9)  # float32 softmax, B.5
         assert (pri[i, k:] == 0).all() and abs(pri[i].sum() - 1) < 1e-5
         assert int(np.argmax(pri[i, :k])) == int(np.argmax(ref))
+
+
+def test_position_history_equals_oracle(eng, xo):
+    """_get_position_hash / position_history (chess_env.py:338,497-504): the device history row
+    holds exactly the oracle's keys (same key function, mover's side byte), ply by ply."""
+    n = 64
+    bb = eng.BoardBatch(n)
+    bb.playout(SEED, 70, capture_bias=80)
+    hist, meta = bb.pos_hist_host(), bb.meta_host()
+    keys = bb.position_hash().cpu().numpy().view(np.uint64)
+    for g in range(n):
+        e = xo.Env()
+        e.playout(SEED, g, 70, 80)
+        want = np.array(e.position_history, dtype=np.uint64)
+        assert meta["hist_len"][g] == len(want)
+        assert np.array_equal(hist[g, :len(want)], want), g
+        assert keys[g] == np.uint64(e.position_hash()), g
+        assert meta["check_len"][g] == len(e.check_history)
+        bits = sum((1 << i) for i, v in enumerate(e.check_history[::-1][:32]) if v)
+        assert int(meta["check_bits"][g]) == bits, g
