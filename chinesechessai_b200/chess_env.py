@@ -148,6 +148,9 @@ class ChineseChess:
 
     # -- chess_env.py:253-406 ----------------------------------------------------------------
     def make_move(self, move: Move):
+        fr, fc, tr, tc = (int(x) for x in move)
+        if not (0 <= fr < BOARD_SIZE and 0 <= tr < BOARD_SIZE and 0 <= fc < BOARD_WIDTH and 0 <= tc < BOARD_WIDTH):
+            raise IndexError(f"move {move} is off the 10x9 board")  # numpy raises here too (>= size)
         dev = _Device1.get()
         self._upload(dev, with_hist=True)
         dev.move.fill_(pack_move(move))

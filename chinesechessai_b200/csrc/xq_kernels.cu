@@ -152,7 +152,11 @@ __global__ void __launch_bounds__(kThreads)
   if (g >= n_games) return;
   WarpSmem& w = slab[threadIdx.x >> 5];
   const int lane = (threadIdx.x & 31);
-  const int mv = move[g];
+  int mv = move[g];
+  if (mv >= XQ_POLICY) {  // not a (from,to) pair: refuse, flag, leave the game untouched
+    if (lane == 0) reinterpret_cast<uint8_t*>(meta + g)[6] |= XQ_F_OVERFLOW;
+    mv = -1;
+  }
   if (mv < 0) {  // frozen game
     if (lane == 0) {
       reward[g] = 0.0;
