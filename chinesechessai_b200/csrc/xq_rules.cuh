@@ -256,7 +256,8 @@ struct Probe {
   bool kocc, in_pal;
 };
 
-XQ_HD Probe make_probe(const WarpSmem& w, int K, int es, int geo, int from, int to, int mover) {
+template <class W>
+XQ_HD Probe make_probe(const W& w, int K, int es, int geo, int from, int to, int mover) {
   Probe p;
   p.K = K; p.es = es; p.geo = geo; p.from = from; p.to = to; p.mover = mover;
   p.kr = K / 9;
@@ -275,13 +276,15 @@ XQ_HD Probe make_probe(const WarpSmem& w, int K, int es, int geo, int from, int 
   return p;
 }
 
-XQ_HD int probe_piece(const WarpSmem& w, const Probe& p, int s) {
+template <class W>
+XQ_HD int probe_piece(const W& w, const Probe& p, int s) {
   return s == p.to ? p.mover : (s == p.from ? 0 : (int)w.sq[s]);
 }
 
 // dir 0..3 = rays (0,+1),(0,-1),(+1,0),(-1,0).  The mask is mirrored for the backward rays so
 // "ahead" is always toward higher bits.
-XQ_HD bool probe_ray(const WarpSmem& w, const Probe& p, int dir) {
+template <class W>
+XQ_HD bool probe_ray(const W& w, const Probe& p, int dir) {
   const bool horiz = dir < 2, fwd = (dir & 1) == 0;
   const int len = horiz ? 9 : 10;
   unsigned m = horiz ? p.rowm : p.colm;
@@ -305,7 +308,8 @@ XQ_HD bool probe_ray(const WarpSmem& w, const Probe& p, int dir) {
 }
 
 // i 0..3 = diagonal neighbour (a,b) in {-1,+1}^2.
-XQ_HD bool probe_diag(const WarpSmem& w, const Probe& p, int i, bool exotic) {
+template <class W>
+XQ_HD bool probe_diag(const W& w, const Probe& p, int i, bool exotic) {
   const int a = (i & 2) ? 1 : -1, b = (i & 1) ? 1 : -1;
   const int lr = p.kr + a, lc = p.kc + b;
   if (lr < 0 || lr > 9 || lc < 0 || lc > 8) return false;
@@ -322,7 +326,8 @@ XQ_HD bool probe_diag(const WarpSmem& w, const Probe& p, int i, bool exotic) {
 }
 
 // `exotic` enables the K/A/B diagonal probes (warp-uniform hint; always safe to pass true).
-XQ_HD bool attacked(const WarpSmem& w, int K, int es, int geo, int from, int to, int mover,
+template <class W>
+XQ_HD bool attacked(const W& w, int K, int es, int geo, int from, int to, int mover,
                     bool exotic, unsigned* colm_out) {
   const Probe p = make_probe(w, K, es, geo, from, to, mover);
   if (colm_out) *colm_out = p.colm;
@@ -340,13 +345,15 @@ XQ_HD bool attacked(const WarpSmem& w, int K, int es, int geo, int from, int to,
 
 // One of the 8 probes of attacked() on the staged board without an override (dir 4..7 = the
 // diagonals).  One lane per direction gives the warp-parallel check test of make_move (:317).
-XQ_HD bool attacked_dir(const WarpSmem& w, int K, int es, int geo, int dir) {
+template <class W>
+XQ_HD bool attacked_dir(const W& w, int K, int es, int geo, int dir) {
   const Probe p = make_probe(w, K, es, geo, -1, -1, 0);
   return dir < 4 ? probe_ray(w, p, dir) : probe_diag(w, p, dir - 4, true);
 }
 
 // _is_in_check(player) on the staged board (chess_env.py:506-548), single-lane form.
-XQ_HD bool in_check(const WarpSmem& w, const Game& g, int player) {
+template <class W>
+XQ_HD bool in_check(const W& w, const Game& g, int player) {
   const int K = player == 1 ? g.red_king : g.black_king;
   if (K < 0) return false;  // :517
   return attacked(w, K, -player, g.player, -1, -1, 0, true, nullptr);
@@ -356,7 +363,8 @@ XQ_HD bool in_check(const WarpSmem& w, const Game& g, int player) {
 // (geometry of the side to move) OR cached kings face each other (:466-495;
 // only the MOVING king's cache is refreshed, :448-451 — stale-cache quirk A.4).
 // from < 0 evaluates the position itself (no move).
-XQ_HD bool suicide(const WarpSmem& w, const Game& g, int from, int to, bool exotic) {
+template <class W>
+XQ_HD bool suicide(const W& w, const Game& g, int from, int to, bool exotic) {
   const int mover = from >= 0 ? (int)w.sq[from] : 0;
   int red = g.red_king, black = g.black_king;
   if (mover == KING) red = to;
@@ -406,7 +414,8 @@ struct FastCtx {
 XQ_HD int diag_index(int dr, int dc) { return (dr > 0 ? 2 : 0) + (dc > 0 ? 1 : 0); }
 
 // Sequential construction (host mirror); the kernel builds the same masks with ballots.
-XQ_HD FastCtx make_fast_ctx(const WarpSmem& w, const Game& g) {
+template <class W>
+XQ_HD FastCtx make_fast_ctx(const W& w, const Game& g) {
   FastCtx f{};
   const int player = g.player, es = -player;
   f.K = player == 1 ? g.red_king : g.black_king;
@@ -548,7 +557,8 @@ XQ_HD int leap_index(int player, int pt, int from, int d) {
   return ((player == 1 ? 0 : 8) + pt) * 360 + from * 4 + d;
 }
 
-XQ_HD Item gen_item(const WarpSmem& w, const uint32_t* __restrict__ leap, int player, int from, int d) {
+template <class W>
+XQ_HD Item gen_item(const W& w, const uint32_t* __restrict__ leap, int player, int from, int d) {
   Item it{from, 0, 0, -1, -1};
   const int p = w.sq[from];
   const int pt = p < 0 ? -p : p;
@@ -601,7 +611,8 @@ XQ_HD bool exotic_piece(int p, int s, int player, int own_king) {
   const int ap = p < 0 ? -p : p;
   return (p * player < 0) && ap <= BISHOP && xq_abs(s / 9 - own_king / 9) <= 3;
 }
-XQ_HD bool regular_king(const WarpSmem& w, int player, int own_king, int n_own_kings) {
+template <class W>
+XQ_HD bool regular_king(const W& w, int player, int own_king, int n_own_kings) {
   return n_own_kings == 1 && own_king >= 0 && w.sq[own_king] == player * KING;
 }
 

@@ -187,11 +187,15 @@ def test_fused_playout_vs_oracle(eng, xo, bias, first):
     assert int(res["plies"].sum()) == total
 
 
-@pytest.mark.parametrize("lpb", [8, 16, 32])
+@pytest.mark.parametrize("lpb", [1, 8, 16, 32])
 def test_fused_playout_tile_widths(eng, xo, lpb, monkeypatch):
-    """The fused kernel with 8, 16 or 32 lanes per board (XQ_PLAYOUT_LPB) is bit-exact, traces
-    included, for uniform and capture-biased games and ragged batch sizes."""
-    monkeypatch.setenv("XQ_PLAYOUT_LPB", str(lpb))
+    """The fused kernel with 1 (thread per board), 8, 16 or 32 lanes per board is bit-exact,
+    traces included, for uniform and capture-biased games and ragged batch sizes."""
+    if lpb == 1:
+        monkeypatch.setenv("XQ_PLAYOUT_MODE", "tpb")
+    else:
+        monkeypatch.setenv("XQ_PLAYOUT_MODE", "warp")
+        monkeypatch.setenv("XQ_PLAYOUT_LPB", str(lpb))
     for n, bias, first in ((4099, 0, 77), (1500, 200, 123456)):
         bb = eng.BoardBatch(n)
         res = eng.results_host(bb.playout(SEED + lpb, 70, first_game_id=first, capture_bias=bias))
