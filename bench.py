@@ -34,11 +34,14 @@ SEED = 0x5EED
 BYTES_PER_STEP_LAUNCH_MODE = 352
 #   fused playout: (board+meta in 128, out 128, result 40) / 70 plies + one 8-byte history append
 BYTES_PER_STEP_FUSED = (128 + 128 + 40) / 70.0 + 8.0
-# warp-instructions per board-step of playout_kernel<false>, from ncu smsp__inst_executed.sum /
-# plies of the same launch (profiles/r1/playout_v7_ncu_summary.txt); refreshed with every capture
-WARP_INST_PER_STEP = 2193.0
-# dram__bytes_read.sum + dram__bytes_write.sum of one playout launch in the same capture
-DRAM_TRAFFIC_PER_LAUNCH = 17.20e6 + 13.79e6
+# warp-instructions per board-step from ncu smsp__inst_executed.sum / plies of the same launch,
+# refreshed with every capture: the shipped thread-per-board kernel
+# (profiles/r1/playout_tpb_ncu_summary.txt) and the warp-per-board kernel
+# (profiles/r1/playout_v7_ncu_summary.txt)
+WARP_INST_PER_STEP = 1018.0
+WARP_INST_PER_STEP_WARP_MODE = 2193.0
+# dram__bytes_read.sum + dram__bytes_write.sum of one playout launch in the same captures
+DRAM_TRAFFIC_PER_LAUNCH = 46.64e6 + 4.35e6
 FLOP_PER_LEAF_EVAL = 263_209_216          # ChessNet.forward, SURVEY.md §8d
 MCTS_GAMES, MCTS_SIMS, MCTS_OPENING_PLIES = 4096, 15, 4
 METRIC = "board-steps/sec (legal movegen+step)"
@@ -435,10 +438,10 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak,
                      "traffic": DRAM_TRAFFIC_PER_LAUNCH if n == BOARDS else None,
-                     "traffic_note": "ncu dram bytes read+write per launch (profiles/r1/playout_v7_ncu_summary.txt); "
+                     "traffic_note": "ncu dram bytes read+write per launch (profiles/r1/playout_tpb_ncu_summary.txt); "
                                      "algorithmic bytes per launch = %.2e" % (BYTES_PER_STEP_FUSED * plies_per_launch),
                      "peak_source": peak_src,
-                     "kernel": "xq::playout_kernel<false>",
+                     "kernel": "xq::playout_tpb_kernel<false> (one thread per board)",
                      "bytes_per_board_step": BYTES_PER_STEP_FUSED,
                      "kernel_ms_per_launch": kern_ms / args.steps,
                      "note": "integer/latency-bound kernel: SM issue rate binds, not HBM "
@@ -461,6 +464,28 @@ def run_ours(args):
         mc_multi["roofline"]["frac"] = mc_multi["roofline"]["achieved"] / tfp
         out["mcts_cfg4"] = mc_multi
     if world == 1 and not args.fast:
+        # the warp-per-board mapping of the same fused kernel (what the API kernels and MCTS use)
+        os.environ["XQ_PLAYOUT_MODE"] = "warp"
+        one_step(3000)
+        torch.cuda.synchronize()
+        w_ms, w_plies = 0.0, 0
+        for k in range(3):
+            flush.zero_()
+            bb.reset()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            bb.playout(SEED + k, PLIES, first_game_id=first_id, results=results)
+            b.record()
+            torch.cuda.synchronize()
+            w_ms += a.elapsed_time(b)
+            w_plies += int(results.view(torch.int32)[:, 0].sum())
+        del os.environ["XQ_PLAYOUT_MODE"]
+        wv = w_plies / (w_ms * 1e-3)
+        out["warp_per_board"] = {"value": wv, "unit": UNIT, "kernel_ms_per_launch": w_ms / 3,
+                                 "kernel": "xq::playout_kernel<false,4,32>",
+                                 "issue": {"warp_inst_per_board_step": WARP_INST_PER_STEP_WARP_MODE,
+                                           "frac": wv * WARP_INST_PER_STEP_WARP_MODE / issue_peak}}
+        out["gpu_launches"] += 8
         v, ms, launches_per_step = measure_step_per_launch(torch, BoardBatch, n, first_id, 2, flush)
         out["step_per_launch"] = {
             "value": v, "unit": UNIT, "ms_per_step": ms, "launches_per_step": launches_per_step,

@@ -37,7 +37,7 @@ constexpr int kThreads = kWarpsPerCta * 32;
 #define XQ_DEFAULT_LPB 32
 #endif
 #ifndef XQ_DEFAULT_TPB
-#define XQ_DEFAULT_TPB false
+#define XQ_DEFAULT_TPB true
 #endif
 
 // ---------------------------------------------------------------------------
