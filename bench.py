@@ -464,6 +464,24 @@ def run_ours(args):
         mc_multi["roofline"]["frac"] = mc_multi["roofline"]["achieved"] / tfp
         out["mcts_cfg4"] = mc_multi
     if world == 1 and not args.fast:
+        # cfg 1 (the reference's own CPU-runnable case): 1,024 games from the initial position
+        b1 = BoardBatch(1024, device=dev, hist_cap=PLIES + 2)
+        r1 = torch.zeros((1024, 40), dtype=torch.uint8, device=dev)
+        b1.playout(SEED, PLIES, results=r1)
+        torch.cuda.synchronize()
+        c_ms, c_plies = 0.0, 0
+        for k in range(5):
+            b1.reset()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            b1.playout(SEED + k, PLIES, results=r1)
+            b.record()
+            torch.cuda.synchronize()
+            c_ms += a.elapsed_time(b)
+            c_plies += int(r1.view(torch.int32)[:, 0].sum())
+        out["cfg1"] = {"workload": "cfg1: 1,024 games x <= 70 plies (latency-bound: 8 CTAs on 148 SMs)",
+                       "value": c_plies / (c_ms * 1e-3), "unit": UNIT, "ms_per_batch": c_ms / 5}
+        out["gpu_launches"] += 11
         # the warp-per-board mapping of the same fused kernel (what the API kernels and MCTS use)
         os.environ["XQ_PLAYOUT_MODE"] = "warp"
         one_step(3000)
