@@ -591,7 +591,7 @@ int xq_playout(int8_t* board, xq_meta* meta, uint64_t* pos_hist, int hist_cap, u
     const int v = e ? atoi(e) : 4;
     return v >= 3 && v <= 5 ? v : 4;
   }();
-  const dim3 block(kThreads), grid((n_games + (kThreads / lpb) - 1) / (kThreads / lpb));
+  const dim3 block(kThreads);
   const cudaStream_t st = (cudaStream_t)stream;
   // mapping of the fused kernel: one thread per board ("tpb", default) or one tile of
   // XQ_PLAYOUT_LPB lanes per board ("warp")
@@ -628,7 +628,6 @@ int xq_playout(int8_t* board, xq_meta* meta, uint64_t* pos_hist, int hist_cap, u
     else if (minb == 5) XQ_LAUNCH_PLAYOUT(false, 5, LL); \
     else XQ_LAUNCH_PLAYOUT(false, 4, LL);              \
   } while (0)
-  (void)grid;
   if (trace) {
     if (lpb == 8) XQ_LAUNCH_PLAYOUT(true, 4, 8);
     else if (lpb == 16) XQ_LAUNCH_PLAYOUT(true, 4, 16);

@@ -344,7 +344,8 @@ XQ_HD bool attacked(const W& w, int K, int es, int geo, int from, int to, int mo
 }
 
 // One of the 8 probes of attacked() on the staged board without an override (dir 4..7 = the
-// diagonals).  One lane per direction gives the warp-parallel check test of make_move (:317).
+// diagonals); the probe round of movegen<L> runs these on 8 lanes.  Kept as a function for the
+// host mirror, which checks that the OR over the 8 directions equals attacked().
 template <class W>
 XQ_HD bool attacked_dir(const W& w, int K, int es, int geo, int dir) {
   const Probe p = make_probe(w, K, es, geo, -1, -1, 0);
@@ -456,7 +457,8 @@ XQ_HD FastCtx make_fast_ctx(const W& w, const Game& g) {
 }
 
 // Kings-facing verdict for a move of the own king to `to` (chess_env.py:448-451,:466-495);
-// p = probe built at the king's NEW square with the move applied.
+// p = probe built at the king's NEW square with the move applied (the probe round inlines the
+// same test; this form is what the host mirror exercises).
 XQ_HD bool king_move_facing(const Game& g, const Probe& p, int to) {
   const int ek = g.player == 1 ? g.black_king : g.red_king;
   if (ek < 0) return false;
