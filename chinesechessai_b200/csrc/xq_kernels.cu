@@ -321,7 +321,10 @@ __global__ void __launch_bounds__(kThreads, MINB)
 // ---------------------------------------------------------------------------
 // Fused random playout, one THREAD per board (xq_tpb.cuh).  Same inputs, outputs, digest and
 // traces as playout_kernel; per-thread board slabs live in dynamic shared memory.
-constexpr int kTpbThreads = 128;
+#ifndef XQ_TPB_THREADS
+#define XQ_TPB_THREADS 128
+#endif
+constexpr int kTpbThreads = XQ_TPB_THREADS;
 
 template <bool TRACE>
 __global__ void __launch_bounds__(kTpbThreads)
