@@ -487,6 +487,30 @@ __global__ void __launch_bounds__(kThreads)
   }
 }
 
+// out = relu(y + bias[c] + x), bf16, 8 elements (16 B) per thread, channels-last (c innermost).
+__global__ void __launch_bounds__(256)
+    bias_residual_relu_kernel(const uint4* __restrict__ y, const uint4* __restrict__ x,
+                              const __nv_bfloat16* __restrict__ bias, uint4* __restrict__ out,
+                              int64_t n_vec, int channels) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_vec) return;
+  const uint4 a = y[i], b = x[i];
+  const int c0 = (int)((i * 8) % channels);
+  const uint4 bb = *reinterpret_cast<const uint4*>(bias + c0);
+  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+  const __nv_bfloat162* pc = reinterpret_cast<const __nv_bfloat162*>(&bb);
+  uint4 r;
+  __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 fa = __bfloat1622float2(pa[k]), fb = __bfloat1622float2(pb[k]),
+                 fc = __bfloat1622float2(pc[k]);
+    pr[k] = __floats2bfloat162_rn(fmaxf(fa.x + fc.x + fb.x, 0.f), fmaxf(fa.y + fc.y + fb.y, 0.f));
+  }
+  out[i] = r;
+}
+
 }  // namespace xq
 
 // ===========================================================================
@@ -726,6 +750,18 @@ int xq_encode_planes(const int8_t* board, int board_stride, const int8_t* player
     encode_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(board, board_stride, player,
                                                                  player_stride, (float*)planes, n);
   return check_launch("xq_encode_planes");
+}
+
+int xq_bias_residual_relu_bf16(const void* y, const void* x, const void* bias, void* out,
+                               int64_t n_elems, int channels, void* stream) {
+  if (n_elems == 0) return 0;
+  XQ_REQUIRE(y && x && bias && out && n_elems > 0 && channels > 0 && n_elems % 8 == 0 &&
+                 channels % 8 == 0,
+             "null pointer or sizes not multiples of 8");
+  const int64_t n_vec = n_elems / 8;
+  bias_residual_relu_kernel<<<(unsigned)((n_vec + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const uint4*)y, (const uint4*)x, (const __nv_bfloat16*)bias, (uint4*)out, n_vec, channels);
+  return check_launch("xq_bias_residual_relu_bf16");
 }
 
 int xq_policy_priors(const void* logits, int logits_bf16, int logits_stride, const int16_t* moves,

@@ -13,7 +13,7 @@ import torch
 
 from . import _lib
 from ._lib import BOARD_STRIDE, MAX_MOVES, check
-from .engine import _ptr, _stream, encode_planes, policy_priors
+from .engine import _ptr, _stream, bias_residual_relu, encode_planes, policy_priors
 
 WAVE = 8  # self_play.py:101
 
@@ -68,6 +68,7 @@ class _FoldedNet(torch.nn.Module):
         self.value_fc1, self.value_fc2 = n.value_fc1, n.value_fc2
         self.to(dtype=dtype, memory_format=torch.channels_last)
         self.fused = False
+        self.own_epilogue = dtype == torch.bfloat16
         if next(self.parameters()).is_cuda:
             try:  # probe the fused cuDNN entry points once
                 x = torch.zeros((2, 15, 10, 9), dtype=dtype, device=fc.weight.device).contiguous(
@@ -88,8 +89,12 @@ class _FoldedNet(torch.nn.Module):
             x = self._cr(self.stem, x)
             for c1, c2 in self.blocks:
                 y = self._cr(c1, x)
-                x = torch.cudnn_convolution_add_relu(y, c2.weight, x, 1.0, c2.bias, c2.stride,
-                                                     c2.padding, c2.dilation, c2.groups)
+                if self.own_epilogue:  # plain conv + one fused HBM pass (our kernel)
+                    z = torch.nn.functional.conv2d(y, c2.weight, None, c2.stride, c2.padding)
+                    x = bias_residual_relu(z, x, c2.bias)
+                else:
+                    x = torch.cudnn_convolution_add_relu(y, c2.weight, x, 1.0, c2.bias, c2.stride,
+                                                         c2.padding, c2.dilation, c2.groups)
             p = self._cr(self.policy_conv, x)
             v = self._cr(self.value_conv, x)
         else:

@@ -175,6 +175,14 @@ int xq_policy_priors(const void *logits, int logits_bf16, int logits_stride,
                      const int16_t *moves, int moves_stride, const int16_t *n_moves,
                      float *priors, int n, void *stream);
 
+/* Residual-block epilogue of ChessNet (neural_network.py:181-187) for the bf16 channels-last
+ * inference copy: out = relu(y + bias[c] + x) in one pass (y = conv2 output without bias,
+ * x = block input, c = innermost index mod channels).  cuDNN's fused conv+add+ReLU runs the same
+ * convolution at half the tensor-pipe utilisation (profiles/r1/nn_kernels_tensor_pipe_cfg3.csv);
+ * plain conv + this HBM-bound pass is faster.  n_elems must be a multiple of 8, channels too. */
+int xq_bias_residual_relu_bf16(const void *y, const void *x, const void *bias, void *out,
+                               int64_t n_elems, int channels, void *stream);
+
 /* ---- MCTS: self_play.py:19-175 ------------------------------------------- */
 /* One flat node pool per game ("tree"), caller-allocated device memory of
  * xq_mcts_tree_bytes(num_simulations) bytes per game (16-byte aligned; every

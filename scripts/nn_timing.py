@@ -28,6 +28,10 @@ with torch.no_grad():
             agree = (out[0][:, :8100].float().argmax(1) == ref[0].argmax(1)).float().mean().item()
             t = timeit(lambda: f(xb))
             print(f"n={n} {dt} fused={f.fused}: {t:.3f} ms  -> {n*263.2e6/t/1e9:.0f} TFLOP/s  max|dlogit|={err_p:.3f} max|dv|={err_v:.4f} argmax agree={agree:.3f}")
+            if dt == torch.bfloat16:
+                f.own_epilogue = False
+                t = timeit(lambda: f(xb))
+                print(f"   cudnn conv+add+relu for the residual: {t:.3f} ms")
             f.fused = False
             t = timeit(lambda: f(xb))
             print(f"   unfused: {t:.3f} ms")

@@ -157,3 +157,47 @@ def test_opponent_mode_runs_and_records_red_only(mods):
     assert len(out) == 12
     for gd, winner, reason in out:
         assert len(gd) == 6 and all((b != 0).sum() >= 30 for b, _, _ in gd)
+
+
+def test_bias_residual_relu_kernel(mods):
+    """xq_bias_residual_relu_bf16 == relu(y + bias + x) computed in fp32 and rounded once."""
+    import torch
+    eng, _ = mods
+    torch.manual_seed(3)
+    for n in (1, 37, 4096):
+        y = torch.randn(n, 128, 10, 9, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last)
+        x = torch.randn(n, 128, 10, 9, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last)
+        b = torch.randn(128, device="cuda").bfloat16()
+        out = eng.bias_residual_relu(y, x, b)
+        ref = torch.relu(y.float() + b.float()[None, :, None, None] + x.float()).bfloat16()
+        assert out.is_contiguous(memory_format=torch.channels_last) and torch.equal(out, ref)
+
+
+def test_folded_net_matches_module(mods):
+    """The bf16 inference copy (BN folded, fused cuDNN calls, padded head, own residual epilogue)
+    against the fp32 module: same arg-max move, logits within bf16 noise (numerics of the network
+    are outside the bit-parity gate)."""
+    import torch
+    eng, mcts = mods
+    from chinesechessai_b200.neural_network import ChessNet
+    torch.manual_seed(0)
+    net = ChessNet().cuda().eval()
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(); m.running_var.uniform_(0.5, 2.0)
+    bb = eng.BoardBatch(256)
+    bb.playout(5, 12)
+    planes = eng.encode_planes(bb.board, bb.meta[:, 0].view(torch.int8))
+    with torch.no_grad():
+        ref_p, ref_v = net(planes)
+        f = mcts._FoldedNet(net, torch.bfloat16)
+        assert f.fused and f.own_epilogue
+        p, v = f(planes.bfloat16().contiguous(memory_format=torch.channels_last))
+    assert p.shape == (256, 8192) and float(p[:, 8100:].abs().max()) == 0.0
+    assert float((p[:, :8100].float() - ref_p).abs().max()) < 0.15
+    assert float((v.float() - ref_v).abs().max()) < 0.05
+    mv, nm = bb.legal_moves()
+    pri_ref = eng.policy_priors(ref_p.contiguous(), mv, nm)
+    pri = eng.policy_priors(p, mv, nm)
+    assert float((pri - pri_ref).abs().max()) < 0.02
+    assert float((pri.argmax(1) == pri_ref.argmax(1)).float().mean()) > 0.95
