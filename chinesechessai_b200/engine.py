@@ -201,14 +201,16 @@ def policy_priors(logits: torch.Tensor, moves: torch.Tensor, n_moves: torch.Tens
     return out
 
 
-def bias_residual_relu(y: torch.Tensor, x: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+def bias_residual_relu(y: torch.Tensor, x: torch.Tensor, bias: torch.Tensor,
+                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """relu(y + bias[c] + x) for bf16 channels-last activations (ResidualBlock epilogue,
     neural_network.py:181-187), one HBM pass in the CUDA kernel xq_bias_residual_relu_bf16."""
     lib = _lib.load()
     assert y.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and bias.dtype == torch.bfloat16
     assert y.shape == x.shape and y.is_contiguous(memory_format=torch.channels_last)
     assert x.is_contiguous(memory_format=torch.channels_last) and bias.is_contiguous()
-    out = torch.empty_like(y)  # preserves channels_last
+    if out is None:
+        out = torch.empty_like(y)  # preserves channels_last
     with torch.cuda.device(y.device):
         check(lib.xq_bias_residual_relu_bf16(_ptr(y), _ptr(x), _ptr(bias), _ptr(out), y.numel(),
                                              y.shape[1], _stream()))
