@@ -26,7 +26,9 @@ struct ThreadBoard {
   uint16_t cols[10];
   uint8_t own[kTpbOwnCap];
   uint16_t mv[kTpbMoveCap];  // from<<8 | to
-  uint32_t pad;
+  uint8_t n_kings[2];  // red / black king pieces on the board (constant while a game runs:
+                       // capturing a king ends it, chess_env.py:291-299)
+  uint16_t pad;
 };
 static_assert(sizeof(ThreadBoard) == 428 && (sizeof(ThreadBoard) / 4) % 2 == 1, "ThreadBoard stride");
 
@@ -48,6 +50,14 @@ __device__ __forceinline__ void tpb_load(ThreadBoard& w, const int8_t* __restric
     for (int r = 0; r < 10; ++r) m |= (w.sq[r * 9 + c] != 0 ? 1u : 0u) << r;
     w.cols[c] = (uint16_t)m;
   }
+  int nr = 0, nb = 0;
+#pragma unroll 1
+  for (int s = 0; s < XQ_NSQ; ++s) {
+    nr += w.sq[s] == KING;
+    nb += w.sq[s] == -KING;
+  }
+  w.n_kings[0] = (uint8_t)(nr > 255 ? 255 : nr);
+  w.n_kings[1] = (uint8_t)(nb > 255 ? 255 : nb);
 }
 
 __device__ __forceinline__ uint64_t tpb_board_key(const ThreadBoard& w) {
@@ -67,23 +77,38 @@ __device__ __forceinline__ int tpb_movegen(ThreadBoard& w, Game& g, const uint32
                                            bool* checked) {
   const int player = g.player;
   const int ownK = player == 1 ? g.red_king : g.black_king;
-  int n_own = 0, n_kings = 0;
+  // :82-87 scan order, four squares per word: sign/zero tests on packed bytes give the own
+  // pieces (any code of the mover's sign) and the enemy K/A/B (|code| <= 3) of exotic_piece()
+  int n_own = 0;
   bool ex = false;
+  const int okr = (ownK < 0 ? 0 : ownK) / 9;
+  const int lo = (okr - 3 < 0 ? 0 : okr - 3) * 9, hi = (okr + 4 > 10 ? 10 : okr + 4) * 9;
+  const uint32_t* sw = reinterpret_cast<const uint32_t*>(w.sq);
 #pragma unroll 1
-  for (int s = 0; s < XQ_NSQ; ++s) {  // :82-87 scan order
-    const int p = w.sq[s];
-    if (p * player > 0) {
+  for (int i = 0; i < 23; ++i) {
+    uint32_t x = sw[i];
+    if (i == 22) x &= 0xFFFFu;  // squares 88, 89; the row padding is not part of the board
+    const uint32_t l7 = x & 0x7F7F7F7Fu;
+    const uint32_t neg = x & 0x80808080u;
+    const uint32_t pos = (l7 + 0x7F7F7F7Fu) & ~x & 0x80808080u;
+    uint32_t own = player == 1 ? pos : neg;
+    const uint32_t kab = player == 1 ? ((l7 + 0x03030303u) & neg) : (pos & ~(l7 + 0x7C7C7C7Cu));
+    if (kab) {  // a word spans 4 squares, the row window >= 36: testing both ends is exact
+      const int a = 4 * i + ((__ffs(kab) - 1) >> 3), b = 4 * i + ((31 - __clz(kab)) >> 3);
+      ex |= (a >= lo && a < hi) || (b >= lo && b < hi);
+    }
+    while (own) {
+      const int s = 4 * i + ((__ffs(own) - 1) >> 3);
+      own &= own - 1;
       if (n_own < kTpbOwnCap) w.own[n_own] = (uint8_t)s;
       ++n_own;
     }
-    n_kings += p == player * KING;
-    ex |= exotic_piece(p, s, player, ownK < 0 ? 0 : ownK);
   }
   if (n_own > kTpbOwnCap) {
     n_own = kTpbOwnCap;
     g.flags |= XQ_F_OVERFLOW;
   }
-  const bool exotic = ex || !regular_king(w, player, ownK, n_kings);
+  const bool exotic = ex || !regular_king(w, player, ownK, (int)w.n_kings[player == 1 ? 0 : 1]);
 
   // candidates in generator order
   int nc = 0;
