@@ -9,7 +9,7 @@
 #include <cuda_bf16.h>
 
 #include "xq_rules.cuh"
-#include "xq_tpb.cuh"
+#include "xq_pair.cuh"
 
 namespace xq {
 
@@ -325,6 +325,9 @@ __global__ void __launch_bounds__(kThreads, MINB)
 #define XQ_TPB_THREADS 128
 #endif
 constexpr int kTpbThreads = XQ_TPB_THREADS;
+#ifndef XQ_PAIR_MINB
+#define XQ_PAIR_MINB 7
+#endif
 
 template <bool TRACE>
 __global__ void __launch_bounds__(kTpbThreads)
@@ -400,6 +403,120 @@ __global__ void __launch_bounds__(kTpbThreads)
   for (int i = 0; i < XQ_BOARD_STRIDE / 4; ++i)
     reinterpret_cast<uint32_t*>(board + (size_t)g * XQ_BOARD_STRIDE)[i] =
         reinterpret_cast<const uint32_t*>(w.sq)[i];
+  {  // store_meta without the tile-lane guard
+    uint4 a, b;
+    a.x = (uint32_t)(G.player & 0xff) | ((uint32_t)(G.winner & 0xff) << 8) |
+          ((uint32_t)(G.reason & 0xff) << 16) | ((uint32_t)(G.done & 0xff) << 24);
+    a.y = (uint32_t)(G.red_king & 0xff) | ((uint32_t)(G.black_king & 0xff) << 8) |
+          ((uint32_t)(G.flags & 0xff) << 16);
+    a.z = (uint32_t)G.move_count;
+    a.w = (uint32_t)G.no_capture;
+    b.x = (uint32_t)G.cchecks;
+    b.y = (uint32_t)G.hist_len;
+    b.z = G.check_bits;
+    b.w = (uint32_t)G.check_len;
+    reinterpret_cast<uint4*>(meta + g)[0] = a;
+    reinterpret_cast<uint4*>(meta + g)[1] = b;
+  }
+  xq_playout_result r;
+  r.plies = ply;
+  r.winner = G.winner;
+  r.reason = G.reason;
+  r.max_legal = max_legal;
+  r.reward_sum = rsum;
+  r.digest = digest;
+  r.final_hash = fkey;
+  results[g] = r;
+}
+
+// ---------------------------------------------------------------------------
+// Fused random playout, TWO lanes per board (xq_pair.cuh): 64 boards per 128-thread CTA.
+constexpr int kPairThreads = 128;
+constexpr int kPairMinBlocks = XQ_PAIR_MINB;
+
+template <bool TRACE>
+__global__ void __launch_bounds__(kPairThreads, kPairMinBlocks)
+    playout_pair_kernel(int8_t* __restrict__ board, xq_meta* __restrict__ meta,
+                       uint64_t* __restrict__ pos_hist, int hist_cap, uint64_t seed,
+                       uint32_t first_game_id, int max_plies, int capture_bias,
+                       xq_playout_result* __restrict__ results, int16_t* __restrict__ tr_moves,
+                       int16_t* __restrict__ tr_n, int16_t* __restrict__ tr_pick,
+                       double* __restrict__ tr_reward, uint8_t* __restrict__ tr_flags,
+                       int8_t* __restrict__ tr_boards, int n_games) {
+  extern __shared__ __align__(16) unsigned char tpb_smem[];
+  const int sub = Pair::sub();
+  const int g = blockIdx.x * (kPairThreads / 2) + (int)(threadIdx.x >> 1);
+  if (g >= n_games) return;  // both lanes of the pair
+  ThreadBoard& w = reinterpret_cast<ThreadBoard*>(tpb_smem)[threadIdx.x >> 1];
+  pair_load(w, board + (size_t)g * XQ_BOARD_STRIDE);
+  Game G = load_meta(meta + g);
+  G.bkey = pair_board_key(w);
+  uint64_t* hist = pos_hist + (size_t)g * hist_cap;
+  const uint32_t gid = first_game_id + (uint32_t)g;
+
+  uint64_t digest = 0, word_a = 0;
+  double rsum = 0.0;
+  int max_legal = 0, ply = 0;
+  bool pending = false, kingcap = false;
+  TpbStep o;
+  o.done = 0;
+  for (;;) {
+    bool checking = false;
+    int n0 = 0;
+    const int n = kingcap ? -1 : pair_movegen(w, G, g_leap, pending, checking, n0);
+    if (pending) {
+      tpb_finish<true>(w, G, o, n, checking, hist);
+      pending = false;
+      rsum = __dadd_rn(rsum, o.reward);
+      const uint64_t word_c = (uint64_t)(o.done & 1) | ((uint64_t)(G.winner + 2) << 8) |
+                              ((uint64_t)G.reason << 16) | ((uint64_t)(o.is_int & 1) << 24);
+      const uint64_t t = word_a * 0x9E3779B97F4A7C15ULL + dbits(o.reward) * 0xC2B2AE3D27D4EB4FULL +
+                         word_c * 0x165667B19E3779F9ULL + o.key_next * 0x27D4EB2F165667C5ULL;
+      digest = mix64(digest ^ t);
+      if (TRACE && sub == 0) {
+        const size_t tt = (size_t)g * max_plies + ply;
+        if (tr_reward) tr_reward[tt] = o.reward;
+        if (tr_flags)
+          tr_flags[tt] = (uint8_t)((o.done & 1) | ((o.is_int & 1) << 1) | (((G.winner + 1) & 3) << 2) |
+                                   ((G.reason & 15) << 4));
+        if (tr_boards)
+          for (int sq = 0; sq < XQ_NSQ; ++sq) tr_boards[tt * XQ_NSQ + sq] = w.sq[sq];
+      }
+      ++ply;
+      if (o.done) break;
+    }
+    if (ply >= max_plies || n == 0) break;  // self_play.py:203,207
+    max_legal = max(max_legal, n);
+    const int idx = pair_pick(w, n, n0, seed, gid, (uint32_t)ply, capture_bias);
+    const unsigned cm = pair_move_at(w, idx, n0);
+    const int mv = tpb_packed(cm);
+    // each lane sums its own part of the list at the moves' global positions
+    const int my_n = sub ? n - n0 : n0, my_off = sub ? n0 : 0;
+    const int my_base = sub ? kTpbMoveCap - 1 : 0, my_dir = sub ? -1 : 1;
+    unsigned lsum = 0;
+#pragma unroll 1
+    for (int i = 0; i < my_n; ++i)
+      lsum += (unsigned)(tpb_packed(w.mv[my_base + my_dir * i]) + 1) * (unsigned)(2 * (my_off + i) + 1);
+    lsum += Pair::other(lsum);
+    word_a = (uint64_t)lsum | ((uint64_t)n << 32) | ((uint64_t)mv << 40) | ((uint64_t)(ply + 1) << 54);
+    if (TRACE) {
+      const size_t tt = (size_t)g * max_plies + ply;
+      if (tr_moves)
+        for (int i = 0; i < my_n; ++i)
+          tr_moves[tt * XQ_MAX_MOVES + my_off + i] = (int16_t)tpb_packed(w.mv[my_base + my_dir * i]);
+      if (tr_n && sub == 0) tr_n[tt] = (int16_t)n;
+      if (tr_pick && sub == 0) tr_pick[tt] = (int16_t)mv;
+    }
+    o = tpb_apply<true>(w, G, (int)(cm >> 8), (int)(cm & 0x7fu), hist, hist_cap);
+    kingcap = o.done != 0;
+    pending = true;
+  }
+  const uint64_t fkey = G.bkey ^ side_key(G.player);
+#pragma unroll
+  for (int i = 0; i < XQ_BOARD_STRIDE / 8; ++i)
+    reinterpret_cast<uint32_t*>(board + (size_t)g * XQ_BOARD_STRIDE)[2 * i + sub] =
+        reinterpret_cast<const uint32_t*>(w.sq)[2 * i + sub];
+  if (sub != 0) return;
   {  // store_meta without the tile-lane guard
     uint4 a, b;
     a.x = (uint32_t)(G.player & 0xff) | ((uint32_t)(G.winner & 0xff) << 8) |
@@ -624,6 +741,20 @@ int xq_playout(int8_t* board, xq_meta* meta, uint64_t* pos_hist, int hist_cap, u
   // XQ_PLAYOUT_LPB lanes per board ("warp")
   const char* mode_env = getenv("XQ_PLAYOUT_MODE");
   const bool tpb = mode_env ? strcmp(mode_env, "warp") != 0 : XQ_DEFAULT_TPB;
+  if (mode_env && strcmp(mode_env, "pair") == 0) {
+    const int bpc = kPairThreads / 2;
+    const size_t smem = sizeof(ThreadBoard) * bpc;
+    const dim3 pgrid((n_games + bpc - 1) / bpc);
+    if (trace)
+      playout_pair_kernel<true><<<pgrid, kPairThreads, smem, st>>>(
+          board, meta, pos_hist, hist_cap, seed, first_game_id, max_plies, capture_bias, results,
+          tr_moves, tr_n, tr_pick, tr_reward, tr_flags, tr_boards, n_games);
+    else
+      playout_pair_kernel<false><<<pgrid, kPairThreads, smem, st>>>(
+          board, meta, pos_hist, hist_cap, seed, first_game_id, max_plies, capture_bias, results,
+          nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, n_games);
+    return check_launch("xq_playout");
+  }
   if (tpb) {
     const size_t smem = sizeof(ThreadBoard) * kTpbThreads;
     const dim3 tgrid((n_games + kTpbThreads - 1) / kTpbThreads);

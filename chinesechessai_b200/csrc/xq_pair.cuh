@@ -1,0 +1,241 @@
+// xq_pair.cuh — two lanes per board for the fused playout.
+//
+// The thread-per-board engine (xq_tpb.cuh) issues the fewest instructions per ply, but at the
+// cfg 2 size (65,536 boards = 2,048 warps = 3.5 warps per scheduler) it is bound by dependent-
+// issue latency: issue-active 52 % (profiles/).  Here two ADJACENT lanes share one board slab and
+// split the divisible work of a ply — candidate generation and legality by halves of the own-
+// piece list, the probe round (check test + king moves) by alternating items, the history scan
+// and the digest sum by halves — so the same batch runs as twice as many warps with about half
+// the dependent chain per lane.  Bookkeeping (make_move's scalar part, the pick) is replicated
+// in both lanes' registers; lane 0 writes the slab.  Lane 0's moves sit at w.mv[0..n0) going up,
+// lane 1's at w.mv[127], w.mv[126], ... going down: the legal list in the reference's order is
+// lane 0's part followed by lane 1's, and is never merged physically (pair_move_at).
+// Outputs are bit-identical to the other two engines (same tests, same digests).
+#pragma once
+
+#include "xq_tpb.cuh"
+
+#if defined(__CUDACC__)
+namespace xq {
+
+// i-th legal move of the pair's list (n0 = lane 0's count)
+__device__ __forceinline__ unsigned pair_move_at(const ThreadBoard& w, int i, int n0) {
+  return w.mv[i < n0 ? i : kTpbMoveCap - 1 - (i - n0)];
+}
+
+__device__ __forceinline__ void pair_load(ThreadBoard& w, const int8_t* __restrict__ row) {
+  const int sub = Pair::sub();
+#pragma unroll
+  for (int i = 0; i < XQ_BOARD_STRIDE / 8; ++i)
+    reinterpret_cast<uint32_t*>(w.sq)[2 * i + sub] = reinterpret_cast<const uint32_t*>(row)[2 * i + sub];
+  Pair::sync();
+  if (sub == 0) {
+#pragma unroll 1
+    for (int r = 0; r < 10; ++r) {
+      unsigned m = 0;
+      for (int c = 0; c < 9; ++c) m |= (w.sq[r * 9 + c] != 0 ? 1u : 0u) << c;
+      w.rows[r] = (uint16_t)m;
+    }
+  } else {
+#pragma unroll 1
+    for (int c = 0; c < 9; ++c) {
+      unsigned m = 0;
+      for (int r = 0; r < 10; ++r) m |= (w.sq[r * 9 + c] != 0 ? 1u : 0u) << r;
+      w.cols[c] = (uint16_t)m;
+    }
+    int nr = 0, nb = 0;
+#pragma unroll 1
+    for (int s = 0; s < XQ_NSQ; ++s) {
+      nr += w.sq[s] == KING;
+      nb += w.sq[s] == -KING;
+    }
+    w.n_kings[0] = (uint8_t)(nr > 255 ? 255 : nr);
+    w.n_kings[1] = (uint8_t)(nb > 255 ? 255 : nb);
+  }
+  Pair::sync();
+}
+
+__device__ __forceinline__ uint64_t pair_board_key(const ThreadBoard& w) {
+  uint64_t h = 0;
+#pragma unroll 1
+  for (int s = Pair::sub(); s < XQ_NSQ; s += 2) {
+    const int p = w.sq[s];
+    if (p != 0) h ^= piece_key(p, s);
+  }
+  return h ^ (uint64_t)Pair::other((unsigned long long)h);
+}
+
+// get_legal_moves (chess_env.py:76-121) by a pair.  Returns the total count; n_first = lane 0's
+// share.  *checked as in tpb_movegen.
+__device__ __forceinline__ int pair_movegen(ThreadBoard& w, Game& g, const uint32_t* __restrict__ leap,
+                                            bool want_check, bool& checked, int& n_first) {
+  const int sub = Pair::sub();
+  const int player = g.player;
+  const int ownK = player == 1 ? g.red_king : g.black_king;
+  // own pieces in scan order (:82-87) and the exotic_piece() hint, as in tpb_movegen; both lanes
+  // run the scan (it is short), lane 0 stores the list
+  int n_own = 0;
+  bool ex = false;
+  {
+    const int okr = (ownK < 0 ? 0 : ownK) / 9;
+    const int lo = (okr - 3 < 0 ? 0 : okr - 3) * 9, hi = (okr + 4 > 10 ? 10 : okr + 4) * 9;
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(w.sq);
+#pragma unroll 1
+    for (int i = 0; i < 23; ++i) {
+      uint32_t x = sw[i];
+      if (i == 22) x &= 0xFFFFu;
+      const uint32_t l7 = x & 0x7F7F7F7Fu;
+      const uint32_t neg = x & 0x80808080u;
+      const uint32_t pos = (l7 + 0x7F7F7F7Fu) & ~x & 0x80808080u;
+      uint32_t own = player == 1 ? pos : neg;
+      const uint32_t kab = player == 1 ? ((l7 + 0x03030303u) & neg) : (pos & ~(l7 + 0x7C7C7C7Cu));
+      if (kab) {
+        const int a = 4 * i + ((__ffs(kab) - 1) >> 3), b = 4 * i + ((31 - __clz(kab)) >> 3);
+        ex |= (a >= lo && a < hi) || (b >= lo && b < hi);
+      }
+      while (own) {
+        const int s = 4 * i + ((__ffs(own) - 1) >> 3);
+        own &= own - 1;
+        if (sub == 0 && n_own < kTpbOwnCap) w.own[n_own] = (uint8_t)s;
+        ++n_own;
+      }
+    }
+  }
+  if (n_own > kTpbOwnCap) {
+    n_own = kTpbOwnCap;
+    g.flags |= XQ_F_OVERFLOW;
+  }
+  const bool exotic = ex || !regular_king(w, player, ownK, (int)w.n_kings[player == 1 ? 0 : 1]);
+  Pair::sync();
+
+  // candidates: lane 0 takes the first half of the pieces, lane 1 the rest
+  const int dir = sub ? -1 : 1, base = sub ? kTpbMoveCap - 1 : 0;
+  const int half = (n_own >> 1) * 4;
+  const int t_end = sub ? n_own * 4 : half;
+  int nc = 0;
+#pragma unroll 1
+  for (int t = sub ? half : 0; t < t_end; ++t) {
+    const Item it = gen_item(w, leap, player, w.own[t >> 2], t & 3);
+    const int cnt = it.empties + (it.e1 >= 0) + (it.e2 >= 0);
+    if (nc + cnt > kTpbMoveCap) {
+      g.flags |= XQ_F_OVERFLOW;
+      break;
+    }
+    const unsigned fs = (unsigned)it.from << 8;
+    uint16_t* out = &w.mv[base + dir * nc];
+    unsigned v = fs | (unsigned)it.from;  // from + k*delta stays inside the low byte
+#pragma unroll 1
+    for (int k = it.empties; k > 0; --k, out += dir) *out = (uint16_t)(v += (unsigned)it.delta);
+    if (it.e1 >= 0) { *out = (uint16_t)(fs | (unsigned)it.e1); out += dir; }
+    if (it.e2 >= 0) *out = (uint16_t)(fs | (unsigned)it.e2);
+    nc += cnt;
+  }
+  // the two parts share the array: more than kTpbMoveCap candidates in total is an overflow
+  // (every entry is still some valid candidate, so nothing downstream can go out of range)
+  int nc_other = Pair::other(nc);
+  if (nc + nc_other > kTpbMoveCap) {
+    g.flags |= XQ_F_OVERFLOW;
+    if (sub == 0) nc = kTpbMoveCap - nc_other;
+    else nc_other = kTpbMoveCap - nc;
+  }
+
+  // legality (:118)
+  int n = 0, kfirst = 0, kcount = 0;
+  if (!exotic) {
+    // bitmask test, marking only: the candidate list as a whole is cut in two equal runs, so the
+    // lanes' trip counts match however the pieces fell (a rook's 17 candidates vs a pawn's 1)
+    const FastCtx f = make_fast_ctx(w, g);
+    const int nc0 = sub ? nc_other : nc, total = nc + nc_other, cut = (total + 1) >> 1;
+    const int j_end = sub ? total : cut;
+    Pair::sync();
+#pragma unroll 1
+    for (int j = sub ? cut : 0; j < j_end; ++j) {
+      const int a = j < nc0 ? j : kTpbMoveCap - 1 - (j - nc0);
+      const unsigned c = w.mv[a];
+      const int from = (int)(c >> 8), to = (int)(c & 0x7fu);
+      if (from != ownK && suicide_fast(f, from, to)) w.mv[a] = (uint16_t)(c | kCandIllegal);
+    }
+    Pair::sync();
+    // each lane compacts its own part in place; the king's candidates (contiguous, one lane)
+    // stay, flagged, for the probe round
+#pragma unroll 1
+    for (int j = 0; j < nc; ++j) {
+      const unsigned c = w.mv[base + dir * j];
+      if ((int)(c >> 8) == ownK) {
+        if (kcount == 0) kfirst = n;
+        ++kcount;
+        w.mv[base + dir * n++] = (uint16_t)(c | kCandIllegal);
+      } else if (!(c & kCandIllegal)) {
+        w.mv[base + dir * n++] = (uint16_t)c;
+      }
+    }
+  } else {
+#pragma unroll 1
+    for (int j = 0; j < nc; ++j) {
+      const unsigned c = w.mv[base + dir * j];
+      if (!suicide(w, g, (int)(c >> 8), (int)(c & 0x7fu), true)) w.mv[base + dir * n++] = (uint16_t)c;
+    }
+  }
+
+  // probe round: item 0 = make_move's check test (:317), items 1.. = the king's candidates
+  // (:448-451); the lanes take alternating items
+  const int kc_other = Pair::other(kcount), kf_other = Pair::other(kfirst);
+  const int k_total = kcount + kc_other;
+  const bool mine = kcount > 0;
+  const int k_base = (mine ? sub : 1 - sub) ? kTpbMoveCap - 1 : 0, k_dir = (mine ? sub : 1 - sub) ? -1 : 1;
+  const int k_first = mine ? kfirst : kf_other;
+  Pair::sync();
+  unsigned bad = 0;
+#pragma unroll 1
+  for (int q = sub; q <= k_total; q += 2) {
+    if (q == 0) {
+      if (want_check && ownK >= 0 && attacked(w, ownK, -player, -player, -1, -1, 0, true, nullptr)) bad |= 1u;
+    } else {
+      const unsigned c = w.mv[k_base + k_dir * (k_first + q - 1)] & 0x7fffu;
+      if (suicide(w, g, (int)(c >> 8), (int)(c & 0x7fu), false)) bad |= 1u << q;
+    }
+  }
+  bad |= Pair::other(bad);
+  checked = (bad & 1u) != 0;
+  if (mine) {
+    int removed = 0;
+#pragma unroll 1
+    for (int k = 0; k < kcount; ++k) {
+      const unsigned c = w.mv[base + dir * (kfirst + k)] & 0x7fffu;
+      if (!((bad >> (k + 1)) & 1u)) w.mv[base + dir * (kfirst + k - removed)] = (uint16_t)c;
+      else ++removed;
+    }
+    if (removed) {  // close the gap behind the king's block
+#pragma unroll 1
+      for (int j = kfirst + kcount; j < n; ++j) w.mv[base + dir * (j - removed)] = w.mv[base + dir * j];
+      n -= removed;
+    }
+  }
+  const int n_other = Pair::other(n);
+  g.flags |= Pair::other(g.flags);
+  n_first = sub ? n_other : n;
+  Pair::sync();
+  return n + n_other;
+}
+
+// shared pick rule: index into the pair's list; both lanes compute the same value
+__device__ __forceinline__ int pair_pick(const ThreadBoard& w, int n, int n0, uint64_t seed,
+                                         uint32_t game_id, uint32_t ply, int capture_bias) {
+  uint32_t x[4];
+  philox4x32(game_id, ply, 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), x);
+  if (capture_bias > 0 && (int)(x[1] & 0xFFu) < capture_bias) {
+    int ncap = 0;
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) ncap += w.sq[pair_move_at(w, i, n0) & 0x7fu] != 0;
+    if (ncap > 0) {
+      int k = (int)(x[0] % (uint32_t)ncap);
+#pragma unroll 1
+      for (int i = 0; i < n; ++i)
+        if (w.sq[pair_move_at(w, i, n0) & 0x7fu] != 0 && k-- == 0) return i;
+    }
+  }
+  return (int)(x[0] % (uint32_t)n);
+}
+
+}  // namespace xq
+#endif  // __CUDACC__

@@ -32,6 +32,16 @@ struct ThreadBoard {
 };
 static_assert(sizeof(ThreadBoard) == 428 && (sizeof(ThreadBoard) / 4) % 2 == 1, "ThreadBoard stride");
 
+// Two adjacent lanes that share one board (xq_pair.cuh).  Collectives use the pair's own mask,
+// so the pairs of a warp may diverge freely.
+struct Pair {
+  static __device__ __forceinline__ int sub() { return (int)(threadIdx.x & 1u); }
+  static __device__ __forceinline__ unsigned mask() { return 3u << (threadIdx.x & 30u); }
+  static __device__ __forceinline__ void sync() { __syncwarp(mask()); }
+  template <class T>
+  static __device__ __forceinline__ T other(T v) { return __shfl_xor_sync(mask(), v, 1); }
+};
+
 __device__ __forceinline__ int tpb_packed(unsigned c) { return (int)(c >> 8) * 90 + (int)(c & 0x7fu); }
 
 __device__ __forceinline__ void tpb_load(ThreadBoard& w, const int8_t* __restrict__ row) {
@@ -121,10 +131,13 @@ __device__ __forceinline__ int tpb_movegen(ThreadBoard& w, Game& g, const uint32
       break;
     }
     const unsigned fs = (unsigned)it.from << 8;
+    uint16_t* out = &w.mv[nc];
+    unsigned v = fs | (unsigned)it.from;  // from + k*delta stays inside the low byte
 #pragma unroll 1
-    for (int k = 1; k <= it.empties; ++k) w.mv[nc++] = (uint16_t)(fs | (unsigned)(it.from + k * it.delta));
-    if (it.e1 >= 0) w.mv[nc++] = (uint16_t)(fs | (unsigned)it.e1);
-    if (it.e2 >= 0) w.mv[nc++] = (uint16_t)(fs | (unsigned)it.e2);
+    for (int k = it.empties; k > 0; --k) *out++ = (uint16_t)(v += (unsigned)it.delta);
+    if (it.e1 >= 0) *out++ = (uint16_t)(fs | (unsigned)it.e1);
+    if (it.e2 >= 0) *out = (uint16_t)(fs | (unsigned)it.e2);
+    nc += cnt;
   }
 
   // legality (:118), compacting in place
@@ -176,13 +189,17 @@ struct TpbStep {
 };
 
 // make_move part 1 (chess_env.py:253-314,:338,:348-349), sequential twin of step_apply<L>.
+// PAIR: both lanes of a pair keep the game registers; lane 0 alone writes the shared slab and
+// the history.
+template <bool PAIR = false>
 __device__ __forceinline__ TpbStep tpb_apply(ThreadBoard& w, Game& g, int from, int to,
                                              uint64_t* __restrict__ hist, int hist_cap) {
   TpbStep o;
   const int captured = w.sq[to], moving = w.sq[from];
-  w.sq[to] = (int8_t)moving;
-  w.sq[from] = 0;
-  {
+  if (PAIR) Pair::sync();  // both lanes have read the old squares
+  if (!PAIR || Pair::sub() == 0) {
+    w.sq[to] = (int8_t)moving;
+    w.sq[from] = 0;
     const int fr = from / 9, fc = from - fr * 9, tr = to / 9, tc = to - tr * 9;
     w.rows[fr] &= ~(1u << fc);
     w.cols[fc] &= ~(1u << fr);
@@ -194,6 +211,7 @@ __device__ __forceinline__ TpbStep tpb_apply(ThreadBoard& w, Game& g, int from, 
       w.cols[tc] &= ~(1u << tr);
     }
   }
+  if (PAIR) Pair::sync();
   if (moving != 0) g.bkey ^= piece_key(moving, from) ^ piece_key(moving, to);
   if (captured != 0) g.bkey ^= piece_key(captured, to);
   if (moving == KING) g.red_king = to;
@@ -220,7 +238,7 @@ __device__ __forceinline__ TpbStep tpb_apply(ThreadBoard& w, Game& g, int from, 
     if (acap == ADVISOR || acap == BISHOP) o.reward = xq_dadd(o.reward, 3.0);
   }
   if (g.hist_len < hist_cap) {
-    hist[g.hist_len] = g.bkey ^ side_key(g.player);
+    if (!PAIR || Pair::sub() == 0) hist[g.hist_len] = g.bkey ^ side_key(g.player);
     g.hist_len += 1;
   } else {
     g.flags |= XQ_F_OVERFLOW;
@@ -232,6 +250,7 @@ __device__ __forceinline__ TpbStep tpb_apply(ThreadBoard& w, Game& g, int from, 
 }
 
 // make_move part 2 (:318-345, :352-404), sequential twin of step_finish<L>.
+template <bool PAIR = false>
 __device__ __forceinline__ void tpb_finish(const ThreadBoard& w, Game& g, TpbStep& o, int n_legal,
                                            bool checking, const uint64_t* __restrict__ hist) {
   const int mover = -g.player;
@@ -260,7 +279,8 @@ __device__ __forceinline__ void tpb_finish(const ThreadBoard& w, Game& g, TpbSte
   } else {
     int cnt = 0;
 #pragma unroll 1
-    for (int i = 0; i < g.hist_len; ++i) cnt += hist[i] == o.key_next;
+    for (int i = PAIR ? Pair::sub() : 0; i < g.hist_len; i += PAIR ? 2 : 1) cnt += hist[i] == o.key_next;
+    if (PAIR) cnt += Pair::other(cnt);
     if (cnt >= 3) {
       o.done = 1; o.reward = 0.0; o.is_int = 1;
       g.winner = 0;
