@@ -36,8 +36,8 @@ constexpr int kThreads = kWarpsPerCta * 32;
 #ifndef XQ_DEFAULT_LPB
 #define XQ_DEFAULT_LPB 32
 #endif
-#ifndef XQ_DEFAULT_TPB
-#define XQ_DEFAULT_TPB true
+#ifndef XQ_PAIR_MIN_GAMES
+#define XQ_PAIR_MIN_GAMES 40960
 #endif
 
 // ---------------------------------------------------------------------------
@@ -737,11 +737,15 @@ int xq_playout(int8_t* board, xq_meta* meta, uint64_t* pos_hist, int hist_cap, u
   }();
   const dim3 block(kThreads);
   const cudaStream_t st = (cudaStream_t)stream;
-  // mapping of the fused kernel: one thread per board ("tpb", default) or one tile of
-  // XQ_PLAYOUT_LPB lanes per board ("warp")
+  // Mapping of the fused kernel, measured on B200 (profiles/r1/playout_mappings_by_batch.txt):
+  // a tile of XQ_PLAYOUT_LPB lanes per board ("warp") is fastest while the batch is too small
+  // to fill the SMs with independent boards, two lanes per board ("pair") from ~40 k boards
+  // up; one thread per board ("tpb") issues the fewest instructions but is latency-bound.
+  // XQ_PLAYOUT_MODE overrides the choice (all three give identical results).
   const char* mode_env = getenv("XQ_PLAYOUT_MODE");
-  const bool tpb = mode_env ? strcmp(mode_env, "warp") != 0 : XQ_DEFAULT_TPB;
-  if (mode_env && strcmp(mode_env, "pair") == 0) {
+  const bool pair = mode_env ? strcmp(mode_env, "pair") == 0 : n_games >= XQ_PAIR_MIN_GAMES;
+  const bool tpb = mode_env != nullptr && strcmp(mode_env, "tpb") == 0;
+  if (pair) {
     const int bpc = kPairThreads / 2;
     const size_t smem = sizeof(ThreadBoard) * bpc;
     const dim3 pgrid((n_games + bpc - 1) / bpc);

@@ -187,12 +187,14 @@ def test_fused_playout_vs_oracle(eng, xo, bias, first):
     assert int(res["plies"].sum()) == total
 
 
-@pytest.mark.parametrize("lpb", [1, 8, 16, 32])
+@pytest.mark.parametrize("lpb", [1, 2, 8, 16, 32])
 def test_fused_playout_tile_widths(eng, xo, lpb, monkeypatch):
-    """The fused kernel with 1 (thread per board), 8, 16 or 32 lanes per board is bit-exact,
-    traces included, for uniform and capture-biased games and ragged batch sizes."""
+    """The fused kernel with 1 (thread per board), 2 (pair), 8, 16 or 32 lanes per board is
+    bit-exact, traces included, for uniform and capture-biased games and ragged batch sizes."""
     if lpb == 1:
         monkeypatch.setenv("XQ_PLAYOUT_MODE", "tpb")
+    elif lpb == 2:
+        monkeypatch.setenv("XQ_PLAYOUT_MODE", "pair")
     else:
         monkeypatch.setenv("XQ_PLAYOUT_MODE", "warp")
         monkeypatch.setenv("XQ_PLAYOUT_LPB", str(lpb))
@@ -215,6 +217,34 @@ def test_fused_playout_tile_widths(eng, xo, lpb, monkeypatch):
         assert np.array_equal(flags[g, :r.plies], t["flags"][:r.plies])
         for q in range(r.plies):
             assert np.array_equal(moves[g, q, :n_arr[g, q]], t["moves"][q, :t["n"][q]])
+
+
+@pytest.mark.parametrize("mode", ["warp", "tpb", "pair"])
+def test_fused_playout_from_arbitrary_positions(eng, xo, golden, mode, monkeypatch):
+    """Playouts that START from the poked golden positions (stale or missing king caches, several
+    kings, enemy K/A/B next to the king, mid-game counters): every mapping of the fused kernel
+    takes its irregular-board paths here and must still equal the oracle, game by game."""
+    monkeypatch.setenv("XQ_PLAYOUT_MODE", mode)
+    P = golden.positions
+    n = len(P["player"])
+    for plies, bias in ((1, 0), (9, 160)):
+        bb = _positions_batch(eng, P)
+        res = eng.results_host(bb.playout(SEED, plies, first_game_id=1000, capture_bias=bias))
+        m = bb.meta_host()
+        boards = bb.boards_host()
+        for i in range(n):
+            L = int(P["ck_len"][i])
+            ck = [bool((int(P["ck_bits"][i]) >> (L - 1 - j)) & 1) for j in range(L)]
+            e = xo.Env().load(P["board"][i].reshape(10, 9), int(P["player"][i]), int(P["mc"][i]), None,
+                              xo.Env._pos(int(P["red"][i])), xo.Env._pos(int(P["black"][i])),
+                              int(P["ncap"][i]), int(P["cc"][i]), ck)
+            r = e.playout(SEED, 1000 + i, plies, bias)
+            for f in ("plies", "winner", "reason", "max_legal", "digest", "final_hash"):
+                assert res[f][i] == getattr(r, f), (mode, plies, i, f)
+            assert np.float64(res["reward_sum"][i]).view(np.uint64) == np.float64(r.reward_sum).view(np.uint64)
+            assert np.array_equal(boards[i], e.board.reshape(90)), (mode, i)
+            assert (m["red_king"][i], m["black_king"][i]) == (e.s.red_king, e.s.black_king), (mode, i)
+            assert m["consecutive_checks"][i] == e.s.consecutive_checks and m["no_capture"][i] == e.s.no_capture
 
 
 def test_step_per_launch_equals_fused(eng):
