@@ -186,13 +186,33 @@ __device__ __forceinline__ int pair_movegen(ThreadBoard& w, Game& g, const uint3
   const int k_first = mine ? kfirst : kf_other;
   Pair::sync();
   unsigned bad = 0;
+  {
+    // one attacked() call site serves both kinds of item: the check test looks at the king where
+    // it stands under the previous mover's geometry with the K/A/B probes on (:317, A.3); a king
+    // move looks at the target square with the move applied, then at the two kings' file
+    const int ek = player == 1 ? g.black_king : g.red_king;
 #pragma unroll 1
-  for (int q = sub; q <= k_total; q += 2) {
-    if (q == 0) {
-      if (want_check && ownK >= 0 && attacked(w, ownK, -player, -player, -1, -1, 0, true, nullptr)) bad |= 1u;
-    } else {
-      const unsigned c = w.mv[k_base + k_dir * (k_first + q - 1)] & 0x7fffu;
-      if (suicide(w, g, (int)(c >> 8), (int)(c & 0x7fu), false)) bad |= 1u << q;
+    for (int q = sub; q <= k_total; q += 2) {
+      const bool is_check = q == 0;
+      if (is_check && !(want_check && ownK >= 0)) continue;
+      int from = -1, to = -1;
+      if (!is_check) {
+        const unsigned c = w.mv[k_base + k_dir * (k_first + q - 1)] & 0x7fffu;
+        from = (int)(c >> 8);
+        to = (int)(c & 0x7fu);
+      }
+      const int K = is_check ? ownK : to;
+      unsigned colm = 0;
+      bool hit = attacked(w, K, -player, is_check ? -player : player, from, to,
+                          is_check ? 0 : player * KING, is_check, &colm);
+      if (!is_check && ek >= 0) {  // kings facing with the moved king (:448-451,:466-495)
+        const int kr = K / 9, kc = K - kr * 9, er = ek / 9, ec = ek - er * 9;
+        if (kc == ec) {
+          const int lo = xq_min(kr, er), hi = xq_max(kr, er);
+          hit |= (colm & (((1u << hi) - 1u) & ~((2u << lo) - 1u))) == 0;
+        }
+      }
+      if (hit) bad |= 1u << q;
     }
   }
   bad |= Pair::other(bad);
