@@ -463,7 +463,8 @@ __global__ void __launch_bounds__(kPairThreads, kPairMinBlocks)
   for (;;) {
     bool checking = false;
     int n0 = 0;
-    const int n = kingcap ? -1 : pair_movegen(w, G, g_leap, pending, checking, n0);
+    unsigned lsum = 0;
+    const int n = kingcap ? -1 : pair_movegen(w, G, g_leap, pending, checking, n0, lsum);
     if (pending) {
       tpb_finish<true>(w, G, o, n, checking, hist);
       pending = false;
@@ -490,20 +491,15 @@ __global__ void __launch_bounds__(kPairThreads, kPairMinBlocks)
     const int idx = pair_pick(w, n, n0, seed, gid, (uint32_t)ply, capture_bias);
     const unsigned cm = pair_move_at(w, idx, n0);
     const int mv = tpb_packed(cm);
-    // each lane sums its own part of the list at the moves' global positions
-    const int my_n = sub ? n - n0 : n0, my_off = sub ? n0 : 0;
-    const int my_base = sub ? kTpbMoveCap - 1 : 0, my_dir = sub ? -1 : 1;
-    unsigned lsum = 0;
-#pragma unroll 1
-    for (int i = 0; i < my_n; ++i)
-      lsum += (unsigned)(tpb_packed(w.mv[my_base + my_dir * i]) + 1) * (unsigned)(2 * (my_off + i) + 1);
-    lsum += Pair::other(lsum);
     word_a = (uint64_t)lsum | ((uint64_t)n << 32) | ((uint64_t)mv << 40) | ((uint64_t)(ply + 1) << 54);
     if (TRACE) {
       const size_t tt = (size_t)g * max_plies + ply;
-      if (tr_moves)
+      if (tr_moves) {  // each lane writes its own part of the list
+        const int my_n = sub ? n - n0 : n0, my_off = sub ? n0 : 0;
+        const int my_base = sub ? kTpbMoveCap - 1 : 0, my_dir = sub ? -1 : 1;
         for (int i = 0; i < my_n; ++i)
           tr_moves[tt * XQ_MAX_MOVES + my_off + i] = (int16_t)tpb_packed(w.mv[my_base + my_dir * i]);
+      }
       if (tr_n && sub == 0) tr_n[tt] = (int16_t)n;
       if (tr_pick && sub == 0) tr_pick[tt] = (int16_t)mv;
     }

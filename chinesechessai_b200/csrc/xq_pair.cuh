@@ -66,66 +66,86 @@ __device__ __forceinline__ uint64_t pair_board_key(const ThreadBoard& w) {
 }
 
 // get_legal_moves (chess_env.py:76-121) by a pair.  Returns the total count; n_first = lane 0's
-// share.  *checked as in tpb_movegen.
+// share, checked as in tpb_movegen, lsum = sum over the list of (move_i + 1) * (2 i + 1) mod 2^32
+// (the digest's list term, folded into the compaction loop).
 __device__ __forceinline__ int pair_movegen(ThreadBoard& w, Game& g, const uint32_t* __restrict__ leap,
-                                            bool want_check, bool& checked, int& n_first) {
+                                            bool want_check, bool& checked, int& n_first,
+                                            unsigned& lsum) {
+  constexpr int kHalfOwn = kTpbOwnCap / 2;
   const int sub = Pair::sub();
   const int player = g.player;
   const int ownK = player == 1 ? g.red_king : g.black_king;
-  // own pieces in scan order (:82-87) and the exotic_piece() hint, as in tpb_movegen; both lanes
-  // run the scan (it is short), lane 0 stores the list
-  int n_own = 0;
-  bool ex = false;
+  // Own pieces in scan order (:82-87) and the exotic_piece() hint, four squares per word as in
+  // tpb_movegen; lane 0 scans words 0..11 into own[0..), lane 1 words 12..22 into own[16..).
+  int my_own = 0;
+  int ex = 0;
   {
     const int okr = (ownK < 0 ? 0 : ownK) / 9;
     const int lo = (okr - 3 < 0 ? 0 : okr - 3) * 9, hi = (okr + 4 > 10 ? 10 : okr + 4) * 9;
     const uint32_t* sw = reinterpret_cast<const uint32_t*>(w.sq);
+    const int i_end = sub ? 23 : 12;
 #pragma unroll 1
-    for (int i = 0; i < 23; ++i) {
+    for (int i = sub ? 12 : 0; i < i_end; ++i) {
       uint32_t x = sw[i];
-      if (i == 22) x &= 0xFFFFu;
+      if (i == 22) x &= 0xFFFFu;  // squares 88, 89; the row padding is not part of the board
       const uint32_t l7 = x & 0x7F7F7F7Fu;
       const uint32_t neg = x & 0x80808080u;
       const uint32_t pos = (l7 + 0x7F7F7F7Fu) & ~x & 0x80808080u;
       uint32_t own = player == 1 ? pos : neg;
       const uint32_t kab = player == 1 ? ((l7 + 0x03030303u) & neg) : (pos & ~(l7 + 0x7C7C7C7Cu));
-      if (kab) {
+      if (kab) {  // a word spans 4 squares, the row window >= 36: testing both ends is exact
         const int a = 4 * i + ((__ffs(kab) - 1) >> 3), b = 4 * i + ((31 - __clz(kab)) >> 3);
-        ex |= (a >= lo && a < hi) || (b >= lo && b < hi);
+        ex |= ((a >= lo && a < hi) || (b >= lo && b < hi)) ? 1 : 0;
       }
       while (own) {
         const int s = 4 * i + ((__ffs(own) - 1) >> 3);
         own &= own - 1;
-        if (sub == 0 && n_own < kTpbOwnCap) w.own[n_own] = (uint8_t)s;
-        ++n_own;
+        if (my_own < kHalfOwn) w.own[sub * kHalfOwn + my_own] = (uint8_t)s;
+        ++my_own;
       }
     }
   }
-  if (n_own > kTpbOwnCap) {
-    n_own = kTpbOwnCap;
+  if (my_own > kHalfOwn) {
+    my_own = kHalfOwn;
     g.flags |= XQ_F_OVERFLOW;
   }
-  const bool exotic = ex || !regular_king(w, player, ownK, (int)w.n_kings[player == 1 ? 0 : 1]);
+  ex |= Pair::other(ex);
+  const int other_own = Pair::other(my_own);
+  const int own0 = sub ? other_own : my_own, n_own = my_own + other_own;
+  const bool exotic = ex != 0 || !regular_king(w, player, ownK, (int)w.n_kings[player == 1 ? 0 : 1]);
   Pair::sync();
 
-  // candidates: lane 0 takes the first half of the pieces, lane 1 the rest
+  // candidates: lane 0 takes the first half of the pieces, lane 1 the rest; the own king's
+  // block of candidates (contiguous) is noted on the way
   const int dir = sub ? -1 : 1, base = sub ? kTpbMoveCap - 1 : 0;
   const int half = (n_own >> 1) * 4;
   const int t_end = sub ? n_own * 4 : half;
-  int nc = 0;
+  int nc = 0, kfirst = 0, kcount = 0;
 #pragma unroll 1
   for (int t = sub ? half : 0; t < t_end; ++t) {
-    const Item it = gen_item(w, leap, player, w.own[t >> 2], t & 3);
+    const int pi = t >> 2;
+    const Item it = gen_item(w, leap, player, w.own[pi < own0 ? pi : kHalfOwn + (pi - own0)], t & 3);
     const int cnt = it.empties + (it.e1 >= 0) + (it.e2 >= 0);
     if (nc + cnt > kTpbMoveCap) {
       g.flags |= XQ_F_OVERFLOW;
       break;
     }
+    if (it.from == ownK) {
+      if (kcount == 0) kfirst = nc;
+      kcount += cnt;
+    }
     const unsigned fs = (unsigned)it.from << 8;
     uint16_t* out = &w.mv[base + dir * nc];
     unsigned v = fs | (unsigned)it.from;  // from + k*delta stays inside the low byte
 #pragma unroll 1
-    for (int k = it.empties; k > 0; --k, out += dir) *out = (uint16_t)(v += (unsigned)it.delta);
+    for (int k = it.empties; k > 0; k -= 2) {
+      *out = (uint16_t)(v += (unsigned)it.delta);
+      out += dir;
+      if (k > 1) {
+        *out = (uint16_t)(v += (unsigned)it.delta);
+        out += dir;
+      }
+    }
     if (it.e1 >= 0) { *out = (uint16_t)(fs | (unsigned)it.e1); out += dir; }
     if (it.e2 >= 0) *out = (uint16_t)(fs | (unsigned)it.e2);
     nc += cnt;
@@ -138,54 +158,41 @@ __device__ __forceinline__ int pair_movegen(ThreadBoard& w, Game& g, const uint3
     if (sub == 0) nc = kTpbMoveCap - nc_other;
     else nc_other = kTpbMoveCap - nc;
   }
-
-  // legality (:118)
-  int n = 0, kfirst = 0, kcount = 0;
+  const int nc0 = sub ? nc_other : nc, total = nc + nc_other;
+  // the candidate list as a whole: entry j of lane 0's run, then of lane 1's
+#define XQ_PAIR_ADDR(j) ((j) < nc0 ? (j) : kTpbMoveCap - 1 - ((j) - nc0))
+  int k_total = 0, k_start = 0;  // the king's block in that numbering (regular boards)
   if (!exotic) {
-    // bitmask test, marking only: the candidate list as a whole is cut in two equal runs, so the
-    // lanes' trip counts match however the pieces fell (a rook's 17 candidates vs a pawn's 1)
+    const int kinfo = kcount > 0 ? (kcount << 8) | (sub ? nc0 + kfirst : kfirst) : 0;
+    const int kboth = kinfo | Pair::other(kinfo);  // at most one lane holds the king
+    k_total = kboth >> 8;
+    k_start = kboth & 0xff;
+  }
+  Pair::sync();
+
+  // legality (:118): verdicts are MARKED in place (kCandIllegal), nothing moves yet
+  if (!exotic) {
+    // non-king moves, bitmask test: the list is cut in two equal runs, so the lanes' trip counts
+    // match however the pieces fell (a rook's 17 candidates vs a pawn's 1)
     const FastCtx f = make_fast_ctx(w, g);
-    const int nc0 = sub ? nc_other : nc, total = nc + nc_other, cut = (total + 1) >> 1;
-    const int j_end = sub ? total : cut;
-    Pair::sync();
+    const int cut = (total + 1) >> 1, j_end = sub ? total : cut;
 #pragma unroll 1
     for (int j = sub ? cut : 0; j < j_end; ++j) {
-      const int a = j < nc0 ? j : kTpbMoveCap - 1 - (j - nc0);
+      const int a = XQ_PAIR_ADDR(j);
       const unsigned c = w.mv[a];
       const int from = (int)(c >> 8), to = (int)(c & 0x7fu);
       if (from != ownK && suicide_fast(f, from, to)) w.mv[a] = (uint16_t)(c | kCandIllegal);
     }
-    Pair::sync();
-    // each lane compacts its own part in place; the king's candidates (contiguous, one lane)
-    // stay, flagged, for the probe round
-#pragma unroll 1
-    for (int j = 0; j < nc; ++j) {
-      const unsigned c = w.mv[base + dir * j];
-      if ((int)(c >> 8) == ownK) {
-        if (kcount == 0) kfirst = n;
-        ++kcount;
-        w.mv[base + dir * n++] = (uint16_t)(c | kCandIllegal);
-      } else if (!(c & kCandIllegal)) {
-        w.mv[base + dir * n++] = (uint16_t)c;
-      }
-    }
   } else {
 #pragma unroll 1
-    for (int j = 0; j < nc; ++j) {
+    for (int j = 0; j < nc; ++j) {  // irregular boards: the general test, king moves included
       const unsigned c = w.mv[base + dir * j];
-      if (!suicide(w, g, (int)(c >> 8), (int)(c & 0x7fu), true)) w.mv[base + dir * n++] = (uint16_t)c;
+      if (suicide(w, g, (int)(c >> 8), (int)(c & 0x7fu), true)) w.mv[base + dir * j] = (uint16_t)(c | kCandIllegal);
     }
   }
-
   // probe round: item 0 = make_move's check test (:317), items 1.. = the king's candidates
   // (:448-451); the lanes take alternating items
-  const int kc_other = Pair::other(kcount), kf_other = Pair::other(kfirst);
-  const int k_total = kcount + kc_other;
-  const bool mine = kcount > 0;
-  const int k_base = (mine ? sub : 1 - sub) ? kTpbMoveCap - 1 : 0, k_dir = (mine ? sub : 1 - sub) ? -1 : 1;
-  const int k_first = mine ? kfirst : kf_other;
-  Pair::sync();
-  unsigned bad = 0;
+  int chk = 0;
   {
     // one attacked() call site serves both kinds of item: the check test looks at the king where
     // it stands under the previous mover's geometry with the K/A/B probes on (:317, A.3); a king
@@ -195,9 +202,10 @@ __device__ __forceinline__ int pair_movegen(ThreadBoard& w, Game& g, const uint3
     for (int q = sub; q <= k_total; q += 2) {
       const bool is_check = q == 0;
       if (is_check && !(want_check && ownK >= 0)) continue;
-      int from = -1, to = -1;
+      int from = -1, to = -1, a = 0;
       if (!is_check) {
-        const unsigned c = w.mv[k_base + k_dir * (k_first + q - 1)] & 0x7fffu;
+        a = XQ_PAIR_ADDR(k_start + q - 1);
+        const unsigned c = w.mv[a];
         from = (int)(c >> 8);
         to = (int)(c & 0x7fu);
       }
@@ -212,28 +220,34 @@ __device__ __forceinline__ int pair_movegen(ThreadBoard& w, Game& g, const uint3
           hit |= (colm & (((1u << hi) - 1u) & ~((2u << lo) - 1u))) == 0;
         }
       }
-      if (hit) bad |= 1u << q;
+      if (is_check) chk = hit ? 1 : 0;
+      else if (hit) w.mv[a] = (uint16_t)(((unsigned)from << 8) | (unsigned)to | kCandIllegal);
     }
   }
-  bad |= Pair::other(bad);
-  checked = (bad & 1u) != 0;
-  if (mine) {
-    int removed = 0;
+#undef XQ_PAIR_ADDR
+  chk |= Pair::other(chk);  // also orders the marks before the compaction reads
+  checked = chk != 0;
+  Pair::sync();
+
+  // each lane compacts its own run in place and sums its part of the digest term
+  int n = 0;
+  unsigned s0 = 0, s1 = 0;
 #pragma unroll 1
-    for (int k = 0; k < kcount; ++k) {
-      const unsigned c = w.mv[base + dir * (kfirst + k)] & 0x7fffu;
-      if (!((bad >> (k + 1)) & 1u)) w.mv[base + dir * (kfirst + k - removed)] = (uint16_t)c;
-      else ++removed;
-    }
-    if (removed) {  // close the gap behind the king's block
-#pragma unroll 1
-      for (int j = kfirst + kcount; j < n; ++j) w.mv[base + dir * (j - removed)] = w.mv[base + dir * j];
-      n -= removed;
+  for (int j = 0; j < nc; ++j) {
+    const unsigned c = w.mv[base + dir * j];
+    if (!(c & kCandIllegal)) {
+      w.mv[base + dir * n] = (uint16_t)c;
+      const unsigned p1 = (unsigned)tpb_packed(c) + 1u;
+      s0 += p1;
+      s1 += p1 * (unsigned)(2 * n + 1);
+      ++n;
     }
   }
   const int n_other = Pair::other(n);
-  g.flags |= Pair::other(g.flags);
   n_first = sub ? n_other : n;
+  const unsigned part = sub ? s1 + 2u * (unsigned)n_first * s0 : s1;  // lane 1's i = n0 + local i
+  lsum = part + Pair::other(part);
+  g.flags |= Pair::other(g.flags);
   Pair::sync();
   return n + n_other;
 }
