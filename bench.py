@@ -38,7 +38,8 @@ BYTES_PER_STEP_FUSED = (128 + 128 + 40) / 70.0 + 8.0
 # refreshed with every capture: the shipped thread-per-board kernel
 # (profiles/r1/playout_tpb_ncu_summary.txt) and the warp-per-board kernel
 # (profiles/r1/playout_v7_ncu_summary.txt)
-WARP_INST_PER_STEP = 1018.0
+WARP_INST_PER_STEP = 1171.0
+WARP_INST_PER_STEP_TPB_MODE = 1018.0
 WARP_INST_PER_STEP_WARP_MODE = 2193.0
 # dram__bytes_read.sum + dram__bytes_write.sum of one playout launch in the same captures
 DRAM_TRAFFIC_PER_LAUNCH = 46.64e6 + 4.35e6
@@ -441,7 +442,8 @@ def run_ours(args):
                      "traffic_note": "ncu dram bytes read+write per launch (profiles/r1/playout_tpb_ncu_summary.txt); "
                                      "algorithmic bytes per launch = %.2e" % (BYTES_PER_STEP_FUSED * plies_per_launch),
                      "peak_source": peak_src,
-                     "kernel": "xq::playout_tpb_kernel<false> (one thread per board)",
+                     "kernel": "xq::playout_pair_kernel<false> (two lanes per board)" if n >= 40960
+                               else "xq::playout_kernel<false,4,32> (one warp per board)",
                      "bytes_per_board_step": BYTES_PER_STEP_FUSED,
                      "kernel_ms_per_launch": kern_ms / args.steps,
                      "note": "integer/latency-bound kernel: SM issue rate binds, not HBM "
@@ -451,9 +453,10 @@ def run_ours(args):
     sm_hz = (clk.get("sm_mhz") or 1965.0) * 1e6 if clk else 1965.0e6
     issue_peak = 148 * 4 * sm_hz
     kern_steps_per_s = plies_per_launch / kern_s
-    out["issue"] = {"achieved": kern_steps_per_s * WARP_INST_PER_STEP, "peak": issue_peak,
-                    "unit": "warp-inst/s", "frac": kern_steps_per_s * WARP_INST_PER_STEP / issue_peak,
-                    "warp_inst_per_board_step": WARP_INST_PER_STEP,
+    wips_main = WARP_INST_PER_STEP if n >= 40960 else WARP_INST_PER_STEP_WARP_MODE
+    out["issue"] = {"achieved": kern_steps_per_s * wips_main, "peak": issue_peak,
+                    "unit": "warp-inst/s", "frac": kern_steps_per_s * wips_main / issue_peak,
+                    "warp_inst_per_board_step": wips_main,
                     "source": "ncu smsp__inst_executed.sum / plies (profiles/), peak = 148 SM x 4 x f_SM"}
     if mc_multi is not None:
         try:
@@ -482,28 +485,32 @@ def run_ours(args):
         out["cfg1"] = {"workload": "cfg1: 1,024 games x <= 70 plies (latency-bound: 8 CTAs on 148 SMs)",
                        "value": c_plies / (c_ms * 1e-3), "unit": UNIT, "ms_per_batch": c_ms / 5}
         out["gpu_launches"] += 11
-        # the warp-per-board mapping of the same fused kernel (what the API kernels and MCTS use)
-        os.environ["XQ_PLAYOUT_MODE"] = "warp"
-        one_step(3000)
-        torch.cuda.synchronize()
-        w_ms, w_plies = 0.0, 0
-        for k in range(3):
-            flush.zero_()
-            bb.reset()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            bb.playout(SEED + k, PLIES, first_game_id=first_id, results=results)
-            b.record()
+        # the other two mappings of the same fused kernel: a warp per board (what the API kernels
+        # and MCTS use; the dispatch picks it below 40,960 boards) and a thread per board
+        out["other_mappings"] = {}
+        for mode, kname, wips in (("warp", "xq::playout_kernel<false,4,32>", WARP_INST_PER_STEP_WARP_MODE),
+                                  ("tpb", "xq::playout_tpb_kernel<false>", WARP_INST_PER_STEP_TPB_MODE)):
+            os.environ["XQ_PLAYOUT_MODE"] = mode
+            one_step(3000)
             torch.cuda.synchronize()
-            w_ms += a.elapsed_time(b)
-            w_plies += int(results.view(torch.int32)[:, 0].sum())
-        del os.environ["XQ_PLAYOUT_MODE"]
-        wv = w_plies / (w_ms * 1e-3)
-        out["warp_per_board"] = {"value": wv, "unit": UNIT, "kernel_ms_per_launch": w_ms / 3,
-                                 "kernel": "xq::playout_kernel<false,4,32>",
-                                 "issue": {"warp_inst_per_board_step": WARP_INST_PER_STEP_WARP_MODE,
-                                           "frac": wv * WARP_INST_PER_STEP_WARP_MODE / issue_peak}}
-        out["gpu_launches"] += 8
+            w_ms, w_plies = 0.0, 0
+            for k in range(3):
+                flush.zero_()
+                bb.reset()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                bb.playout(SEED + k, PLIES, first_game_id=first_id, results=results)
+                b.record()
+                torch.cuda.synchronize()
+                w_ms += a.elapsed_time(b)
+                w_plies += int(results.view(torch.int32)[:, 0].sum())
+            del os.environ["XQ_PLAYOUT_MODE"]
+            wv = w_plies / (w_ms * 1e-3)
+            out["other_mappings"][mode] = {"value": wv, "unit": UNIT, "kernel_ms_per_launch": w_ms / 3,
+                                           "kernel": kname,
+                                           "issue": {"warp_inst_per_board_step": wips,
+                                                     "frac": wv * wips / issue_peak}}
+            out["gpu_launches"] += 8
         v, ms, launches_per_step = measure_step_per_launch(torch, BoardBatch, n, first_id, 2, flush)
         out["step_per_launch"] = {
             "value": v, "unit": UNIT, "ms_per_step": ms, "launches_per_step": launches_per_step,

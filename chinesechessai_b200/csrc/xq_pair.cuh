@@ -97,11 +97,12 @@ __device__ __forceinline__ int pair_movegen(ThreadBoard& w, Game& g, const uint3
         const int a = 4 * i + ((__ffs(kab) - 1) >> 3), b = 4 * i + ((31 - __clz(kab)) >> 3);
         ex |= ((a >= lo && a < hi) || (b >= lo && b < hi)) ? 1 : 0;
       }
-      while (own) {
-        const int s = 4 * i + ((__ffs(own) - 1) >> 3);
-        own &= own - 1;
-        if (my_own < kHalfOwn) w.own[sub * kHalfOwn + my_own] = (uint8_t)s;
-        ++my_own;
+      // branch-free append: every square is written at the cursor, the cursor moves on only
+      // past an own piece (so the lanes of a warp stay converged whatever the piece counts)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        if (my_own < kHalfOwn) w.own[sub * kHalfOwn + my_own] = (uint8_t)(4 * i + b);
+        my_own += (int)((own >> (8 * b + 7)) & 1u);
       }
     }
   }
@@ -134,21 +135,35 @@ __device__ __forceinline__ int pair_movegen(ThreadBoard& w, Game& g, const uint3
       if (kcount == 0) kfirst = nc;
       kcount += cnt;
     }
+    // a quiet ray reserves its `empties` slots and leaves ONE descriptor in the first of them
+    // (from<<8 | 0x80 | d<<5 | empties); the flat pass below expands it in place
     const unsigned fs = (unsigned)it.from << 8;
     uint16_t* out = &w.mv[base + dir * nc];
-    unsigned v = fs | (unsigned)it.from;  // from + k*delta stays inside the low byte
-#pragma unroll 1
-    for (int k = it.empties; k > 0; k -= 2) {
-      *out = (uint16_t)(v += (unsigned)it.delta);
-      out += dir;
-      if (k > 1) {
-        *out = (uint16_t)(v += (unsigned)it.delta);
-        out += dir;
-      }
-    }
+    if (it.empties > 0) *out = (uint16_t)(fs | 0x80u | ((unsigned)(t & 3) << 5) | (unsigned)it.empties);
+    out += dir * it.empties;
     if (it.e1 >= 0) { *out = (uint16_t)(fs | (unsigned)it.e1); out += dir; }
     if (it.e2 >= 0) *out = (uint16_t)(fs | (unsigned)it.e2);
     nc += cnt;
+  }
+  {  // expand the ray descriptors: one slot per iteration, all lanes in step
+    unsigned v = 0, delta = 0;
+    int left = 0;
+#pragma unroll 1
+    for (int j = 0; j < nc; ++j) {
+      uint16_t* slot = &w.mv[base + dir * j];
+      if (left > 0) {
+        *slot = (uint16_t)(v += delta);
+        --left;
+      } else {
+        const unsigned c = *slot;
+        if (c & 0x80u) {  // slot d of gen_item: (0,1),(0,-1),(1,0),(-1,0)
+          delta = ((c & 0x40u) ? 9u : 1u) * ((c & 0x20u) ? 0xFFFFFFFFu : 1u);
+          left = (int)(c & 15u) - 1;
+          v = (c & 0x7f00u) | ((c >> 8) + delta);  // from + delta stays inside the low byte
+          *slot = (uint16_t)v;
+        }
+      }
+    }
   }
   // the two parts share the array: more than kTpbMoveCap candidates in total is an overflow
   // (every entry is still some valid candidate, so nothing downstream can go out of range)
