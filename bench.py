@@ -35,14 +35,15 @@ BYTES_PER_STEP_LAUNCH_MODE = 352
 #   fused playout: (board+meta in 128, out 128, result 40) / 70 plies + one 8-byte history append
 BYTES_PER_STEP_FUSED = (128 + 128 + 40) / 70.0 + 8.0
 # warp-instructions per board-step from ncu smsp__inst_executed.sum / plies of the same launch,
-# refreshed with every capture: the shipped thread-per-board kernel
+# refreshed with every capture: the shipped pair-per-board kernel
+# (profiles/r1/playout_pair_ncu_summary.txt), the thread-per-board kernel
 # (profiles/r1/playout_tpb_ncu_summary.txt) and the warp-per-board kernel
 # (profiles/r1/playout_v7_ncu_summary.txt)
-WARP_INST_PER_STEP = 1171.0
+WARP_INST_PER_STEP = 1092.0
 WARP_INST_PER_STEP_TPB_MODE = 1018.0
 WARP_INST_PER_STEP_WARP_MODE = 2193.0
 # dram__bytes_read.sum + dram__bytes_write.sum of one playout launch in the same captures
-DRAM_TRAFFIC_PER_LAUNCH = 46.64e6 + 4.35e6
+DRAM_TRAFFIC_PER_LAUNCH = 45.86e6 + 5.39e6
 FLOP_PER_LEAF_EVAL = 263_209_216          # ChessNet.forward, SURVEY.md §8d
 MCTS_GAMES, MCTS_SIMS, MCTS_OPENING_PLIES = 4096, 15, 4
 METRIC = "board-steps/sec (legal movegen+step)"
@@ -439,7 +440,7 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak,
                      "traffic": DRAM_TRAFFIC_PER_LAUNCH if n == BOARDS else None,
-                     "traffic_note": "ncu dram bytes read+write per launch (profiles/r1/playout_tpb_ncu_summary.txt); "
+                     "traffic_note": "ncu dram bytes read+write per launch (profiles/r1/playout_pair_ncu_summary.txt); "
                                      "algorithmic bytes per launch = %.2e" % (BYTES_PER_STEP_FUSED * plies_per_launch),
                      "peak_source": peak_src,
                      "kernel": "xq::playout_pair_kernel<false> (two lanes per board)" if n >= 40960
