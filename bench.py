@@ -130,7 +130,7 @@ def run_reference(args):
         return
     threads = os.cpu_count() or 1
     rate, _, _ = cpu_port_rate(1024, threads)                   # calibrate
-    games = int(max(256, min(BOARDS, rate * 8.0 / 69.0)))       # ~8 s per step
+    games = int(max(256, min(args.boards, rate * 8.0 / 69.0)))  # ~8 s per step
     for w in range(args.warmup):
         cpu_port_rate(min(games, 512), threads, SEED + 1000 + w)
     tot_plies, tot_t = 0, 0.0
@@ -139,12 +139,12 @@ def run_reference(args):
         tot_plies += plies
         tot_t += dt
     value = tot_plies / tot_t
-    sample = f"{games} of {BOARDS} games per step from the initial position, <= {PLIES} plies"
+    sample = f"{games} of {args.boards} games per step from the initial position, <= {PLIES} plies"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8/f64",
-        "data": "synthetic", "config": {"workload": f"cfg2 random playouts {BOARDS}x{PLIES} (sampled)",
+        "data": "synthetic", "config": {"workload": f"cfg2 random playouts {args.boards}x{PLIES} (sampled)",
                                         "pick": "philox4x32-10(seed,(game,ply)) mod n_legal"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": sample},
@@ -307,6 +307,39 @@ def measure_mcts(torch, dev, plies_timed=6, games=MCTS_GAMES, sims=MCTS_SIMS, la
             "ms_per_ply": ms / plies_timed, "unique_leaf_evals_per_s": evals / (ms * 1e-3),
             "roofline": {"bound": "tensor", "achieved": evals / (ms * 1e-3) * FLOP_PER_LEAF_EVAL / 1e12,
                          "unit": "TFLOP/s", "flop_per_leaf_eval": FLOP_PER_LEAF_EVAL}}
+
+
+def measure_selfplay_iteration(torch, dev, games=MCTS_GAMES, sims=MCTS_SIMS):
+    """The self-play half of cfg 5: `games` complete games (to a terminal state or the 70-ply cap,
+    all rules active) with `sims` simulations per move through the drop-in batch loop, plus the
+    training tensors Trainer.train_network consumes (boards, shaped rewards) left on the device.
+    Timed by wall clock around the whole call, host control flow included."""
+    from chinesechessai_b200.neural_network import ChessNet
+    from chinesechessai_b200.samples import training_tensors
+    from chinesechessai_b200.self_play import BatchedSelfPlay
+    torch.manual_seed(0)
+    net = ChessNet().to(dev).eval()
+    warm = BatchedSelfPlay(net, games, sims, temperature=1.0, device=dev, net_dtype=torch.bfloat16, seed=1)
+    warm.play(2, check_done=False)
+    del warm
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    sp = BatchedSelfPlay(net, games, sims, temperature=1.0, device=dev, net_dtype=torch.bfloat16, seed=0)
+    sp.play()
+    smp = training_tensors(sp)
+    n_samples = int(smp["reward"].shape[0])
+    checksum = float(smp["reward"].sum())           # device -> host read of the result
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    st = sp.stats()
+    meta = sp.boards.meta_host()
+    return {"workload": f"self-play half of cfg 5: {games} complete games, {sims} sims/move, random-init "
+                        "ChessNet (bf16), T=1.0, samples left on the device as training tensors",
+            "seconds": dt, "games_per_s": games / dt, "plies": st["plies"], "sims_per_s": st["sims"] / dt,
+            "samples": n_samples, "reward_checksum": checksum,
+            "decisive_games": int((meta["winner"] != 2).sum() - (meta["winner"] == 0).sum()),
+            "reference_note": "the unmodified reference plays one such game in 32 s per core "
+                              "(BASELINE.md section 2)"}
 
 
 def run_ours(args):
@@ -514,6 +547,9 @@ def run_ours(args):
                                            "issue": {"warp_inst_per_board_step": wips,
                                                      "frac": wv * wips / issue_peak}}
             out["gpu_launches"] += 8
+        l_sp = lib.xq_launch_count()
+        out["selfplay_iteration"] = measure_selfplay_iteration(torch, dev)
+        out["selfplay_iteration"]["gpu_launches"] = int(lib.xq_launch_count() - l_sp)
         v, ms, launches_per_step = measure_step_per_launch(torch, BoardBatch, n, first_id, 2, flush)
         out["step_per_launch"] = {
             "value": v, "unit": UNIT, "ms_per_step": ms, "launches_per_step": launches_per_step,

@@ -62,7 +62,7 @@ enum {
 };
 
 /* xq_meta.flags */
-#define XQ_F_OVERFLOW 1u /* >XQ_MAX_MOVES legal, >XQ_CAND_CAP candidates or history full */
+#define XQ_F_OVERFLOW 1u /* >XQ_MAX_MOVES legal, too many candidates / own pieces, or history full */
 
 typedef struct {
   int8_t player;              /* current_player +1/-1           chess_env.py:62  */
@@ -145,6 +145,12 @@ int xq_pick_moves(const int8_t *board, const xq_meta *meta, const int16_t *moves
 /* Fused random playout: up to max_plies x (get_legal_moves -> pick ->
  * make_move) per game in ONE launch, state in shared memory
  * (the loop of self_play.py:203-256 with the search replaced by the pick rule).
+ * The library maps boards to lanes by batch size (one warp per board below
+ * 40,960 boards, two lanes per board above; environment XQ_PLAYOUT_MODE =
+ * warp | tpb | pair forces one) - results are identical in every mapping.
+ * A game whose meta.flags gets XQ_F_OVERFLOW (more than XQ_MAX_MOVES candidate
+ * moves or a full history; unreachable from legal chess positions) keeps
+ * running on in-range but unspecified moves.
  * Optional per-ply traces (NULL to skip), each [n_games][max_plies]:
  *   tr_moves int16[..][XQ_MAX_MOVES], tr_n int16, tr_pick int16,
  *   tr_reward float64, tr_flags uint8, tr_boards int8[..][XQ_NSQ]. */

@@ -56,3 +56,23 @@ def test_product_does_not_import_oracle():
                 src = open(os.path.join(dirpath, f), encoding="utf-8").read()
                 assert "oracle" not in src.replace("the oracle", "").replace("CPU oracle", ""), \
                     f"{f} references oracle/"
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py's contract: exactly ONE line on stdout, a JSON object with the contract's keys.
+    The reference arm (CPU port of the path) runs without a GPU, so it is checked here."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
+                        "--steps", "1", "--warmup", "0", "--boards", "2048"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout[:300]
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step",
+              "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] in ("port", "reference")
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
