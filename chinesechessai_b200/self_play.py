@@ -226,6 +226,13 @@ class BatchedSelfPlay:
         per-ply "all games over?" host read (benchmarks that time a fixed number of plies)."""
         b = self.boards
         done = self.done
+        # "all games over?" is read from pinned memory two plies late, so the host keeps
+        # enqueueing ahead of the device instead of draining it every ply; the plies launched
+        # past the end are no-ops (every game inactive) and are not counted
+        lag = 2
+        first = self.plies
+        flag = torch.zeros((MAX_PLIES,), dtype=torch.bool).pin_memory() if check_done else None
+        events = {}
         for ply in range(self.plies, min(MAX_PLIES, self.plies + max_plies)):
             active = (~done).to(torch.uint8)
             mv, vis, nc = self._search(active)
@@ -248,8 +255,22 @@ class BatchedSelfPlay:
             done = done | ~live | ((flags & 1) != 0)
             self.done = done
             self.plies = ply + 1
-            if check_done and bool(done.all()):
-                break
+            if check_done:
+                flag[ply].copy_(done.all(), non_blocking=True)
+                events[ply] = torch.cuda.Event()
+                events[ply].record()
+                q = ply - lag
+                if q >= first:
+                    events.pop(q).synchronize()
+                    if bool(flag[q]):
+                        self.plies = q + 1
+                        break
+        if check_done:  # the last `lag` plies were not looked at inside the loop
+            for q in sorted(events):
+                events[q].synchronize()
+                if bool(flag[q]):
+                    self.plies = min(self.plies, q + 1)
+                    break
 
     def stats(self) -> Dict[str, int]:
         plies = int(self.rec_played[:self.plies].sum())
