@@ -120,9 +120,11 @@ class NetEvaluator:
         self.net = net
         self.dtype = dtype
         self._fast = None
+        self.version = 0  # bumped by refresh(); captured CUDA graphs of a search are keyed on it
 
     def refresh(self) -> None:
         self._fast = None
+        self.version += 1
 
     @torch.no_grad()
     def __call__(self, leaf_board, leaf_player, leaf_moves, leaf_n):

@@ -20,7 +20,10 @@ from ._lib import BOARD_STRIDE, MAX_MOVES, META_DTYPE, check
 from .chess_env import ChineseChess, format_end_reason
 from .config import MAX_MOVES as MAX_PLIES, MCTS_SIMULATIONS
 from .engine import BoardBatch, _ptr, _stream, pack_move, unpack_move
-from .mcts import WAVE, BatchedMCTS, NetEvaluator
+from .mcts import WAVE, BatchedMCTS, HashEvaluator, NetEvaluator
+
+GRAPH_MAX_GAMES = 2048  # measured (scripts/single_game_latency.py): 4.5x at 1-64 games, 1.6x at 1,024,
+                        # 1.1x at 2,048; beyond that a ply is device-bound
 
 Move = Tuple[int, int, int, int]
 
@@ -168,7 +171,7 @@ class BatchedSelfPlay:
     def __init__(self, network, n_games: int, num_simulations: int, temperature: float = 1.0,
                  opponent_network=None, device: Optional[torch.device] = None,
                  net_dtype: torch.dtype = torch.float32, seed: Optional[int] = None,
-                 first_game_id: int = 0):
+                 first_game_id: int = 0, use_graph: Optional[bool] = None):
         self.n = int(n_games)
         self.n_sims = int(num_simulations)
         self.temperature = float(temperature)
@@ -199,8 +202,40 @@ class BatchedSelfPlay:
         self.rec_played = torch.zeros((P, self.n), dtype=torch.bool, device=d)
         self.plies = 0
         self.done = torch.zeros(self.n, dtype=torch.bool, device=d)
+        # Small batches are launch-bound (about 60 launches per ply against ~1 ms of device
+        # work up to a few hundred games): the whole search of a ply — init, every wave's
+        # select / encode / forward / priors / backup, root visits — is captured once as a CUDA
+        # graph and replayed.  Large batches are device-bound and stay eager.
+        self.use_graph = (self.n <= GRAPH_MAX_GAMES and self.eval_black is None and
+                          isinstance(self.eval_red, (NetEvaluator, HashEvaluator))) if use_graph is None \
+            else bool(use_graph)
+        self._graph = None
+        self._graph_key = None
+        self._active = torch.ones(self.n, dtype=torch.uint8, device=d)
 
     def _search(self, active: torch.Tensor):
+        if not self.use_graph or self.n == 0:
+            return self._search_eager(active)
+        self._active.copy_(active)
+        key = (getattr(self.eval_red, "version", 0), getattr(self.eval_black, "version", 0))
+        if self._graph is None or self._graph_key != key:
+            self._search_eager(self._active)  # warm-up: library handles, workspaces, folded net
+            torch.cuda.current_stream(self.device).synchronize()
+            graph = torch.cuda.CUDAGraph()
+            try:
+                with torch.cuda.graph(graph):
+                    self._search_eager(self._active)
+            except Exception as exc:  # an evaluator that cannot be captured (host syncs, ...)
+                import warnings
+                warnings.warn(f"CUDA-graph capture of the search failed ({exc}); running eagerly")
+                self.use_graph = False
+                return self._search_eager(active)
+            self._graph, self._graph_key = graph, key
+        self._graph.replay()
+        m = self.mcts
+        return m.root_moves, m.root_visits, m.root_n
+
+    def _search_eager(self, active: torch.Tensor):
         m, b = self.mcts, self.boards
         m.init(b.board, b.meta, active)
         if self.eval_black is None:

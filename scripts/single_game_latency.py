@@ -25,10 +25,11 @@ t0 = time.perf_counter()
 data, winner, reason = self_play_game(net, temperature=1.0, num_simulations=sims)
 t_game = time.perf_counter() - t0
 out = {"sims": sims, "search_ms_per_move": 1e3 * t_search, "self_play_game_s": t_game, "plies": len(data)}
-for n in (1, 8, 64):
-    sp = BatchedSelfPlay(net, n, sims, 1.0, net_dtype=torch.bfloat16, seed=0)
-    sp.play(3, check_done=False); torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    sp.play(20, check_done=False); torch.cuda.synchronize()
-    out[f"batched_ply_ms_n{n}"] = 1e3 * (time.perf_counter() - t0) / 20
+for n in (1, 64, 512, 1024, 2048):
+    for graph in (False, True):
+        sp = BatchedSelfPlay(net, n, sims, 1.0, net_dtype=torch.bfloat16, seed=0, use_graph=graph)
+        sp.play(3, check_done=False); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        sp.play(20, check_done=False); torch.cuda.synchronize()
+        out[f"batched_ply_ms_n{n}_{'graph' if graph else 'eager'}"] = round(1e3 * (time.perf_counter() - t0) / 20, 3)
 print(json.dumps(out))

@@ -257,3 +257,48 @@ def test_device_training_tensors_match_materialised_samples(pkg):
         want = np.stack([net.encode_board(boards[i].reshape(10, 9), 1) for i in idx.cpu().tolist()[:5]])
         assert np.array_equal(states[:5].cpu().numpy(), want)
         assert target.shape == (len(idx), 1) and target.dtype == torch.float32
+
+
+@pytest.mark.gpu
+def test_batched_self_play_cuda_graph_equals_eager():
+    """Small batches replay the per-ply search as a captured CUDA graph; with the deterministic
+    hashed evaluator every recorded move, visit count and reward equals the eager loop's."""
+    import torch
+    from chinesechessai_b200.mcts import HashEvaluator
+    from chinesechessai_b200.self_play import BatchedSelfPlay
+    runs = []
+    for graph in (False, True):
+        sp = BatchedSelfPlay(HashEvaluator(), 24, 15, temperature=1.0, seed=77, first_game_id=5, use_graph=graph)
+        assert sp.use_graph == graph
+        sp.play()
+        runs.append(sp)
+    a, b = runs
+    assert b._graph is not None and a._graph is None
+    assert a.plies == b.plies and a.plies > 10
+    P = a.plies
+    for f in ("rec_move", "rec_visits", "rec_moves", "rec_n", "rec_board", "rec_played"):
+        assert torch.equal(getattr(a, f)[:P], getattr(b, f)[:P]), f
+    assert torch.equal(a.rec_reward[:P].view(torch.int64), b.rec_reward[:P].view(torch.int64))
+    assert torch.equal(a.boards.board, b.boards.board) and torch.equal(a.boards.meta, b.boards.meta)
+
+
+@pytest.mark.gpu
+def test_batched_self_play_cuda_graph_with_network():
+    """The captured search with the real evaluator (encode -> folded bf16 net -> priors): every
+    live root receives the same number of child visits as in the eager loop."""
+    import torch
+    from chinesechessai_b200.neural_network import ChessNet
+    from chinesechessai_b200.self_play import BatchedSelfPlay
+    torch.manual_seed(0)
+    net = ChessNet().cuda().eval()
+    sp = BatchedSelfPlay(net, 16, 15, temperature=1.0, seed=3, net_dtype=torch.bfloat16)
+    assert sp.use_graph                       # auto mode: small batch, network evaluator
+    sp.play(6)
+    assert sp._graph is not None
+    ref = BatchedSelfPlay(net, 16, 15, temperature=1.0, seed=3, net_dtype=torch.bfloat16, use_graph=False)
+    ref.play(1)
+    played = sp.rec_played[:sp.plies]
+    tot = sp.rec_visits[:sp.plies].sum(-1)
+    expect = int(ref.rec_visits[0, 0].sum())
+    # 15 sims = a wave of 8 that expands the root + a wave of 7 through its children (B.2)
+    assert expect == 7 and bool((tot[played] == expect).all())
