@@ -430,6 +430,104 @@ __global__ void __launch_bounds__(kTpbThreads)
 }
 
 // ---------------------------------------------------------------------------
+// get_legal_moves / make_move for LARGE batches, two lanes per board (xq_pair.cuh): the same
+// entry points, the mapping that is faster once the batch fills the SMs (see xq_playout).
+__device__ __forceinline__ void pair_store_meta(xq_meta* __restrict__ dst, const Game& G) {
+  uint4 a, b;
+  a.x = (uint32_t)(G.player & 0xff) | ((uint32_t)(G.winner & 0xff) << 8) |
+        ((uint32_t)(G.reason & 0xff) << 16) | ((uint32_t)(G.done & 0xff) << 24);
+  a.y = (uint32_t)(G.red_king & 0xff) | ((uint32_t)(G.black_king & 0xff) << 8) |
+        ((uint32_t)(G.flags & 0xff) << 16);
+  a.z = (uint32_t)G.move_count;
+  a.w = (uint32_t)G.no_capture;
+  b.x = (uint32_t)G.cchecks;
+  b.y = (uint32_t)G.hist_len;
+  b.z = G.check_bits;
+  b.w = (uint32_t)G.check_len;
+  reinterpret_cast<uint4*>(dst)[0] = a;
+  reinterpret_cast<uint4*>(dst)[1] = b;
+}
+
+// the pair's legal list (lane 0's run, then lane 1's) to a row of int16 from*90+to
+__device__ __forceinline__ void pair_store_moves(const ThreadBoard& w, int16_t* __restrict__ row, int n,
+                                                 int n0) {
+  const int sub = Pair::sub();
+  const int my_n = sub ? n - n0 : n0, my_off = sub ? n0 : 0;
+  const int my_base = sub ? kTpbMoveCap - 1 : 0, my_dir = sub ? -1 : 1;
+  for (int i = 0; i < my_n; ++i) row[my_off + i] = (int16_t)tpb_packed(w.mv[my_base + my_dir * i]);
+}
+
+__global__ void __launch_bounds__(128, 7)
+    legal_moves_pair_kernel(const int8_t* __restrict__ board, xq_meta* __restrict__ meta,
+                            int16_t* __restrict__ moves, int16_t* __restrict__ n_moves,
+                            uint8_t* __restrict__ in_check_out, int n_games) {
+  extern __shared__ __align__(16) unsigned char tpb_smem[];
+  const int g = blockIdx.x * 64 + (int)(threadIdx.x >> 1);
+  if (g >= n_games) return;
+  ThreadBoard& w = reinterpret_cast<ThreadBoard*>(tpb_smem)[threadIdx.x >> 1];
+  pair_load(w, board + (size_t)g * XQ_BOARD_STRIDE);
+  Game G = load_meta(meta + g);
+  const int flags0 = G.flags;
+  bool checking = false;
+  int n0 = 0;
+  unsigned lsum = 0;
+  const int n = pair_movegen(w, G, g_leap, false, checking, n0, lsum);
+  pair_store_moves(w, moves + (size_t)g * XQ_MAX_MOVES, n, n0);
+  if (Pair::sub() == 0) {
+    n_moves[g] = (int16_t)n;
+    if (in_check_out) in_check_out[g] = in_check(w, G, G.player) ? 1 : 0;
+    if (G.flags != flags0) reinterpret_cast<uint8_t*>(meta + g)[6] = (uint8_t)G.flags;
+  }
+}
+
+__global__ void __launch_bounds__(128, 7)
+    step_pair_kernel(int8_t* __restrict__ board, xq_meta* __restrict__ meta,
+                     uint64_t* __restrict__ pos_hist, int hist_cap, const int16_t* __restrict__ move,
+                     double* __restrict__ reward, uint8_t* __restrict__ flags,
+                     int16_t* __restrict__ next_moves, int16_t* __restrict__ next_n, int n_games) {
+  extern __shared__ __align__(16) unsigned char tpb_smem[];
+  const int sub = Pair::sub();
+  const int g = blockIdx.x * 64 + (int)(threadIdx.x >> 1);
+  if (g >= n_games) return;
+  ThreadBoard& w = reinterpret_cast<ThreadBoard*>(tpb_smem)[threadIdx.x >> 1];
+  int mv = move[g];
+  if (mv >= XQ_POLICY) {  // not a (from,to) pair: refuse, flag, leave the game untouched
+    if (sub == 0) reinterpret_cast<uint8_t*>(meta + g)[6] |= XQ_F_OVERFLOW;
+    mv = -1;
+  }
+  if (mv < 0) {  // frozen game
+    if (sub == 0) {
+      reward[g] = 0.0;
+      const xq_meta m = meta[g];
+      flags[g] = (uint8_t)((m.done & 1) | 2u | (((m.winner + 1) & 3) << 2) | ((m.reason & 15) << 4));
+      if (next_n) next_n[g] = 0;
+    }
+    return;
+  }
+  pair_load(w, board + (size_t)g * XQ_BOARD_STRIDE);
+  Game G = load_meta(meta + g);
+  G.bkey = pair_board_key(w);
+  uint64_t* hist = pos_hist + (size_t)g * hist_cap;
+  TpbStep o = tpb_apply<true>(w, G, mv / 90, mv % 90, hist, hist_cap);
+  bool checking = false;
+  int n = -1, n0 = 0;
+  unsigned lsum = 0;
+  if (!o.done) n = pair_movegen(w, G, g_leap, true, checking, n0, lsum);  // :317 + :354/:376
+  tpb_finish<true>(w, G, o, n, checking, hist);
+#pragma unroll
+  for (int i = 0; i < XQ_BOARD_STRIDE / 8; ++i)
+    reinterpret_cast<uint32_t*>(board + (size_t)g * XQ_BOARD_STRIDE)[2 * i + sub] =
+        reinterpret_cast<const uint32_t*>(w.sq)[2 * i + sub];
+  if (next_n && next_moves && n > 0) pair_store_moves(w, next_moves + (size_t)g * XQ_MAX_MOVES, n, n0);
+  if (sub != 0) return;
+  pair_store_meta(meta + g, G);
+  reward[g] = o.reward;
+  flags[g] = (uint8_t)((o.done & 1) | ((o.is_int & 1) << 1) | (((G.winner + 1) & 3) << 2) |
+                       ((G.reason & 15) << 4));
+  if (next_n) next_n[g] = (int16_t)(n < 0 ? -1 : n);
+}
+
+// ---------------------------------------------------------------------------
 // Fused random playout, TWO lanes per board (xq_pair.cuh): 64 boards per 128-thread CTA.
 constexpr int kPairThreads = 128;
 constexpr int kPairMinBlocks = XQ_PAIR_MINB;
@@ -668,12 +766,24 @@ int xq_position_hash(const int8_t* board, const xq_meta* meta, uint64_t* out, in
   return check_launch("xq_position_hash");
 }
 
+// Lane mapping by batch size (measured, profiles/r1/playout_mappings_by_batch.txt): a warp per
+// board while the batch is small, a lane pair per board once it fills the SMs.
+// XQ_PLAYOUT_MODE = warp | tpb | pair overrides (tpb only exists for the fused playout).
+static bool use_pair_mapping(int n_games) {
+  const char* e = getenv("XQ_PLAYOUT_MODE");
+  return e ? strcmp(e, "pair") == 0 : n_games >= XQ_PAIR_MIN_GAMES;
+}
+
 int xq_legal_moves(const int8_t* board, xq_meta* meta, int16_t* moves, int16_t* n_moves,
                    uint8_t* in_check, int n_games, void* stream) {
   if (n_games == 0) return 0;
   XQ_REQUIRE(board && meta && moves && n_moves && n_games >= 0, "null pointer or negative n_games");
-  legal_moves_kernel<<<ctas_for(n_games), kThreads, 0, (cudaStream_t)stream>>>(
-      board, meta, moves, n_moves, in_check, n_games);
+  if (use_pair_mapping(n_games))
+    legal_moves_pair_kernel<<<(n_games + 63) / 64, 128, 64 * sizeof(ThreadBoard), (cudaStream_t)stream>>>(
+        board, meta, moves, n_moves, in_check, n_games);
+  else
+    legal_moves_kernel<<<ctas_for(n_games), kThreads, 0, (cudaStream_t)stream>>>(
+        board, meta, moves, n_moves, in_check, n_games);
   return check_launch("xq_legal_moves");
 }
 
@@ -693,8 +803,12 @@ int xq_step(int8_t* board, xq_meta* meta, uint64_t* pos_hist, int hist_cap, cons
   XQ_REQUIRE(board && meta && pos_hist && move && reward && flags && n_games >= 0 && hist_cap > 0,
              "null pointer, negative n_games or hist_cap <= 0");
   XQ_REQUIRE(!(next_moves && !next_n), "next_moves requires next_n");
-  step_kernel<<<ctas_for(n_games), kThreads, 0, (cudaStream_t)stream>>>(
-      board, meta, pos_hist, hist_cap, move, reward, flags, next_moves, next_n, n_games);
+  if (use_pair_mapping(n_games))
+    step_pair_kernel<<<(n_games + 63) / 64, 128, 64 * sizeof(ThreadBoard), (cudaStream_t)stream>>>(
+        board, meta, pos_hist, hist_cap, move, reward, flags, next_moves, next_n, n_games);
+  else
+    step_kernel<<<ctas_for(n_games), kThreads, 0, (cudaStream_t)stream>>>(
+        board, meta, pos_hist, hist_cap, move, reward, flags, next_moves, next_n, n_games);
   return check_launch("xq_step");
 }
 
@@ -739,7 +853,7 @@ int xq_playout(int8_t* board, xq_meta* meta, uint64_t* pos_hist, int hist_cap, u
   // up; one thread per board ("tpb") issues the fewest instructions but is latency-bound.
   // XQ_PLAYOUT_MODE overrides the choice (all three give identical results).
   const char* mode_env = getenv("XQ_PLAYOUT_MODE");
-  const bool pair = mode_env ? strcmp(mode_env, "pair") == 0 : n_games >= XQ_PAIR_MIN_GAMES;
+  const bool pair = use_pair_mapping(n_games);
   const bool tpb = mode_env != nullptr && strcmp(mode_env, "tpb") == 0;
   if (pair) {
     const int bpc = kPairThreads / 2;

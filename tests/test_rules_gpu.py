@@ -40,6 +40,13 @@ def _positions_batch(eng, P):
     return bb
 
 
+@pytest.fixture(params=["warp", "pair"])
+def api_mapping(request, monkeypatch):
+    """xq_legal_moves / xq_step pick their lane mapping by batch size; the tests force each one."""
+    monkeypatch.setenv("XQ_PLAYOUT_MODE", request.param)
+    return request.param
+
+
 def test_initial_position(eng, golden):
     bb = eng.BoardBatch(3)
     mv, n = bb.legal_moves()
@@ -50,7 +57,7 @@ def test_initial_position(eng, golden):
     assert m["black_king"].tolist() == [4] * 3 and m["winner"].tolist() == [2] * 3
 
 
-def test_legal_moves_arbitrary_positions(eng, golden):
+def test_legal_moves_arbitrary_positions(eng, golden, api_mapping):
     import torch
     P = golden.positions
     bb = _positions_batch(eng, P)
@@ -64,7 +71,7 @@ def test_legal_moves_arbitrary_positions(eng, golden):
     assert np.array_equal(chk, P["chk_self"])
 
 
-def test_step_arbitrary_positions(eng, golden):
+def test_step_arbitrary_positions(eng, golden, api_mapping):
     import torch
     P = golden.positions
     bb = _positions_batch(eng, P)
@@ -94,7 +101,7 @@ LINES = ["double_cannon_mate", "knight_shuffle", "quiet_knight", "pawn_line", "c
 
 
 @pytest.mark.parametrize("name", LINES)
-def test_kat_lines(eng, golden, name):
+def test_kat_lines(eng, golden, name, api_mapping):
     import torch
     k = golden.kats[name]
     st = k["start"]
@@ -119,7 +126,7 @@ def test_kat_lines(eng, golden, name):
     assert len(set(bb.pos_hist_host()[0, :meta["hist_len"]].tolist())) == k["distinct_hashes"]
 
 
-def test_kat_positions(eng, golden):
+def test_kat_positions(eng, golden, api_mapping):
     for name, p in golden.kats["positions"].items():
         bb = eng.BoardBatch(1)
         bb.set_state(np.array(p["board"], np.int8).reshape(1, 90),
@@ -247,7 +254,7 @@ def test_fused_playout_from_arbitrary_positions(eng, xo, golden, mode, monkeypat
             assert m["consecutive_checks"][i] == e.s.consecutive_checks and m["no_capture"][i] == e.s.no_capture
 
 
-def test_step_per_launch_equals_fused(eng):
+def test_step_per_launch_equals_fused(eng, api_mapping):
     import torch
     n, bias = 2048, 96
     fused = eng.BoardBatch(n)
@@ -370,7 +377,7 @@ def test_encode_planes_and_priors(eng, xo):
         assert int(np.argmax(pri[i, :k])) == int(np.argmax(ref))
 
 
-def test_position_history_equals_oracle(eng, xo):
+def test_position_history_equals_oracle(eng, xo, api_mapping):
     """_get_position_hash / position_history (chess_env.py:338,497-504): the device history row
     holds exactly the oracle's keys (same key function, mover's side byte), ply by ply."""
     n = 64
