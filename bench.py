@@ -42,7 +42,7 @@ BYTES_PER_STEP_FUSED = (128 + 128 + 40) / 70.0 + 8.0
 # (profiles/r1/playout_tpb_ncu_summary.txt) and the warp-per-board kernel
 # (profiles/r1/playout_v7_ncu_summary.txt)
 WARP_INST_PER_STEP = 1092.0
-WARP_INST_PER_STEP_TPB_MODE = 1018.0
+WARP_INST_PER_STEP_TPB_MODE = 956.0
 WARP_INST_PER_STEP_WARP_MODE = 2193.0
 # dram__bytes_read.sum + dram__bytes_write.sum of one playout launch in the same captures
 DRAM_TRAFFIC_PER_LAUNCH = 45.86e6 + 5.39e6
