@@ -63,6 +63,7 @@ SIGNATURES = {
                         _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "xq_playout_host": (_i, [_vp, _vp, _u64, _u32, _i, _i, _vp, _i, _i]),
     "xq_encode_planes": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _vp]),
+    "xq_encode_planes_nhwc16": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp]),
     "xq_policy_priors": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _i, _vp]),
     "xq_bias_residual_relu_bf16": (_i, [_vp, _vp, _vp, _vp, C.c_int64, _i, _vp]),
     "xq_mcts_tree_bytes": (C.c_int64, [_i]),

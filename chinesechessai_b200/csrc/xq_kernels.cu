@@ -660,6 +660,30 @@ __global__ void __launch_bounds__(256)
   out[14 * XQ_NSQ] = pl == 1 ? one : zero;
 }
 
+// encode_board for the folded bf16 network: channels-last with the channel count padded to 16,
+// one thread per square writes its 16 channels as two 16-byte stores.
+__global__ void __launch_bounds__(256)
+    encode_nhwc16_kernel(const int8_t* __restrict__ board, int board_stride,
+                         const int8_t* __restrict__ player, int player_stride,
+                         uint4* __restrict__ planes, int n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)n * XQ_NSQ) return;
+  const int g = (int)(i / XQ_NSQ), s = (int)(i - (int64_t)g * XQ_NSQ);
+  const int p = board[(size_t)g * board_stride + s];
+  const int pl = player[(size_t)g * player_stride];
+  // channel k-1 = (piece == +k), channel k+6 = (piece == -k), k = 1..7; channel 14 = red to move
+  const int ch = p > 0 && p <= 7 ? p - 1 : (p < 0 && p >= -7 ? 6 - p : -1);
+  uint32_t w[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const uint32_t lo = (ch == 2 * k) ? 0x3F80u : 0u, hi = (ch == 2 * k + 1) ? 0x3F80u : 0u;  // bf16 1.0
+    w[k] = lo | (hi << 16);
+  }
+  if (pl == 1) w[7] |= 0x3F80u;  // channel 14; channel 15 stays 0
+  planes[2 * i] = make_uint4(w[0], w[1], w[2], w[3]);
+  planes[2 * i + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
 // _logits_to_move_probs (neural_network.py:148-169): warp per position.
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
@@ -995,6 +1019,17 @@ int xq_encode_planes(const int8_t* board, int board_stride, const int8_t* player
     encode_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(board, board_stride, player,
                                                                  player_stride, (float*)planes, n);
   return check_launch("xq_encode_planes");
+}
+
+int xq_encode_planes_nhwc16(const int8_t* board, int board_stride, const int8_t* player,
+                            int player_stride, void* planes, int n, void* stream) {
+  if (n == 0) return 0;
+  XQ_REQUIRE(board && player && planes && n >= 0 && board_stride >= XQ_NSQ && player_stride >= 1,
+             "null pointer or bad stride");
+  const int64_t total = (int64_t)n * XQ_NSQ;
+  encode_nhwc16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      board, board_stride, player, player_stride, (uint4*)planes, n);
+  return check_launch("xq_encode_planes_nhwc16");
 }
 
 int xq_bias_residual_relu_bf16(const void* y, const void* x, const void* bias, void* out,

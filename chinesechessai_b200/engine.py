@@ -185,6 +185,20 @@ def encode_planes(board: torch.Tensor, player: torch.Tensor, out: Optional[torch
     return out
 
 
+def encode_planes_nhwc16(board: torch.Tensor, player: torch.Tensor) -> torch.Tensor:
+    """The same planes as a bf16 tensor of shape [n,16,10,9] in channels_last memory format
+    (channel 15 is zero padding): what the folded inference network consumes, written by the
+    kernel in that layout instead of NCHW + a layout-conversion pass."""
+    lib = _lib.load()
+    n = board.shape[0]
+    out = torch.empty((n, 16, 10, 9), dtype=torch.bfloat16, device=board.device,
+                      memory_format=torch.channels_last)
+    with torch.cuda.device(board.device):
+        check(lib.xq_encode_planes_nhwc16(_ptr(board), board.stride(0), _ptr(player), player.stride(0),
+                                          _ptr(out), n, _stream()))
+    return out
+
+
 def policy_priors(logits: torch.Tensor, moves: torch.Tensor, n_moves: torch.Tensor,
                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """ChessNet._logits_to_move_probs (neural_network.py:148-169) for a batch."""

@@ -13,7 +13,8 @@ import torch
 
 from . import _lib
 from ._lib import BOARD_STRIDE, MAX_MOVES, check
-from .engine import _ptr, _stream, bias_residual_relu, encode_planes, policy_priors
+from .engine import (_ptr, _stream, bias_residual_relu, encode_planes, encode_planes_nhwc16,
+                     policy_priors)
 
 WAVE = 8  # self_play.py:101
 
@@ -53,6 +54,19 @@ class _FoldedNet(torch.nn.Module):
         from torch.nn.utils.fusion import fuse_conv_bn_eval
         n = copy.deepcopy(net).eval()
         self.stem = fuse_conv_bn_eval(n.conv1, n.bn1)
+        self.in_channels = self.stem.in_channels
+        if dtype == torch.bfloat16 and self.stem.in_channels == 15:
+            # 16 input channels (one zero plane): 32-byte pixels in channels-last, so cuDNN needs
+            # no padding pass and the planes come straight from xq_encode_planes_nhwc16
+            st = self.stem
+            padded = torch.nn.Conv2d(16, st.out_channels, st.kernel_size, st.stride, st.padding,
+                                     bias=True, device=st.weight.device)
+            with torch.no_grad():
+                padded.weight.zero_()
+                padded.weight[:, :15].copy_(st.weight)
+                padded.bias.copy_(st.bias)
+            self.stem = padded
+            self.in_channels = 16
         self.blocks = torch.nn.ModuleList(
             torch.nn.ModuleList([fuse_conv_bn_eval(b.conv1, b.bn1), fuse_conv_bn_eval(b.conv2, b.bn2)])
             for b in n.res_blocks)
@@ -71,7 +85,7 @@ class _FoldedNet(torch.nn.Module):
         self.own_epilogue = dtype == torch.bfloat16
         if next(self.parameters()).is_cuda:
             try:  # probe the fused cuDNN entry points once
-                x = torch.zeros((2, 15, 10, 9), dtype=dtype, device=fc.weight.device).contiguous(
+                x = torch.zeros((2, self.in_channels, 10, 9), dtype=dtype, device=fc.weight.device).contiguous(
                     memory_format=torch.channels_last)
                 self.fused = True
                 self.forward(x)
@@ -128,13 +142,17 @@ class NetEvaluator:
 
     @torch.no_grad()
     def __call__(self, leaf_board, leaf_player, leaf_moves, leaf_n):
-        planes = encode_planes(leaf_board, leaf_player, dtype=self.dtype)
         if self.dtype == torch.float32:
-            logits, value = self.net(planes)
+            logits, value = self.net(encode_planes(leaf_board, leaf_player, dtype=self.dtype))
         else:
             if self._fast is None:
                 self._fast = _FoldedNet(self.net, self.dtype)
-            logits, value = self._fast(planes.contiguous(memory_format=torch.channels_last))
+            if self._fast.in_channels == 16:
+                planes = encode_planes_nhwc16(leaf_board, leaf_player)
+            else:
+                planes = encode_planes(leaf_board, leaf_player, dtype=self.dtype).contiguous(
+                    memory_format=torch.channels_last)
+            logits, value = self._fast(planes)
         if logits.stride(1) != 1:
             logits = logits.contiguous()
         if logits.dtype not in (torch.float32, torch.bfloat16):

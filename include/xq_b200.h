@@ -173,6 +173,13 @@ int xq_encode_planes(const int8_t *board, int board_stride, const int8_t *player
                      int player_stride, void *planes, int out_bf16, int n,
                      void *stream);
 
+/* Same planes for the inference copy of the network: bf16, channels-last
+ * [n][10][9][16] (the 15 planes + one zero channel), i.e. the memory a torch
+ * tensor of shape [n,16,10,9] in channels_last format has - 32 contiguous
+ * bytes per square, the layout the tensor-core convolution reads directly. */
+int xq_encode_planes_nhwc16(const int8_t *board, int board_stride, const int8_t *player,
+                            int player_stride, void *planes, int n, void *stream);
+
 /* ChessNet._logits_to_move_probs (neural_network.py:148-169): gather the
  * legal moves' logits and softmax in float32.  logits: float32 or bf16 rows of
  * logits_stride >= XQ_POLICY elements (a padded policy head may be passed as is);

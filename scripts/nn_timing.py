@@ -21,7 +21,10 @@ with torch.no_grad():
         ref = net(x)
         for dt in (torch.bfloat16, torch.float16):
             f = _FoldedNet(net, dt)
-            xb = x.to(dt).contiguous(memory_format=torch.channels_last)
+            xb = x.to(dt)
+            if f.in_channels == 16:
+                xb = torch.cat([xb, torch.zeros_like(xb[:, :1])], 1)
+            xb = xb.contiguous(memory_format=torch.channels_last)
             out = f(xb)
             err_p = (out[0][:, :8100].float() - ref[0]).abs().max().item()
             err_v = (out[1].float() - ref[1]).abs().max().item()

@@ -192,7 +192,8 @@ def test_folded_net_matches_module(mods):
         ref_p, ref_v = net(planes)
         f = mcts._FoldedNet(net, torch.bfloat16)
         assert f.fused and f.own_epilogue
-        p, v = f(planes.bfloat16().contiguous(memory_format=torch.channels_last))
+        assert f.in_channels == 16  # zero-padded stem fed by the channels-last encode kernel
+        p, v = f(eng.encode_planes_nhwc16(bb.board, bb.meta[:, 0].view(torch.int8)))
     assert p.shape == (256, 8192) and float(p[:, 8100:].abs().max()) == 0.0
     assert float((p[:, :8100].float() - ref_p).abs().max()) < 0.15
     assert float((v.float() - ref_v).abs().max()) < 0.05

@@ -365,6 +365,11 @@ def test_encode_planes_and_priors(eng, xo):
         assert np.array_equal(planes[i], xo.encode_board(boards[i], int(meta["player"][i]))), i
     pb = eng.encode_planes(bb.board, pl, dtype=torch.bfloat16).float().cpu().numpy()
     assert np.array_equal(pb, planes)
+    # channels-last bf16 with the channel count padded to 16 (the inference net's input layout)
+    cl = eng.encode_planes_nhwc16(bb.board, pl)
+    assert cl.shape == (n, 16, 10, 9) and cl.is_contiguous(memory_format=torch.channels_last)
+    clh = cl.float().cpu().numpy()
+    assert np.array_equal(clh[:, :15], planes) and not clh[:, 15].any()
     mv, nm = bb.legal_moves()
     logits = torch.randn(n, 8100, device=bb.device) * 3
     pri = eng.policy_priors(logits, mv, nm).cpu().numpy()
