@@ -80,6 +80,14 @@ class _FoldedNet(torch.nn.Module):
             self.policy_fc.weight[:fc.out_features].copy_(fc.weight)
             self.policy_fc.bias[:fc.out_features].copy_(fc.bias)
         self.value_fc1, self.value_fc2 = n.value_fc1, n.value_fc2
+        # The reference flattens NCHW (.view): feature index = c*90 + square.  The activations here
+        # are channels-last, so the two FC layers get their input columns re-ordered once to
+        # square*C + c and read the conv outputs as they lie in memory (no transpose pass).
+        with torch.no_grad():
+            for fc_layer, c_in in ((self.policy_fc, self.policy_conv.out_channels),
+                                   (self.value_fc1, self.value_conv.out_channels)):
+                w = fc_layer.weight
+                fc_layer.weight.copy_(w.view(w.shape[0], c_in, 90).permute(0, 2, 1).reshape(w.shape[0], -1))
         self.to(dtype=dtype, memory_format=torch.channels_last)
         self.fused = False
         self.own_epilogue = dtype == torch.bfloat16
@@ -117,8 +125,9 @@ class _FoldedNet(torch.nn.Module):
                 x = torch.relu(c2(torch.relu(c1(x))) + x)
             p = torch.relu(self.policy_conv(x))
             v = torch.relu(self.value_conv(x))
-        p = self.policy_fc(p.flatten(1))  # NCHW-order flatten, as the reference's .view
-        v = torch.tanh(self.value_fc2(torch.relu(self.value_fc1(v.flatten(1)))))
+        nb = p.shape[0]
+        p = self.policy_fc(p.permute(0, 2, 3, 1).reshape(nb, -1))  # a view of channels-last memory
+        v = torch.tanh(self.value_fc2(torch.relu(self.value_fc1(v.permute(0, 2, 3, 1).reshape(nb, -1)))))
         return p, v
 
 
