@@ -66,6 +66,7 @@ SIGNATURES = {
     "xq_encode_planes_nhwc16": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp]),
     "xq_policy_priors": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _i, _vp]),
     "xq_bias_residual_relu_bf16": (_i, [_vp, _vp, _vp, _vp, C.c_int64, _i, _vp]),
+    "xq_stem_lookup_bf16": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _vp]),
     "xq_mcts_tree_bytes": (C.c_int64, [_i]),
     "xq_mcts_init": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp]),
     "xq_mcts_select": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),

@@ -684,6 +684,74 @@ __global__ void __launch_bounds__(256)
   planes[2 * i + 1] = make_uint4(w[4], w[5], w[6], w[7]);
 }
 
+// encode_board + conv1/bn1/ReLU by table lookup (see xq_stem_lookup_bf16 in the header).
+// Persistent CTAs stage the weight table in shared memory once; the 16 lanes that own a square
+// decode its 9 neighbours in parallel — lane k looks at tap k — and share the plane indices by
+// shuffle, then every lane accumulates 8 output channels in float32 (one 16-byte store).
+constexpr int kStemCh = 128;  // first-layer output channels (config.py:33): 16 vectors per square
+
+__global__ void __launch_bounds__(256)
+    stem_lookup_kernel(const int8_t* __restrict__ board, int board_stride,
+                       const int8_t* __restrict__ player, int player_stride,
+                       const uint4* __restrict__ table, const float* __restrict__ bias,
+                       uint4* __restrict__ out, int64_t n_pix) {
+  constexpr int kVec = kStemCh / 8, kPixPerCta = 256 / kVec;
+  __shared__ uint4 tab[9 * 16 * kVec];  // [9][16][128] bf16, 36,864 B
+  for (int i = threadIdx.x; i < 9 * 16 * kVec; i += blockDim.x) tab[i] = table[i];
+  __syncthreads();
+  const int v = threadIdx.x % kVec, lp = threadIdx.x / kVec;
+  // the loop bound is uniform over the CTA: every lane takes part in the shuffles, `valid`
+  // guards the memory traffic
+  for (int64_t base = (int64_t)blockIdx.x * kPixPerCta; base < n_pix;
+       base += (int64_t)gridDim.x * kPixPerCta) {
+    const int64_t pix = base + lp;
+    const bool valid = pix < n_pix;
+    const int g = valid ? (int)(pix / XQ_NSQ) : 0, s = valid ? (int)(pix - (int64_t)g * XQ_NSQ) : 0;
+    int code = -1;
+    if (valid && v < 9) {
+      const int r = s / 9, c = s - r * 9;
+      const int rr = r + v / 3 - 1, cc = c + v % 3 - 1;
+      if (rr >= 0 && rr <= 9 && cc >= 0 && cc <= 8) {  // else zero padding
+        const int p = board[(size_t)g * board_stride + rr * 9 + cc];
+        // plane index of encode_board: +k -> k-1, -k -> k+6 (k = 1..7)
+        code = p > 0 && p <= 7 ? p - 1 : (p < 0 && p >= -7 ? 6 - p : -1);
+      }
+    }
+    // bias[red][square][c]: the BN-folded bias plus, when red is to move, the side-to-move
+    // plane's weights over the taps that fall on the board (a function of the square only)
+    float acc[8];
+    {
+      const bool red = valid && player[(size_t)g * player_stride] == 1;
+      const float4* bp = reinterpret_cast<const float4*>(bias + ((size_t)(red ? 1 : 0) * XQ_NSQ + s) * kStemCh) + 2 * v;
+      const float4 b0 = bp[0], b1 = bp[1];
+      acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w;
+      acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+    }
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int ch = __shfl_sync(0xffffffffu, code, tap, kVec);  // lane `tap` of this 16-lane segment
+      if (ch >= 0) {
+        const uint4 w = tab[(tap * 16 + ch) * kVec + v];
+        const __nv_bfloat162* pw = reinterpret_cast<const __nv_bfloat162*>(&w);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __bfloat1622float2(pw[k]);
+          acc[2 * k] += f.x;
+          acc[2 * k + 1] += f.y;
+        }
+      }
+    }
+    if (valid) {
+      uint4 o;
+      __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        po[k] = __floats2bfloat162_rn(fmaxf(acc[2 * k], 0.f), fmaxf(acc[2 * k + 1], 0.f));
+      out[pix * kVec + v] = o;
+    }
+  }
+}
+
 // _logits_to_move_probs (neural_network.py:148-169): warp per position.
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
@@ -1030,6 +1098,30 @@ int xq_encode_planes_nhwc16(const int8_t* board, int board_stride, const int8_t*
   encode_nhwc16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       board, board_stride, player, player_stride, (uint4*)planes, n);
   return check_launch("xq_encode_planes_nhwc16");
+}
+
+int xq_stem_lookup_bf16(const int8_t* board, int board_stride, const int8_t* player,
+                        int player_stride, const void* table, const float* bias, void* out,
+                        int channels, int n, void* stream) {
+  if (n == 0) return 0;
+  XQ_REQUIRE(board && player && table && bias && out && n >= 0 && board_stride >= XQ_NSQ &&
+                 player_stride >= 1,
+             "null pointer or bad stride");
+  XQ_REQUIRE(channels == kStemCh, "the kernel is built for ChessNet's 128 first-layer channels");
+  static int sm_count = 0;
+  if (sm_count == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        sm_count <= 0)
+      sm_count = 148;
+  }
+  const int64_t n_pix = (int64_t)n * XQ_NSQ;
+  const int64_t want = (n_pix + 15) / 16;     // 16 squares per 256-thread CTA and iteration
+  const int64_t cap = (int64_t)sm_count * 5;  // persistent: the table is staged once per CTA
+  stem_lookup_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(
+      board, board_stride, player, player_stride, (const uint4*)table, bias, (uint4*)out, n_pix);
+  return check_launch("xq_stem_lookup_bf16");
 }
 
 int xq_bias_residual_relu_bf16(const void* y, const void* x, const void* bias, void* out,

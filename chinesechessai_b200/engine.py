@@ -199,6 +199,23 @@ def encode_planes_nhwc16(board: torch.Tensor, player: torch.Tensor) -> torch.Ten
     return out
 
 
+def stem_lookup(board: torch.Tensor, player: torch.Tensor, table: torch.Tensor, bias: torch.Tensor
+                ) -> torch.Tensor:
+    """encode_board + conv1/bn1/ReLU of ChessNet in one kernel (xq_stem_lookup_bf16): the planes are
+    one-hot, so the first convolution is a sum of weight columns picked by the neighbouring
+    pieces.  table bf16 [9,16,C], bias float32 [C] -> bf16 [n,C,10,9] channels-last."""
+    lib = _lib.load()
+    n, ch = board.shape[0], table.shape[2]
+    assert table.dtype == torch.bfloat16 and table.shape[:2] == (9, 16) and table.is_contiguous()
+    assert bias.dtype == torch.float32 and bias.shape == (2, 90, ch) and bias.is_contiguous()
+    out = torch.empty((n, ch, 10, 9), dtype=torch.bfloat16, device=board.device,
+                      memory_format=torch.channels_last)
+    with torch.cuda.device(board.device):
+        check(lib.xq_stem_lookup_bf16(_ptr(board), board.stride(0), _ptr(player), player.stride(0),
+                                      _ptr(table), _ptr(bias), _ptr(out), ch, n, _stream()))
+    return out
+
+
 def policy_priors(logits: torch.Tensor, moves: torch.Tensor, n_moves: torch.Tensor,
                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """ChessNet._logits_to_move_probs (neural_network.py:148-169) for a batch."""

@@ -14,7 +14,7 @@ import torch
 from . import _lib
 from ._lib import BOARD_STRIDE, MAX_MOVES, check
 from .engine import (_ptr, _stream, bias_residual_relu, encode_planes, encode_planes_nhwc16,
-                     policy_priors)
+                     policy_priors, stem_lookup)
 
 WAVE = 8  # self_play.py:101
 
@@ -91,6 +91,25 @@ class _FoldedNet(torch.nn.Module):
         self.to(dtype=dtype, memory_format=torch.channels_last)
         self.fused = False
         self.own_epilogue = dtype == torch.bfloat16
+        # encode_board + conv1/bn1/ReLU as a lookup (xq_stem_lookup_bf16): table[tap][plane][c_out]
+        # from the same bf16 weights the cuDNN stem uses
+        self.stem_table = None
+        st = self.stem
+        if (dtype == torch.bfloat16 and self.in_channels == 16 and tuple(st.kernel_size) == (3, 3) and
+                tuple(st.stride) == (1, 1) and tuple(st.padding) == (1, 1) and st.out_channels == 128 and
+                st.weight.is_cuda):
+            with torch.no_grad():
+                self.stem_table = st.weight.detach().permute(2, 3, 1, 0).reshape(9, 16, st.out_channels).contiguous()
+                # bias per (side to move, square): plane 14 is all ones when red moves, so its
+                # taps that fall on the board add a square-dependent constant
+                b = st.bias.detach().float()
+                w14 = self.stem_table[:, 14].float()                       # [9, C]
+                on = torch.zeros((90, 9), device=b.device)
+                for sq in range(90):
+                    for tap in range(9):
+                        rr, cc = sq // 9 + tap // 3 - 1, sq % 9 + tap % 3 - 1
+                        on[sq, tap] = 1.0 if 0 <= rr <= 9 and 0 <= cc <= 8 else 0.0
+                self.stem_bias = torch.stack([b[None, :].expand(90, -1), b[None, :] + on @ w14]).contiguous()
         if next(self.parameters()).is_cuda:
             try:  # probe the fused cuDNN entry points once
                 x = torch.zeros((2, self.in_channels, 10, 9), dtype=dtype, device=fc.weight.device).contiguous(
@@ -106,9 +125,22 @@ class _FoldedNet(torch.nn.Module):
         return torch.cudnn_convolution_relu(x, conv.weight, conv.bias, conv.stride, conv.padding,
                                             conv.dilation, conv.groups)
 
+    def forward_boards(self, board, player):
+        """The network on raw positions (int8 boards + side to move): the stem runs as the fused
+        lookup kernel, the rest as in forward()."""
+        if self.stem_table is None or not self.fused:
+            return self.forward(encode_planes_nhwc16(board, player) if self.in_channels == 16 else
+                                encode_planes(board, player, dtype=self.stem.weight.dtype).contiguous(
+                                    memory_format=torch.channels_last))
+        return self._trunk(stem_lookup(board, player, self.stem_table, self.stem_bias))
+
     def forward(self, x):
         if self.fused:
-            x = self._cr(self.stem, x)
+            return self._trunk(self._cr(self.stem, x))
+        return self._trunk(torch.relu(self.stem(x)))
+
+    def _trunk(self, x):
+        if self.fused:
             for c1, c2 in self.blocks:
                 y = self._cr(c1, x)
                 if self.own_epilogue:  # plain conv + one fused HBM pass (our kernel)
@@ -120,7 +152,6 @@ class _FoldedNet(torch.nn.Module):
             p = self._cr(self.policy_conv, x)
             v = self._cr(self.value_conv, x)
         else:
-            x = torch.relu(self.stem(x))
             for c1, c2 in self.blocks:
                 x = torch.relu(c2(torch.relu(c1(x))) + x)
             p = torch.relu(self.policy_conv(x))
@@ -156,12 +187,7 @@ class NetEvaluator:
         else:
             if self._fast is None:
                 self._fast = _FoldedNet(self.net, self.dtype)
-            if self._fast.in_channels == 16:
-                planes = encode_planes_nhwc16(leaf_board, leaf_player)
-            else:
-                planes = encode_planes(leaf_board, leaf_player, dtype=self.dtype).contiguous(
-                    memory_format=torch.channels_last)
-            logits, value = self._fast(planes)
+            logits, value = self._fast.forward_boards(leaf_board, leaf_player)
         if logits.stride(1) != 1:
             logits = logits.contiguous()
         if logits.dtype not in (torch.float32, torch.bfloat16):

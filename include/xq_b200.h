@@ -196,6 +196,21 @@ int xq_policy_priors(const void *logits, int logits_bf16, int logits_stride,
 int xq_bias_residual_relu_bf16(const void *y, const void *x, const void *bias, void *out,
                                int64_t n_elems, int channels, void *stream);
 
+/* encode_board (neural_network.py:128-146) + the network's first layer conv1 -> bn1 -> ReLU
+ * (neural_network.py:25-27,:60) in ONE kernel for the bf16 inference copy.  The 15 input planes
+ * are one-hot, so the 3x3 convolution at a square is a SUM of weight columns selected by the
+ * pieces on its 9 neighbours: no planes tensor and no GEMM; float32 accumulation of the same
+ * bf16 weights cuDNN would use.  (A tensor-core form of the same idea, mma.sync m16n8k16 with
+ * the one-hot operand built in registers, was measured slower: DESIGN.md section 7.)
+ * table: bf16 [9 taps][16 input channels][channels] with tap = kh*3+kw of the BN-folded
+ * 3x3/stride 1/pad 1 weight (input channel 15 unused); bias: float32 [2][90][channels] =
+ * the folded bias for black to move and, for red to move ([1]), the bias plus the
+ * side-to-move plane's weights summed over the taps that lie on the board at that square;
+ * out: bf16 [n][10][9][channels] (channels-last).  channels == 128 (config.py:33). */
+int xq_stem_lookup_bf16(const int8_t *board, int board_stride, const int8_t *player,
+                        int player_stride, const void *table, const float *bias, void *out,
+                        int channels, int n, void *stream);
+
 /* ---- MCTS: self_play.py:19-175 ------------------------------------------- */
 /* One flat node pool per game ("tree"), caller-allocated device memory of
  * xq_mcts_tree_bytes(num_simulations) bytes per game (16-byte aligned; every

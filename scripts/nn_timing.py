@@ -29,6 +29,12 @@ with torch.no_grad():
             err_p = (out[0][:, :8100].float() - ref[0]).abs().max().item()
             err_v = (out[1].float() - ref[1]).abs().max().item()
             agree = (out[0][:, :8100].float().argmax(1) == ref[0].argmax(1)).float().mean().item()
+            if dt == torch.bfloat16 and f.stem_table is not None:
+                from chinesechessai_b200.engine import BoardBatch
+                bb = BoardBatch(n); bb.playout(1, 8)
+                plr = bb.meta[:, 0].view(torch.int8)
+                tb = timeit(lambda: f.forward_boards(bb.board, plr))
+                print(f"   forward_boards (fused encode+stem lookup): {tb:.3f} ms -> {n*263.2e6/tb/1e9:.0f} TFLOP/s")
             t = timeit(lambda: f(xb))
             print(f"n={n} {dt} fused={f.fused}: {t:.3f} ms  -> {n*263.2e6/t/1e9:.0f} TFLOP/s  max|dlogit|={err_p:.3f} max|dv|={err_v:.4f} argmax agree={agree:.3f}")
             if dt == torch.bfloat16:

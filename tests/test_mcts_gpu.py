@@ -193,7 +193,19 @@ def test_folded_net_matches_module(mods):
         f = mcts._FoldedNet(net, torch.bfloat16)
         assert f.fused and f.own_epilogue
         assert f.in_channels == 16  # zero-padded stem fed by the channels-last encode kernel
-        p, v = f(eng.encode_planes_nhwc16(bb.board, bb.meta[:, 0].view(torch.int8)))
+        pl = bb.meta[:, 0].view(torch.int8)
+        p, v = f(eng.encode_planes_nhwc16(bb.board, pl))
+        # the production entry: raw boards in, stem = fused encode + conv1 lookup kernel
+        assert f.stem_table is not None
+        p2, v2 = f.forward_boards(bb.board, pl)
+        assert float((p2.float() - p.float()).abs().max()) < 0.05 and float((v2.float() - v.float()).abs().max()) < 0.02
+        a = f._cr(f.stem, eng.encode_planes_nhwc16(bb.board, pl)).float()
+        b = eng.stem_lookup(bb.board, pl, f.stem_table, f.stem_bias)
+        assert b.shape == a.shape and b.is_contiguous(memory_format=torch.channels_last)
+        d = (a - b.float()).abs()
+        # same bf16 weights, float32 accumulation in a different order: at most one bf16 ulp apart
+        assert float((d / a.abs().clamp(min=1.0)).max()) < 2 ** -7 and float((d > 0).float().mean()) < 0.05
+        p, v = p2, v2
     assert p.shape == (256, 8192) and float(p[:, 8100:].abs().max()) == 0.0
     assert float((p[:, :8100].float() - ref_p).abs().max()) < 0.15
     assert float((v.float() - ref_v).abs().max()) < 0.05
