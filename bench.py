@@ -319,8 +319,11 @@ def measure_selfplay_iteration(torch, dev, games=MCTS_GAMES, sims=MCTS_SIMS):
     from chinesechessai_b200.self_play import BatchedSelfPlay
     torch.manual_seed(0)
     net = ChessNet().to(dev).eval()
+    # one complete untimed iteration first: allocator growth, library handles and the first-call
+    # costs of the sample-shaping ops are warm-up, like the W warm-up steps of the main leg
     warm = BatchedSelfPlay(net, games, sims, temperature=1.0, device=dev, net_dtype=torch.bfloat16, seed=1)
-    warm.play(2, check_done=False)
+    warm.play()
+    training_tensors(warm)
     del warm
     torch.cuda.synchronize()
     t0 = time.perf_counter()

@@ -73,6 +73,8 @@ SIGNATURES = {
     "xq_mcts_backup": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "xq_mcts_root_visits": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp]),
     "xq_sample_moves": (_i, [_vp, _vp, _vp, C.c_double, _u64, _u32, _u32, _vp, _i, _vp]),
+    "xq_selfplay_commit": (_i, [_vp] * 15 + [_i, _vp]),
+    "xq_selfplay_finish": (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
     "xq_hash_eval": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp]),
 }
 

@@ -391,6 +391,45 @@ __global__ void __launch_bounds__(256)
   chosen[g] = (int16_t)pick;
 }
 
+// Game-loop glue of one ply (see xq_selfplay_commit / xq_selfplay_finish in the header):
+// one CTA of XQ_MAX_MOVES threads per game.
+__global__ void __launch_bounds__(XQ_MAX_MOVES)
+    selfplay_commit_kernel(const int16_t* __restrict__ root_moves, const int32_t* __restrict__ root_visits,
+                           const int16_t* __restrict__ root_n, const int16_t* __restrict__ chosen,
+                           const int8_t* __restrict__ board, const xq_meta* __restrict__ meta,
+                           int8_t* __restrict__ rec_board, int8_t* __restrict__ rec_player,
+                           int16_t* __restrict__ rec_moves, int32_t* __restrict__ rec_visits,
+                           int16_t* __restrict__ rec_n, uint8_t* __restrict__ rec_played,
+                           int16_t* __restrict__ rec_move, int16_t* __restrict__ move,
+                           int32_t* __restrict__ any_active) {
+  const int g = blockIdx.x, k = threadIdx.x;
+  const size_t row = (size_t)g * XQ_MAX_MOVES;
+  rec_moves[row + k] = root_moves[row + k];
+  rec_visits[row + k] = root_visits[row + k];
+  if (k < XQ_NSQ) rec_board[(size_t)g * XQ_NSQ + k] = board[(size_t)g * XQ_BOARD_STRIDE + k];
+  if (k == 0) {
+    const int c = chosen[g];
+    const int16_t mv = c >= 0 ? root_moves[row + c] : (int16_t)-1;
+    rec_n[g] = root_n[g];
+    rec_player[g] = meta[g].player;
+    rec_played[g] = c >= 0 ? 1 : 0;
+    rec_move[g] = mv;
+    move[g] = mv;
+    if (g == 0) *any_active = 0;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    selfplay_finish_kernel(const int16_t* __restrict__ move, const uint8_t* __restrict__ step_flags,
+                           uint8_t* __restrict__ active, int32_t* __restrict__ any_active, int n) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  if (!active[g]) return;
+  const bool on = move[g] >= 0 && !(step_flags[g] & XQ_STEP_DONE);
+  active[g] = on ? 1 : 0;
+  if (on) *any_active = 1;  // same value from every writer
+}
+
 // Mirror of the oracle's deterministic evaluator (order-independent arithmetic).
 __global__ void __launch_bounds__(kThreadsM)
     hash_eval_kernel(const int8_t* __restrict__ board, int board_stride,
@@ -506,6 +545,32 @@ int xq_sample_moves(const int32_t* visits, const int16_t* n_children, const uint
   sample_moves_kernel<<<(n_games + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
       visits, n_children, active, temperature, seed, first_game_id, ply, chosen, n_games);
   return check_launch("xq_sample_moves");
+}
+
+int xq_selfplay_commit(const int16_t* root_moves, const int32_t* root_visits, const int16_t* root_n,
+                       const int16_t* chosen, const int8_t* board, const xq_meta* meta,
+                       int8_t* rec_board, int8_t* rec_player, int16_t* rec_moves, int32_t* rec_visits,
+                       int16_t* rec_n, uint8_t* rec_played, int16_t* rec_move, int16_t* move,
+                       int32_t* any_active, int n_games, void* stream) {
+  if (n_games == 0) return 0;
+  XQM_REQUIRE(root_moves && root_visits && root_n && chosen && board && meta && rec_board &&
+                  rec_player && rec_moves && rec_visits && rec_n && rec_played && rec_move && move &&
+                  any_active && n_games > 0,
+              "null pointer or non-positive size");
+  selfplay_commit_kernel<<<n_games, XQ_MAX_MOVES, 0, (cudaStream_t)stream>>>(
+      root_moves, root_visits, root_n, chosen, board, meta, rec_board, rec_player, rec_moves,
+      rec_visits, rec_n, rec_played, rec_move, move, any_active);
+  return check_launch("xq_selfplay_commit");
+}
+
+int xq_selfplay_finish(const int16_t* move, const uint8_t* step_flags, uint8_t* active,
+                       int32_t* any_active, int n_games, void* stream) {
+  if (n_games == 0) return 0;
+  XQM_REQUIRE(move && step_flags && active && any_active && n_games > 0,
+              "null pointer or non-positive size");
+  selfplay_finish_kernel<<<(n_games + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      move, step_flags, active, any_active, n_games);
+  return check_launch("xq_selfplay_finish");
 }
 
 int xq_hash_eval(const int8_t* board, int board_stride, const int8_t* player, const int16_t* moves,

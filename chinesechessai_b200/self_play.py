@@ -201,7 +201,11 @@ class BatchedSelfPlay:
         self.rec_move = torch.full((P, self.n), -1, dtype=torch.int16, device=d)
         self.rec_played = torch.zeros((P, self.n), dtype=torch.bool, device=d)
         self.plies = 0
-        self.done = torch.zeros(self.n, dtype=torch.bool, device=d)
+        # game-loop state on the device: active[g] = 1 while game g is running, the move about to
+        # be played, and a one-word "any game still running" flag (xq_selfplay_commit / _finish)
+        self.active = torch.ones(self.n, dtype=torch.uint8, device=d)
+        self.move = torch.full((self.n,), -1, dtype=torch.int16, device=d)
+        self.any_active = torch.ones(1, dtype=torch.int32, device=d)
         # Small batches are launch-bound (about 60 launches per ply against ~1 ms of device
         # work up to a few hundred games): the whole search of a ply — init, every wave's
         # select / encode / forward / priors / backup, root visits — is captured once as a CUDA
@@ -211,20 +215,23 @@ class BatchedSelfPlay:
             else bool(use_graph)
         self._graph = None
         self._graph_key = None
-        self._active = torch.ones(self.n, dtype=torch.uint8, device=d)
 
-    def _search(self, active: torch.Tensor):
+    @property
+    def done(self) -> torch.Tensor:
+        return self.active == 0
+
+    def _search(self):
+        active = self.active
         if not self.use_graph or self.n == 0:
             return self._search_eager(active)
-        self._active.copy_(active)
         key = (getattr(self.eval_red, "version", 0), getattr(self.eval_black, "version", 0))
         if self._graph is None or self._graph_key != key:
-            self._search_eager(self._active)  # warm-up: library handles, workspaces, folded net
+            self._search_eager(active)  # warm-up: library handles, workspaces, folded net
             torch.cuda.current_stream(self.device).synchronize()
             graph = torch.cuda.CUDAGraph()
             try:
                 with torch.cuda.graph(graph):
-                    self._search_eager(self._active)
+                    self._search_eager(active)
             except Exception as exc:  # an evaluator that cannot be captured (host syncs, ...)
                 import warnings
                 warnings.warn(f"CUDA-graph capture of the search failed ({exc}); running eagerly")
@@ -259,51 +266,49 @@ class BatchedSelfPlay:
         """Advance every unfinished game by up to ``max_plies`` further plies (the reference's
         cap of MAX_MOVES plies per game applies to the total).  ``check_done=False`` skips the
         per-ply "all games over?" host read (benchmarks that time a fixed number of plies)."""
-        b = self.boards
-        done = self.done
-        # "all games over?" is read from pinned memory two plies late, so the host keeps
+        b, lib, n = self.boards, self.lib, self.n
+        # "any game still running?" is read from pinned memory two plies late, so the host keeps
         # enqueueing ahead of the device instead of draining it every ply; the plies launched
         # past the end are no-ops (every game inactive) and are not counted
         lag = 2
         first = self.plies
-        flag = torch.zeros((MAX_PLIES,), dtype=torch.bool).pin_memory() if check_done else None
+        flag = torch.ones((MAX_PLIES,), dtype=torch.int32).pin_memory() if check_done else None
         events = {}
         for ply in range(self.plies, min(MAX_PLIES, self.plies + max_plies)):
-            active = (~done).to(torch.uint8)
-            mv, vis, nc = self._search(active)
-            # self_play.py:219-243 on device; idx = -1: game over / no legal move / empty search
-            check(self.lib.xq_sample_moves(_ptr(vis), _ptr(nc), _ptr(active), self.temperature,
-                                           self.seed, self.first_game_id, ply, _ptr(self.chosen),
-                                           self.n, _stream()))
-            live = self.chosen >= 0
-            move = mv.gather(1, self.chosen.clamp(min=0).to(torch.int64)[:, None]).squeeze(1)
-            move = torch.where(live, move, torch.full_like(move, -1))
-            self.rec_board[ply].copy_(b.board[:, :90])
-            self.rec_player[ply].copy_(b.meta[:, 0].view(torch.int8))
-            self.rec_moves[ply].copy_(mv)
-            self.rec_visits[ply].copy_(vis)
-            self.rec_n[ply].copy_(nc)
-            self.rec_played[ply].copy_(live)
-            self.rec_move[ply].copy_(move)
-            reward, flags = b.step(move.contiguous())
-            self.rec_reward[ply].copy_(reward)
-            done = done | ~live | ((flags & 1) != 0)
-            self.done = done
+            mv, vis, nc = self._search()
+            with torch.cuda.device(self.device):
+                st = _stream()
+                # self_play.py:219-243 on device; idx = -1: game over / no legal move / empty search
+                check(lib.xq_sample_moves(_ptr(vis), _ptr(nc), _ptr(self.active), self.temperature,
+                                          self.seed, self.first_game_id, ply, _ptr(self.chosen), n, st))
+                # :229-231 sample capture into this ply's rows + the move to play
+                check(lib.xq_selfplay_commit(
+                    _ptr(mv), _ptr(vis), _ptr(nc), _ptr(self.chosen), _ptr(b.board), _ptr(b.meta),
+                    _ptr(self.rec_board[ply]), _ptr(self.rec_player[ply]), _ptr(self.rec_moves[ply]),
+                    _ptr(self.rec_visits[ply]), _ptr(self.rec_n[ply]), _ptr(self.rec_played[ply]),
+                    _ptr(self.rec_move[ply]), _ptr(self.move), _ptr(self.any_active), n, st))
+                # :245 make_move; the step reward goes straight into this ply's row
+                check(lib.xq_step(_ptr(b.board), _ptr(b.meta), _ptr(b.pos_hist), b.hist_cap,
+                                  _ptr(self.move), _ptr(self.rec_reward[ply]), _ptr(b.flags), None, None,
+                                  n, st))
+                # :254-255 retire finished games
+                check(lib.xq_selfplay_finish(_ptr(self.move), _ptr(b.flags), _ptr(self.active),
+                                             _ptr(self.any_active), n, st))
             self.plies = ply + 1
             if check_done:
-                flag[ply].copy_(done.all(), non_blocking=True)
+                flag[ply:ply + 1].copy_(self.any_active, non_blocking=True)
                 events[ply] = torch.cuda.Event()
                 events[ply].record()
                 q = ply - lag
                 if q >= first:
                     events.pop(q).synchronize()
-                    if bool(flag[q]):
+                    if int(flag[q]) == 0:
                         self.plies = q + 1
                         break
         if check_done:  # the last `lag` plies were not looked at inside the loop
             for q in sorted(events):
                 events[q].synchronize()
-                if bool(flag[q]):
+                if int(flag[q]) == 0:
                     self.plies = min(self.plies, q + 1)
                     break
 

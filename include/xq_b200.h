@@ -265,6 +265,26 @@ int xq_sample_moves(const int32_t *visits, const int16_t *n_children, const uint
                     double temperature, uint64_t seed, uint32_t first_game_id, uint32_t ply,
                     int16_t *chosen, int n_games, void *stream);
 
+/* The rest of one ply of the batched game loop (self_play.py:203-256), so that a ply is
+ * search + 4 launches instead of ~25 framework launches:
+ * xq_selfplay_commit records what the reference appends to game_data (:229-231) — the board
+ * before the move, the side to move, the root's move list and visit counts — into the caller's
+ * per-ply rows, resolves chosen[g] to the move to play (move[g] = -1 for a game that is
+ * inactive or has no legal move) and clears *any_active;
+ * xq_selfplay_finish, called after xq_step(move), retires games: active[g] stays 1 only if
+ * the game was stepped and the step did not end it (:254-255), and *any_active is set to 1 if
+ * any game is still running.
+ * rec_board int8[n][90], rec_player int8[n], rec_moves int16[n][XQ_MAX_MOVES],
+ * rec_visits int32[n][XQ_MAX_MOVES], rec_n int16[n], rec_played uint8[n], rec_move int16[n]. */
+int xq_selfplay_commit(const int16_t *root_moves, const int32_t *root_visits,
+                       const int16_t *root_n, const int16_t *chosen, const int8_t *board,
+                       const xq_meta *meta, int8_t *rec_board, int8_t *rec_player,
+                       int16_t *rec_moves, int32_t *rec_visits, int16_t *rec_n,
+                       uint8_t *rec_played, int16_t *rec_move, int16_t *move,
+                       int32_t *any_active, int n_games, void *stream);
+int xq_selfplay_finish(const int16_t *move, const uint8_t *step_flags, uint8_t *active,
+                       int32_t *any_active, int n_games, void *stream);
+
 /* Deterministic test evaluator (hashed or flat priors, hashed value) identical
  * to the oracle's, so MCTS parity can be checked at batch scale without a net. */
 int xq_hash_eval(const int8_t *board, int board_stride, const int8_t *player,
