@@ -346,49 +346,78 @@ __global__ void __launch_bounds__(kThreadsM)
   if (lane == 0) n_children[g] = (int16_t)n;
 }
 
-// Temperature sampling of the move to play (self_play.py:219-243), one thread per game.
+// Temperature sampling of the move to play (self_play.py:219-243), one warp per game: the lanes
+// load the visit counts coalesced and do the expensive part (pow, float64 division) in parallel;
+// the two float64 sums run in index order, as numpy's sum/cumsum do, on values passed round by
+// shuffle — every lane computes the same sums, so the early exit is warp-uniform.
 __global__ void __launch_bounds__(256)
     sample_moves_kernel(const int32_t* __restrict__ visits, const int16_t* __restrict__ n_children,
                         const uint8_t* __restrict__ active, double temperature, uint64_t seed,
                         uint32_t first_game_id, uint32_t ply, int16_t* __restrict__ chosen,
                         int n_games) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (g >= n_games) return;
-  const int n = n_children[g];
+  constexpr int kPer = XQ_MAX_MOVES / 32;
+  const int n = min((int)n_children[g], XQ_MAX_MOVES);
   if (n <= 0 || (active && !active[g])) {
-    chosen[g] = -1;
+    if (lane == 0) chosen[g] = -1;
     return;
   }
   const int32_t* v = visits + (size_t)g * XQ_MAX_MOVES;
+  int cnt[kPer];
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) cnt[j] = 32 * j + lane < n ? v[32 * j + lane] : 0;
   uint32_t x[4];
   philox4x32(first_game_id + (uint32_t)g, ply, 1u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), x);
   int pick = 0;
   if (temperature < 0.01) {  // :224-227, np.argmax = first maximum
-    int best = v[0];
-    for (int i = 1; i < n; ++i)
-      if (v[i] > best) { best = v[i]; pick = i; }
+    int best = -1, best_i = 0;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j)
+      if (32 * j + lane < n && cnt[j] > best) { best = cnt[j]; best_i = 32 * j + lane; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const int ob = __shfl_xor_sync(0xffffffffu, best, o), oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+      if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
+    }
+    pick = best_i;
   } else {
     const double inv_t = 1.0 / temperature;
     // counts ** (1/T): exact shortcuts for the reference's two temperatures (trainer.py:166)
-    auto weight = [&](int c) -> double {
-      const double x = (double)c;
-      return inv_t == 1.0 ? x : (inv_t == 2.0 ? __dmul_rn(x, x) : pow(x, inv_t));
-    };
+    double w[kPer];
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      const double c = (double)cnt[j];
+      w[j] = inv_t == 1.0 ? c : (inv_t == 2.0 ? __dmul_rn(c, c) : pow(c, inv_t));
+    }
     double total = 0.0;
-    for (int i = 0; i < n; ++i) total = __dadd_rn(total, weight(v[i]));
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      if (32 * j >= n) break;
+#pragma unroll 1
+      for (int l = 0; l < 32 && 32 * j + l < n; ++l) total = __dadd_rn(total, __shfl_sync(0xffffffffu, w[j], l));
+    }
     if (!(total > 0.0)) {  // all-zero counts (n_sims <= 8): the reference divides by zero here
       pick = (int)(x[0] % (uint32_t)n);
     } else {
       const double u = (double)((((uint64_t)x[0] << 32) | x[1]) >> 11) * (1.0 / 9007199254740992.0);
+#pragma unroll
+      for (int j = 0; j < kPer; ++j) w[j] = __ddiv_rn(w[j], total);
       double cdf = 0.0;
       pick = n - 1;
-      for (int i = 0; i < n; ++i) {  // searchsorted(cumsum(p), u, side="right")
-        cdf = __dadd_rn(cdf, __ddiv_rn(weight(v[i]), total));
-        if (cdf > u) { pick = i; break; }
+      bool found = false;
+#pragma unroll
+      for (int j = 0; j < kPer; ++j) {  // searchsorted(cumsum(p), u, side="right")
+        if (found || 32 * j >= n) break;
+#pragma unroll 1
+        for (int l = 0; l < 32 && 32 * j + l < n; ++l) {
+          cdf = __dadd_rn(cdf, __shfl_sync(0xffffffffu, w[j], l));
+          if (cdf > u) { pick = 32 * j + l; found = true; break; }
+        }
       }
     }
   }
-  chosen[g] = (int16_t)pick;
+  if (lane == 0) chosen[g] = (int16_t)pick;
 }
 
 // Game-loop glue of one ply (see xq_selfplay_commit / xq_selfplay_finish in the header):
@@ -542,7 +571,7 @@ int xq_sample_moves(const int32_t* visits, const int16_t* n_children, const uint
   if (n_games == 0) return 0;
   XQM_REQUIRE(visits && n_children && chosen && n_games > 0, "null pointer or non-positive size");
   XQM_REQUIRE(temperature >= 0.0, "negative temperature");
-  sample_moves_kernel<<<(n_games + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+  sample_moves_kernel<<<(n_games + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
       visits, n_children, active, temperature, seed, first_game_id, ply, chosen, n_games);
   return check_launch("xq_sample_moves");
 }
