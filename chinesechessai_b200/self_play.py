@@ -22,8 +22,9 @@ from .config import MAX_MOVES as MAX_PLIES, MCTS_SIMULATIONS
 from .engine import BoardBatch, _ptr, _stream, pack_move, unpack_move
 from .mcts import WAVE, BatchedMCTS, HashEvaluator, NetEvaluator
 
-GRAPH_MAX_GAMES = 2048  # measured (scripts/single_game_latency.py): 4.5x at 1-64 games, 1.6x at 1,024,
-                        # 1.1x at 2,048; beyond that a ply is device-bound
+GRAPH_MAX_GAMES = 4096  # measured (scripts/single_game_latency.py): 4x at 1-64
+                        # games, 1.3x at 1,024, 1.05x at 4,096; at 16,384 games x 50 sims the
+                        # eager loop is as fast (the ply is 30 ms of kernels)
 
 Move = Tuple[int, int, int, int]
 
