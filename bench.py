@@ -296,6 +296,7 @@ def measure_mcts(torch, dev, plies_timed=6, games=MCTS_GAMES, sims=MCTS_SIMS, la
     b.record()
     torch.cuda.synchronize()
     ms = a.elapsed_time(b)
+    graph_launches = plies_timed * sp.graph_kernels if sp.use_graph else 0
     played = int(sp.rec_played[p0:sp.plies].sum())
     sims = played * MCTS_SIMS
     waves = (MCTS_SIMS + 7) // 8
@@ -303,7 +304,9 @@ def measure_mcts(torch, dev, plies_timed=6, games=MCTS_GAMES, sims=MCTS_SIMS, la
     return {"metric": "MCTS sims/sec", "value": sims / (ms * 1e-3), "unit": "sims/s",
             "config": {"workload": f"{label}: {MCTS_GAMES} concurrent games, {MCTS_SIMS} sims/move, "
                                    f"random-init ChessNet, T=1.0, {MCTS_OPENING_PLIES} random opening plies",
-                       "plies_timed": plies_timed, "nn_dtype": "bf16 autocast (reference: fp32)"},
+                       "plies_timed": plies_timed, "nn_dtype": "bf16 autocast (reference: fp32)",
+                       "cuda_graph": bool(sp.use_graph)},
+            "xq_kernels_replayed_by_graph": graph_launches,
             "ms_per_ply": ms / plies_timed, "unique_leaf_evals_per_s": evals / (ms * 1e-3),
             "roofline": {"bound": "tensor", "achieved": evals / (ms * 1e-3) * FLOP_PER_LEAF_EVAL / 1e12,
                          "unit": "TFLOP/s", "flop_per_leaf_eval": FLOP_PER_LEAF_EVAL}}
@@ -571,7 +574,7 @@ def run_ours(args):
         mc["roofline"]["peak"] = tf_peak
         mc["roofline"]["frac"] = mc["roofline"]["achieved"] / tf_peak
         mc["tree_only"] = measure_tree_only(torch, dev, MCTS_GAMES, MCTS_SIMS)
-        mc["gpu_launches"] = int(lib.xq_launch_count() - l0)
+        mc["gpu_launches"] = int(lib.xq_launch_count() - l0) + int(mc.get("xq_kernels_replayed_by_graph", 0))
         out["mcts"] = mc
         if not args.no_cfg4:
             m4 = measure_mcts(torch, dev, plies_timed=2, games=16384, sims=50, label="cfg4 (one GPU's shard)")

@@ -216,6 +216,8 @@ class BatchedSelfPlay:
             else bool(use_graph)
         self._graph = None
         self._graph_key = None
+        self.graph_kernels = 0   # xq:: kernel launches captured in the graph
+        self.graph_replays = 0   # (the library's launch counter only sees the capture)
 
     @property
     def done(self) -> torch.Tensor:
@@ -230,6 +232,7 @@ class BatchedSelfPlay:
             self._search_eager(active)  # warm-up: library handles, workspaces, folded net
             torch.cuda.current_stream(self.device).synchronize()
             graph = torch.cuda.CUDAGraph()
+            c0 = self.lib.xq_launch_count()
             try:
                 with torch.cuda.graph(graph):
                     self._search_eager(active)
@@ -239,7 +242,9 @@ class BatchedSelfPlay:
                 self.use_graph = False
                 return self._search_eager(active)
             self._graph, self._graph_key = graph, key
+            self.graph_kernels = int(self.lib.xq_launch_count() - c0)  # xq:: kernels per replay
         self._graph.replay()
+        self.graph_replays += 1
         m = self.mcts
         return m.root_moves, m.root_visits, m.root_n
 
