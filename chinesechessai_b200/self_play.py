@@ -22,9 +22,10 @@ from .config import MAX_MOVES as MAX_PLIES, MCTS_SIMULATIONS
 from .engine import BoardBatch, _ptr, _stream, pack_move, unpack_move
 from .mcts import WAVE, BatchedMCTS, HashEvaluator, NetEvaluator
 
-GRAPH_MAX_GAMES = 4096  # measured (scripts/single_game_latency.py): 4x at 1-64
-                        # games, 1.3x at 1,024, 1.05x at 4,096; at 16,384 games x 50 sims the
-                        # eager loop is as fast (the ply is 30 ms of kernels)
+GRAPH_MAX_GAMES = 1024  # measured (scripts/single_game_latency.py): a ply is 4x
+                        # faster at 1-64 games, 1.3x at 1,024, 1.05x at 4,096 — but the capture
+                        # costs ~10 ms per BatchedSelfPlay instance, which a 70-ply batch only
+                        # earns back below ~1,000 games
 
 Move = Tuple[int, int, int, int]
 
