@@ -104,11 +104,8 @@ class _FoldedNet(torch.nn.Module):
                 # taps that fall on the board add a square-dependent constant
                 b = st.bias.detach().float()
                 w14 = self.stem_table[:, 14].float()                       # [9, C]
-                on = torch.zeros((90, 9), device=b.device)
-                for sq in range(90):
-                    for tap in range(9):
-                        rr, cc = sq // 9 + tap // 3 - 1, sq % 9 + tap % 3 - 1
-                        on[sq, tap] = 1.0 if 0 <= rr <= 9 and 0 <= cc <= 8 else 0.0
+                on = torch.tensor([[1.0 if 0 <= sq // 9 + tap // 3 - 1 <= 9 and 0 <= sq % 9 + tap % 3 - 1 <= 8
+                                    else 0.0 for tap in range(9)] for sq in range(90)], device=b.device)
                 self.stem_bias = torch.stack([b[None, :].expand(90, -1), b[None, :] + on @ w14]).contiguous()
         if next(self.parameters()).is_cuda:
             try:  # probe the fused cuDNN entry points once
