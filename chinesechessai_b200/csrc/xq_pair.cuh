@@ -1,15 +1,22 @@
-// xq_pair.cuh — two lanes per board for the fused playout.
+// xq_pair.cuh — two lanes per board: fused playout, xq_step and xq_legal_moves on large batches.
 //
 // The thread-per-board engine (xq_tpb.cuh) issues the fewest instructions per ply, but at the
 // cfg 2 size (65,536 boards = 2,048 warps = 3.5 warps per scheduler) it is bound by dependent-
 // issue latency: issue-active 52 % (profiles/).  Here two ADJACENT lanes share one board slab and
-// split the divisible work of a ply — candidate generation and legality by halves of the own-
-// piece list, the probe round (check test + king moves) by alternating items, the history scan
-// and the digest sum by halves — so the same batch runs as twice as many warps with about half
-// the dependent chain per lane.  Bookkeeping (make_move's scalar part, the pick) is replicated
-// in both lanes' registers; lane 0 writes the slab.  Lane 0's moves sit at w.mv[0..n0) going up,
-// lane 1's at w.mv[127], w.mv[126], ... going down: the legal list in the reference's order is
-// lane 0's part followed by lane 1's, and is never merged physically (pair_move_at).
+// split the divisible work of a ply, so the same batch runs as twice as many warps with about
+// half the dependent chain per lane:
+//   * own-piece scan: lane 0 the squares of words 0..11, lane 1 words 12..22 (four squares per
+//     32-bit load, branch-free append), each into its half of the own list;
+//   * candidate generation: by halves of the piece list; lane 0's candidates grow up from
+//     mv[0], lane 1's down from mv[127]; a quiet ray is one descriptor expanded by a flat pass;
+//   * legality: suicide_fast over EQUAL halves of the whole candidate list (verdicts marked in
+//     place), the probe round (check test + king moves, one attacked() call site) by alternating
+//     items;
+//   * one compaction pass per lane that also sums the digest's list term; the repetition scan
+//     by alternating history entries.
+// Bookkeeping (make_move's scalar part, the pick) is replicated in both lanes' registers; lane 0
+// writes the slab.  The legal list in the reference's order is lane 0's run followed by lane
+// 1's and is never merged physically (pair_move_at).  Pair-mask shuffles and __syncwarp only.
 // Outputs are bit-identical to the other two engines (same tests, same digests).
 #pragma once
 
