@@ -1025,6 +1025,7 @@ int xq_playout_host(int8_t* board_h, xq_meta* meta_h, uint64_t seed, uint32_t fi
   uint64_t* hist = nullptr;
   xq_playout_result* res = nullptr;
   cudaStream_t st = nullptr;
+  unsigned char* arena = nullptr;
   const size_t nb = (size_t)n_games * XQ_BOARD_STRIDE, nm = (size_t)n_games * sizeof(xq_meta);
   int hist_cap = 0;
   {
@@ -1046,11 +1047,27 @@ int xq_playout_host(int8_t* board_h, xq_meta* meta_h, uint64_t seed, uint32_t fi
   for (int g = 0; g < n_games; ++g) hist_cap = meta_h[g].hist_len > hist_cap ? meta_h[g].hist_len : hist_cap;
   XQ_REQUIRE(hist_cap == 0, "xq_playout_host starts from states without position history");
   hist_cap = max_plies > 0 ? max_plies : 1;
-  XQ_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-  XQ_CUDA(cudaMallocAsync(&board, nb, st));
-  XQ_CUDA(cudaMallocAsync(&meta, nm, st));
-  XQ_CUDA(cudaMallocAsync(&hist, (size_t)n_games * hist_cap * sizeof(uint64_t), st));
-  XQ_CUDA(cudaMallocAsync(&res, (size_t)n_games * sizeof(xq_playout_result), st));
+  {  // one stream per host thread and device, kept for the life of the thread
+    static thread_local cudaStream_t cached_stream = nullptr;
+    static thread_local int cached_dev = -1;
+    if (cached_dev != device) {
+      cached_stream = nullptr;
+      XQ_CUDA(cudaStreamCreateWithFlags(&cached_stream, cudaStreamNonBlocking));
+      cached_dev = device;
+    }
+    st = cached_stream;
+  }
+  {  // one stream-ordered allocation carved into the four device arrays
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t o_meta = up(nb), o_hist = o_meta + up(nm);
+    const size_t o_res = o_hist + up((size_t)n_games * hist_cap * sizeof(uint64_t));
+    const size_t total = o_res + up((size_t)n_games * sizeof(xq_playout_result));
+    XQ_CUDA(cudaMallocAsync(&arena, total, st));
+    board = reinterpret_cast<int8_t*>(arena);
+    meta = reinterpret_cast<xq_meta*>(arena + o_meta);
+    hist = reinterpret_cast<uint64_t*>(arena + o_hist);
+    res = reinterpret_cast<xq_playout_result*>(arena + o_res);
+  }
   XQ_CUDA(cudaMemcpyAsync(board, board_h, nb, cudaMemcpyHostToDevice, st));
   XQ_CUDA(cudaMemcpyAsync(meta, meta_h, nm, cudaMemcpyHostToDevice, st));
   rc = xq_playout(board, meta, hist, hist_cap, seed, first_game_id, max_plies, capture_bias, res,
@@ -1062,13 +1079,9 @@ int xq_playout_host(int8_t* board_h, xq_meta* meta_h, uint64_t seed, uint32_t fi
                           cudaMemcpyDeviceToHost, st));
   XQ_CUDA(cudaStreamSynchronize(st));
 done:
-  if (st) {
-    if (board) cudaFreeAsync(board, st);
-    if (meta) cudaFreeAsync(meta, st);
-    if (hist) cudaFreeAsync(hist, st);
-    if (res) cudaFreeAsync(res, st);
-    cudaStreamSynchronize(st);
-    cudaStreamDestroy(st);
+  if (arena) {
+    if (rc) cudaStreamSynchronize(st);  // nothing may still be using the arena on an error path
+    cudaFreeAsync(arena, st);           // stream-ordered: returns the block to the pool
   }
   return rc;
 }
