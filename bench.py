@@ -484,7 +484,7 @@ def run_ours(args):
                      "traffic_note": "ncu dram bytes read+write per launch (profiles/r1/playout_pair_ncu_summary.txt); "
                                      "algorithmic bytes per launch = %.2e" % (BYTES_PER_STEP_FUSED * plies_per_launch),
                      "peak_source": peak_src,
-                     "kernel": "xq::playout_pair_kernel<false> (two lanes per board)" if n >= 40960
+                     "kernel": "xq::playout_lane_kernel<false,true> (two lanes per board)" if n >= 40960
                                else "xq::playout_kernel<false,4,32> (one warp per board)",
                      "bytes_per_board_step": BYTES_PER_STEP_FUSED,
                      "kernel_ms_per_launch": kern_ms / args.steps,
@@ -531,7 +531,7 @@ def run_ours(args):
         # and MCTS use; the dispatch picks it below 40,960 boards) and a thread per board
         out["other_mappings"] = {}
         for mode, kname, wips in (("warp", "xq::playout_kernel<false,4,32>", WARP_INST_PER_STEP_WARP_MODE),
-                                  ("tpb", "xq::playout_tpb_kernel<false>", WARP_INST_PER_STEP_TPB_MODE)):
+                                  ("tpb", "xq::playout_lane_kernel<false,false>", WARP_INST_PER_STEP_TPB_MODE)):
             os.environ["XQ_PLAYOUT_MODE"] = mode
             one_step(3000)
             torch.cuda.synchronize()

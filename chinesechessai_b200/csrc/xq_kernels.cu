@@ -319,117 +319,6 @@ __global__ void __launch_bounds__(kThreads, MINB)
 }
 
 // ---------------------------------------------------------------------------
-// Fused random playout, one THREAD per board (xq_tpb.cuh).  Same inputs, outputs, digest and
-// traces as playout_kernel; per-thread board slabs live in dynamic shared memory.
-#ifndef XQ_TPB_THREADS
-#define XQ_TPB_THREADS 128
-#endif
-constexpr int kTpbThreads = XQ_TPB_THREADS;
-#ifndef XQ_PAIR_MINB
-#define XQ_PAIR_MINB 7
-#endif
-
-template <bool TRACE>
-__global__ void __launch_bounds__(kTpbThreads)
-    playout_tpb_kernel(int8_t* __restrict__ board, xq_meta* __restrict__ meta,
-                       uint64_t* __restrict__ pos_hist, int hist_cap, uint64_t seed,
-                       uint32_t first_game_id, int max_plies, int capture_bias,
-                       xq_playout_result* __restrict__ results, int16_t* __restrict__ tr_moves,
-                       int16_t* __restrict__ tr_n, int16_t* __restrict__ tr_pick,
-                       double* __restrict__ tr_reward, uint8_t* __restrict__ tr_flags,
-                       int8_t* __restrict__ tr_boards, int n_games) {
-  extern __shared__ __align__(16) unsigned char tpb_smem[];
-  const int g = blockIdx.x * kTpbThreads + threadIdx.x;
-  if (g >= n_games) return;
-  ThreadBoard& w = reinterpret_cast<ThreadBoard*>(tpb_smem)[threadIdx.x];
-  tpb_load(w, board + (size_t)g * XQ_BOARD_STRIDE);
-  Game G = load_meta(meta + g);
-  G.bkey = tpb_board_key(w);
-  uint64_t* hist = pos_hist + (size_t)g * hist_cap;
-  const uint32_t gid = first_game_id + (uint32_t)g;
-
-  uint64_t digest = 0, word_a = 0;
-  double rsum = 0.0;
-  int max_legal = 0, ply = 0;
-  bool pending = false, kingcap = false;
-  TpbStep o;
-  o.done = 0;
-  for (;;) {
-    bool checking = false;
-    const int n = kingcap ? -1 : tpb_movegen(w, G, g_leap, pending ? &checking : nullptr);
-    if (pending) {
-      tpb_finish(w, G, o, n, checking, hist);
-      pending = false;
-      rsum = __dadd_rn(rsum, o.reward);
-      const uint64_t word_c = (uint64_t)(o.done & 1) | ((uint64_t)(G.winner + 2) << 8) |
-                              ((uint64_t)G.reason << 16) | ((uint64_t)(o.is_int & 1) << 24);
-      const uint64_t t = word_a * 0x9E3779B97F4A7C15ULL + dbits(o.reward) * 0xC2B2AE3D27D4EB4FULL +
-                         word_c * 0x165667B19E3779F9ULL + o.key_next * 0x27D4EB2F165667C5ULL;
-      digest = mix64(digest ^ t);
-      if (TRACE) {
-        const size_t tt = (size_t)g * max_plies + ply;
-        if (tr_reward) tr_reward[tt] = o.reward;
-        if (tr_flags)
-          tr_flags[tt] = (uint8_t)((o.done & 1) | ((o.is_int & 1) << 1) | (((G.winner + 1) & 3) << 2) |
-                                   ((G.reason & 15) << 4));
-        if (tr_boards)
-          for (int sq = 0; sq < XQ_NSQ; ++sq) tr_boards[tt * XQ_NSQ + sq] = w.sq[sq];
-      }
-      ++ply;
-      if (o.done) break;
-    }
-    if (ply >= max_plies || n == 0) break;  // self_play.py:203,207
-    max_legal = max(max_legal, n);
-    const int idx = tpb_pick(w, n, seed, gid, (uint32_t)ply, capture_bias);
-    const unsigned cm = w.mv[idx];
-    const int mv = tpb_packed(cm);
-    unsigned lsum = 0;
-#pragma unroll 1
-    for (int i = 0; i < n; ++i) lsum += (unsigned)(tpb_packed(w.mv[i]) + 1) * (unsigned)(2 * i + 1);
-    word_a = (uint64_t)lsum | ((uint64_t)n << 32) | ((uint64_t)mv << 40) | ((uint64_t)(ply + 1) << 54);
-    if (TRACE) {
-      const size_t tt = (size_t)g * max_plies + ply;
-      if (tr_moves)
-        for (int i = 0; i < n; ++i) tr_moves[tt * XQ_MAX_MOVES + i] = (int16_t)tpb_packed(w.mv[i]);
-      if (tr_n) tr_n[tt] = (int16_t)n;
-      if (tr_pick) tr_pick[tt] = (int16_t)mv;
-    }
-    o = tpb_apply(w, G, (int)(cm >> 8), (int)(cm & 0x7fu), hist, hist_cap);
-    kingcap = o.done != 0;
-    pending = true;
-  }
-  const uint64_t fkey = G.bkey ^ side_key(G.player);
-#pragma unroll
-  for (int i = 0; i < XQ_BOARD_STRIDE / 4; ++i)
-    reinterpret_cast<uint32_t*>(board + (size_t)g * XQ_BOARD_STRIDE)[i] =
-        reinterpret_cast<const uint32_t*>(w.sq)[i];
-  {  // store_meta without the tile-lane guard
-    uint4 a, b;
-    a.x = (uint32_t)(G.player & 0xff) | ((uint32_t)(G.winner & 0xff) << 8) |
-          ((uint32_t)(G.reason & 0xff) << 16) | ((uint32_t)(G.done & 0xff) << 24);
-    a.y = (uint32_t)(G.red_king & 0xff) | ((uint32_t)(G.black_king & 0xff) << 8) |
-          ((uint32_t)(G.flags & 0xff) << 16);
-    a.z = (uint32_t)G.move_count;
-    a.w = (uint32_t)G.no_capture;
-    b.x = (uint32_t)G.cchecks;
-    b.y = (uint32_t)G.hist_len;
-    b.z = G.check_bits;
-    b.w = (uint32_t)G.check_len;
-    reinterpret_cast<uint4*>(meta + g)[0] = a;
-    reinterpret_cast<uint4*>(meta + g)[1] = b;
-  }
-  xq_playout_result r;
-  r.plies = ply;
-  r.winner = G.winner;
-  r.reason = G.reason;
-  r.max_legal = max_legal;
-  r.reward_sum = rsum;
-  r.digest = digest;
-  r.final_hash = fkey;
-  results[g] = r;
-}
-
-// ---------------------------------------------------------------------------
 // get_legal_moves / make_move for LARGE batches, two lanes per board (xq_pair.cuh): the same
 // entry points, the mapping that is faster once the batch fills the SMs (see xq_playout).
 __device__ __forceinline__ void pair_store_meta(xq_meta* __restrict__ dst, const Game& G) {
@@ -528,27 +417,33 @@ __global__ void __launch_bounds__(128, 7)
 }
 
 // ---------------------------------------------------------------------------
-// Fused random playout, TWO lanes per board (xq_pair.cuh): 64 boards per 128-thread CTA.
-constexpr int kPairThreads = 128;
-constexpr int kPairMinBlocks = XQ_PAIR_MINB;
+// Fused random playout on the per-lane engines: one THREAD per board (xq_tpb.cuh, PAIR = false,
+// 128 boards per CTA) or TWO lanes per board (xq_pair.cuh, PAIR = true, 64 boards per CTA).
+// Same inputs, outputs, digest and traces as playout_kernel; the board slabs (ThreadBoard)
+// live in dynamic shared memory.  The pair mapping is compiled for 7 CTAs per SM (72 registers)
+// so that 65,536 boards are resident in one wave.
+constexpr int kLaneThreads = 128;
 
-template <bool TRACE>
-__global__ void __launch_bounds__(kPairThreads, kPairMinBlocks)
-    playout_pair_kernel(int8_t* __restrict__ board, xq_meta* __restrict__ meta,
-                       uint64_t* __restrict__ pos_hist, int hist_cap, uint64_t seed,
-                       uint32_t first_game_id, int max_plies, int capture_bias,
-                       xq_playout_result* __restrict__ results, int16_t* __restrict__ tr_moves,
-                       int16_t* __restrict__ tr_n, int16_t* __restrict__ tr_pick,
-                       double* __restrict__ tr_reward, uint8_t* __restrict__ tr_flags,
-                       int8_t* __restrict__ tr_boards, int n_games) {
+template <bool TRACE, bool PAIR>
+__global__ void __launch_bounds__(kLaneThreads, PAIR ? 7 : 1)
+    playout_lane_kernel(int8_t* __restrict__ board, xq_meta* __restrict__ meta,
+                        uint64_t* __restrict__ pos_hist, int hist_cap, uint64_t seed,
+                        uint32_t first_game_id, int max_plies, int capture_bias,
+                        xq_playout_result* __restrict__ results, int16_t* __restrict__ tr_moves,
+                        int16_t* __restrict__ tr_n, int16_t* __restrict__ tr_pick,
+                        double* __restrict__ tr_reward, uint8_t* __restrict__ tr_flags,
+                        int8_t* __restrict__ tr_boards, int n_games) {
   extern __shared__ __align__(16) unsigned char tpb_smem[];
-  const int sub = Pair::sub();
-  const int g = blockIdx.x * (kPairThreads / 2) + (int)(threadIdx.x >> 1);
-  if (g >= n_games) return;  // both lanes of the pair
-  ThreadBoard& w = reinterpret_cast<ThreadBoard*>(tpb_smem)[threadIdx.x >> 1];
-  pair_load(w, board + (size_t)g * XQ_BOARD_STRIDE);
+  const int sub = PAIR ? Pair::sub() : 0;  // lane of the pair; lane 0 writes the outputs
+  const int slot = PAIR ? (int)(threadIdx.x >> 1) : (int)threadIdx.x;
+  const int g = blockIdx.x * (PAIR ? kLaneThreads / 2 : kLaneThreads) + slot;
+  if (g >= n_games) return;  // both lanes of a pair
+  ThreadBoard& w = reinterpret_cast<ThreadBoard*>(tpb_smem)[slot];
+  if constexpr (PAIR) pair_load(w, board + (size_t)g * XQ_BOARD_STRIDE);
+  else tpb_load(w, board + (size_t)g * XQ_BOARD_STRIDE);
   Game G = load_meta(meta + g);
-  G.bkey = pair_board_key(w);
+  if constexpr (PAIR) G.bkey = pair_board_key(w);
+  else G.bkey = tpb_board_key(w);
   uint64_t* hist = pos_hist + (size_t)g * hist_cap;
   const uint32_t gid = first_game_id + (uint32_t)g;
 
@@ -560,11 +455,14 @@ __global__ void __launch_bounds__(kPairThreads, kPairMinBlocks)
   o.done = 0;
   for (;;) {
     bool checking = false;
-    int n0 = 0;
-    unsigned lsum = 0;
-    const int n = kingcap ? -1 : pair_movegen(w, G, g_leap, pending, checking, n0, lsum);
+    int n = -1, n0 = 0;  // n0: lane 0's share of the pair's list
+    unsigned lsum = 0;   // digest term of the legal list
+    if (!kingcap) {
+      if constexpr (PAIR) n = pair_movegen(w, G, g_leap, pending, checking, n0, lsum);
+      else n = tpb_movegen(w, G, g_leap, pending ? &checking : nullptr);
+    }
     if (pending) {
-      tpb_finish<true>(w, G, o, n, checking, hist);
+      tpb_finish<PAIR>(w, G, o, n, checking, hist);
       pending = false;
       rsum = __dadd_rn(rsum, o.reward);
       const uint64_t word_c = (uint64_t)(o.done & 1) | ((uint64_t)(G.winner + 2) << 8) |
@@ -586,46 +484,42 @@ __global__ void __launch_bounds__(kPairThreads, kPairMinBlocks)
     }
     if (ply >= max_plies || n == 0) break;  // self_play.py:203,207
     max_legal = max(max_legal, n);
-    const int idx = pair_pick(w, n, n0, seed, gid, (uint32_t)ply, capture_bias);
-    const unsigned cm = pair_move_at(w, idx, n0);
+    unsigned cm;
+    if constexpr (PAIR) {
+      cm = pair_move_at(w, pair_pick(w, n, n0, seed, gid, (uint32_t)ply, capture_bias), n0);
+    } else {
+      cm = w.mv[tpb_pick(w, n, seed, gid, (uint32_t)ply, capture_bias)];
+#pragma unroll 1
+      for (int i = 0; i < n; ++i) lsum += (unsigned)(tpb_packed(w.mv[i]) + 1) * (unsigned)(2 * i + 1);
+    }
     const int mv = tpb_packed(cm);
     word_a = (uint64_t)lsum | ((uint64_t)n << 32) | ((uint64_t)mv << 40) | ((uint64_t)(ply + 1) << 54);
     if (TRACE) {
       const size_t tt = (size_t)g * max_plies + ply;
-      if (tr_moves) {  // each lane writes its own part of the list
-        const int my_n = sub ? n - n0 : n0, my_off = sub ? n0 : 0;
-        const int my_base = sub ? kTpbMoveCap - 1 : 0, my_dir = sub ? -1 : 1;
-        for (int i = 0; i < my_n; ++i)
-          tr_moves[tt * XQ_MAX_MOVES + my_off + i] = (int16_t)tpb_packed(w.mv[my_base + my_dir * i]);
+      if (tr_moves) {
+        if constexpr (PAIR) pair_store_moves(w, tr_moves + tt * XQ_MAX_MOVES, n, n0);
+        else
+          for (int i = 0; i < n; ++i) tr_moves[tt * XQ_MAX_MOVES + i] = (int16_t)tpb_packed(w.mv[i]);
       }
       if (tr_n && sub == 0) tr_n[tt] = (int16_t)n;
       if (tr_pick && sub == 0) tr_pick[tt] = (int16_t)mv;
     }
-    o = tpb_apply<true>(w, G, (int)(cm >> 8), (int)(cm & 0x7fu), hist, hist_cap);
+    o = tpb_apply<PAIR>(w, G, (int)(cm >> 8), (int)(cm & 0x7fu), hist, hist_cap);
     kingcap = o.done != 0;
     pending = true;
   }
   const uint64_t fkey = G.bkey ^ side_key(G.player);
+  uint32_t* bo = reinterpret_cast<uint32_t*>(board + (size_t)g * XQ_BOARD_STRIDE);
+  const uint32_t* bi = reinterpret_cast<const uint32_t*>(w.sq);
+  if constexpr (PAIR) {
 #pragma unroll
-  for (int i = 0; i < XQ_BOARD_STRIDE / 8; ++i)
-    reinterpret_cast<uint32_t*>(board + (size_t)g * XQ_BOARD_STRIDE)[2 * i + sub] =
-        reinterpret_cast<const uint32_t*>(w.sq)[2 * i + sub];
-  if (sub != 0) return;
-  {  // store_meta without the tile-lane guard
-    uint4 a, b;
-    a.x = (uint32_t)(G.player & 0xff) | ((uint32_t)(G.winner & 0xff) << 8) |
-          ((uint32_t)(G.reason & 0xff) << 16) | ((uint32_t)(G.done & 0xff) << 24);
-    a.y = (uint32_t)(G.red_king & 0xff) | ((uint32_t)(G.black_king & 0xff) << 8) |
-          ((uint32_t)(G.flags & 0xff) << 16);
-    a.z = (uint32_t)G.move_count;
-    a.w = (uint32_t)G.no_capture;
-    b.x = (uint32_t)G.cchecks;
-    b.y = (uint32_t)G.hist_len;
-    b.z = G.check_bits;
-    b.w = (uint32_t)G.check_len;
-    reinterpret_cast<uint4*>(meta + g)[0] = a;
-    reinterpret_cast<uint4*>(meta + g)[1] = b;
+    for (int i = 0; i < XQ_BOARD_STRIDE / 8; ++i) bo[2 * i + sub] = bi[2 * i + sub];
+    if (sub != 0) return;
+  } else {
+#pragma unroll
+    for (int i = 0; i < XQ_BOARD_STRIDE / 4; ++i) bo[i] = bi[i];
   }
+  pair_store_meta(meta + g, G);
   xq_playout_result r;
   r.plies = ply;
   r.winner = G.winner;
@@ -947,38 +841,27 @@ int xq_playout(int8_t* board, xq_meta* meta, uint64_t* pos_hist, int hist_cap, u
   const char* mode_env = getenv("XQ_PLAYOUT_MODE");
   const bool pair = use_pair_mapping(n_games);
   const bool tpb = mode_env != nullptr && strcmp(mode_env, "tpb") == 0;
-  if (pair) {
-    const int bpc = kPairThreads / 2;
+  if (pair || tpb) {
+    const int bpc = pair ? kLaneThreads / 2 : kLaneThreads;  // boards per CTA
     const size_t smem = sizeof(ThreadBoard) * bpc;
-    const dim3 pgrid((n_games + bpc - 1) / bpc);
-    if (trace)
-      playout_pair_kernel<true><<<pgrid, kPairThreads, smem, st>>>(
-          board, meta, pos_hist, hist_cap, seed, first_game_id, max_plies, capture_bias, results,
-          tr_moves, tr_n, tr_pick, tr_reward, tr_flags, tr_boards, n_games);
-    else
-      playout_pair_kernel<false><<<pgrid, kPairThreads, smem, st>>>(
-          board, meta, pos_hist, hist_cap, seed, first_game_id, max_plies, capture_bias, results,
-          nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, n_games);
-    return check_launch("xq_playout");
-  }
-  if (tpb) {
-    const size_t smem = sizeof(ThreadBoard) * kTpbThreads;
-    const dim3 tgrid((n_games + kTpbThreads - 1) / kTpbThreads);
-    cudaError_t e1 = cudaFuncSetAttribute(playout_tpb_kernel<false>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaError_t e2 = cudaFuncSetAttribute(playout_tpb_kernel<true>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e1 != cudaSuccess || e2 != cudaSuccess)
-      return fail(XQ_E_CUDA, "xq_playout: cudaFuncSetAttribute: %s",
-                  cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
-    if (trace)
-      playout_tpb_kernel<true><<<tgrid, kTpbThreads, smem, st>>>(
-          board, meta, pos_hist, hist_cap, seed, first_game_id, max_plies, capture_bias, results,
-          tr_moves, tr_n, tr_pick, tr_reward, tr_flags, tr_boards, n_games);
-    else
-      playout_tpb_kernel<false><<<tgrid, kTpbThreads, smem, st>>>(
-          board, meta, pos_hist, hist_cap, seed, first_game_id, max_plies, capture_bias, results,
-          nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, n_games);
+    const dim3 lgrid((n_games + bpc - 1) / bpc);
+#define XQ_LAUNCH_LANE(T, P)                                                                      \
+  do {                                                                                            \
+    if (smem > 48 * 1024) {                                                                       \
+      cudaError_t e1 = cudaFuncSetAttribute(playout_lane_kernel<T, P>,                            \
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      if (e1 != cudaSuccess)                                                                      \
+        return fail(XQ_E_CUDA, "xq_playout: cudaFuncSetAttribute: %s", cudaGetErrorString(e1));   \
+    }                                                                                             \
+    playout_lane_kernel<T, P><<<lgrid, kLaneThreads, smem, st>>>(                                 \
+        board, meta, pos_hist, hist_cap, seed, first_game_id, max_plies, capture_bias, results,   \
+        tr_moves, tr_n, tr_pick, tr_reward, tr_flags, tr_boards, n_games);                        \
+  } while (0)
+    if (pair && trace) XQ_LAUNCH_LANE(true, true);
+    else if (pair) XQ_LAUNCH_LANE(false, true);
+    else if (trace) XQ_LAUNCH_LANE(true, false);
+    else XQ_LAUNCH_LANE(false, false);
+#undef XQ_LAUNCH_LANE
     return check_launch("xq_playout");
   }
 #define XQ_LAUNCH_PLAYOUT(T, M, LL)                                                              \
