@@ -76,3 +76,18 @@ def test_bench_reference_arm_prints_one_json_line():
         assert k in d, k
     assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] in ("port", "reference")
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_bench_product_arm_refuses_to_run_without_a_gpu():
+    """No CPU fallback: on a machine without a CUDA device the product arm of bench.py exits
+    with an error instead of timing something else."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--fast", "--no-cpu"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0
+    assert "CUDA" in (r.stderr + r.stdout)
+    assert not [ln for ln in r.stdout.splitlines() if ln.strip().startswith("{")]
