@@ -62,7 +62,10 @@ enum {
 };
 
 /* xq_meta.flags */
-#define XQ_F_OVERFLOW 1u /* >XQ_MAX_MOVES legal, too many candidates / own pieces, or history full */
+#define XQ_F_OVERFLOW 1u /* >XQ_MAX_MOVES legal, too many candidates / own pieces, or history full.
+                          * Capacities cover every position with <= 16 pieces per side; boards
+                          * with more (not chess) may raise the flag in one lane mapping and not
+                          * in another - results are only specified while the flag is clear. */
 
 typedef struct {
   int8_t player;              /* current_player +1/-1           chess_env.py:62  */
