@@ -61,6 +61,7 @@ SIGNATURES = {
     "xq_pick_moves": (_i, [_vp, _vp, _vp, _vp, _u64, _u32, _u32, _i, _vp, _i, _vp]),
     "xq_playout": (_i, [_vp, _vp, _vp, _i, _u64, _u32, _i, _i, _vp,
                         _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "xq_debug_playout_timing": (_i, [_vp]),
     "xq_playout_host": (_i, [_vp, _vp, _u64, _u32, _i, _i, _vp, _i, _i]),
     "xq_encode_planes": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _vp]),
     "xq_encode_planes_nhwc16": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp]),

@@ -424,6 +424,26 @@ __global__ void __launch_bounds__(128, 7)
 // so that 65,536 boards are resident in one wave.
 constexpr int kLaneThreads = 128;
 
+// Per-warp {first start, last end (ns, %globaltimer), SM id} for xq_debug_playout_timing.
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void warp_stamp_begin(unsigned long long* timing) {
+  const size_t wid = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if ((threadIdx.x & 31) == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+    timing[3 * wid] = global_ns();
+    timing[3 * wid + 2] = smid;
+  }
+}
+__device__ __forceinline__ void warp_stamp_end(unsigned long long* timing) {
+  const size_t wid = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  atomicMax(&timing[3 * wid + 1], global_ns());
+}
+
 template <bool TRACE, bool PAIR>
 __global__ void __launch_bounds__(kLaneThreads, PAIR ? 7 : 1)
     playout_lane_kernel(int8_t* __restrict__ board, xq_meta* __restrict__ meta,
@@ -432,8 +452,10 @@ __global__ void __launch_bounds__(kLaneThreads, PAIR ? 7 : 1)
                         xq_playout_result* __restrict__ results, int16_t* __restrict__ tr_moves,
                         int16_t* __restrict__ tr_n, int16_t* __restrict__ tr_pick,
                         double* __restrict__ tr_reward, uint8_t* __restrict__ tr_flags,
-                        int8_t* __restrict__ tr_boards, int n_games) {
+                        int8_t* __restrict__ tr_boards, int n_games,
+                        unsigned long long* __restrict__ timing) {
   extern __shared__ __align__(16) unsigned char tpb_smem[];
+  if (timing) warp_stamp_begin(timing);  // diagnostics only (xq_debug_playout_timing)
   const int sub = PAIR ? Pair::sub() : 0;  // lane of the pair; lane 0 writes the outputs
   const int slot = PAIR ? (int)(threadIdx.x >> 1) : (int)threadIdx.x;
   const int g = blockIdx.x * (PAIR ? kLaneThreads / 2 : kLaneThreads) + slot;
@@ -509,6 +531,7 @@ __global__ void __launch_bounds__(kLaneThreads, PAIR ? 7 : 1)
     pending = true;
   }
   const uint64_t fkey = G.bkey ^ side_key(G.player);
+  if (timing) warp_stamp_end(timing);
   uint32_t* bo = reinterpret_cast<uint32_t*>(board + (size_t)g * XQ_BOARD_STRIDE);
   const uint32_t* bi = reinterpret_cast<const uint32_t*>(w.sq);
   if constexpr (PAIR) {
@@ -663,7 +686,10 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
   for (int k = 0; k < XQ_MAX_MOVES / 32; ++k) {
     const int i = k * 32 + lane;
-    v[k] = i < cnt ? (float)lg[mv[i]] : -INFINITY;
+    // a packed move outside [0, XQ_POLICY) has no logit: it gets prior 0 and takes no part in the
+    // softmax (the reference skips such entries, neural_network.py:161 `if idx < len(logits)`)
+    const int m = i < cnt ? (int)mv[i] : -1;
+    v[k] = (m >= 0 && m < XQ_POLICY) ? (float)lg[m] : -INFINITY;
     mx = fmaxf(mx, v[k]);
   }
 #pragma unroll
@@ -672,7 +698,7 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
   for (int k = 0; k < XQ_MAX_MOVES / 32; ++k) {
     const int i = k * 32 + lane;
-    v[k] = i < cnt ? expf(v[k] - mx) : 0.f;
+    v[k] = v[k] > -INFINITY ? expf(v[k] - mx) : 0.f;
     sum += v[k];
   }
 #pragma unroll
@@ -680,7 +706,8 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
   for (int k = 0; k < XQ_MAX_MOVES / 32; ++k) {
     const int i = k * 32 + lane;
-    if (i < XQ_MAX_MOVES) priors[(size_t)g * XQ_MAX_MOVES + i] = i < cnt ? __fdiv_rn(v[k], sum) : 0.f;
+    if (i < XQ_MAX_MOVES)
+      priors[(size_t)g * XQ_MAX_MOVES + i] = (i < cnt && sum > 0.f) ? __fdiv_rn(v[k], sum) : 0.f;
   }
 }
 
@@ -810,6 +837,15 @@ int xq_pick_moves(const int8_t* board, const xq_meta* meta, const int16_t* moves
   return check_launch("xq_pick_moves");
 }
 
+// Diagnostics: while a device buffer of 3 * ceil(threads / 32) uint64 (zero-filled by the caller)
+// is registered, the per-lane fused playout kernels record every warp's first start / last end
+// time (ns) and SM id in it.  NULL switches the recording off (the default).
+static unsigned long long* g_timing = nullptr;
+int xq_debug_playout_timing(uint64_t* device_buf) {
+  g_timing = reinterpret_cast<unsigned long long*>(device_buf);
+  return 0;
+}
+
 int xq_playout(int8_t* board, xq_meta* meta, uint64_t* pos_hist, int hist_cap, uint64_t seed,
                uint32_t first_game_id, int max_plies, int capture_bias, xq_playout_result* results,
                int16_t* tr_moves, int16_t* tr_n, int16_t* tr_pick, double* tr_reward,
@@ -855,7 +891,7 @@ int xq_playout(int8_t* board, xq_meta* meta, uint64_t* pos_hist, int hist_cap, u
     }                                                                                             \
     playout_lane_kernel<T, P><<<lgrid, kLaneThreads, smem, st>>>(                                 \
         board, meta, pos_hist, hist_cap, seed, first_game_id, max_plies, capture_bias, results,   \
-        tr_moves, tr_n, tr_pick, tr_reward, tr_flags, tr_boards, n_games);                        \
+        tr_moves, tr_n, tr_pick, tr_reward, tr_flags, tr_boards, n_games, g_timing);              \
   } while (0)
     if (pair && trace) XQ_LAUNCH_LANE(true, true);
     else if (pair) XQ_LAUNCH_LANE(false, true);

@@ -4,7 +4,9 @@ the weight broadcast that replaces the per-game state_dict pickle of self_play.p
 sample gather that replaces the pickled results of :404-408."""
 from __future__ import annotations
 
-from typing import Dict, Optional, Tuple
+import math
+import weakref
+from typing import Dict, List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
@@ -17,68 +19,184 @@ def shard_range(n_games: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def broadcast_weights(module: torch.nn.Module, src: int = 0) -> int:
-    """Broadcast every parameter and buffer from ``src`` as ONE flat buffer per dtype
-    (24,634,141 fp32 parameters = 98.5 MB for ChessNet).  Returns the bytes sent."""
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-        return 0
-    groups: Dict[torch.dtype, list] = {}
-    for t in list(module.parameters()) + list(module.buffers()):
-        groups.setdefault(t.dtype, []).append(t)
-    sent = 0
-    for dtype, tensors in groups.items():
-        flat = torch.cat([t.detach().reshape(-1) for t in tensors])
-        dist.broadcast(flat, src=src)
-        sent += flat.numel() * flat.element_size()
-        off = 0
+def _active() -> bool:
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+class FlatParams:
+    """All parameters and buffers of a module living in ONE persistent flat buffer per dtype.
+
+    ``attach`` re-points every tensor's storage at a slice of the flat buffer (values preserved),
+    so the per-iteration weight broadcast is a single collective on memory the module already
+    uses: no ``torch.cat`` staging buffer, no per-tensor copy back (round 1 did both on every
+    call: 98.5 MB through two extra HBM passes and ~60 small launches).  Optimizers keep working —
+    they update ``p.data`` in place — and ``load_state_dict`` copies into the same storage.
+    ``module.to(...)`` would re-allocate the tensors; ``attached()`` notices and re-attaches."""
+
+    def __init__(self, module: torch.nn.Module):
+        self.module = weakref.ref(module)
+        self.flat: Dict[torch.dtype, torch.Tensor] = {}
+        self._slots: List[Tuple[torch.Tensor, torch.dtype, int, int]] = []
+        self.attach()
+
+    def _tensors(self) -> List[torch.Tensor]:
+        m = self.module()
+        seen, out = set(), []
+        for t in list(m.parameters()) + list(m.buffers()):
+            if id(t) not in seen:
+                seen.add(id(t))
+                out.append(t)
+        return out
+
+    def attach(self) -> None:
+        tensors = self._tensors()
+        sizes: Dict[torch.dtype, int] = {}
+        for t in tensors:
+            # 64-element alignment keeps every view 16-byte aligned for vectorised kernels
+            sizes[t.dtype] = sizes.get(t.dtype, 0) + (t.numel() + 63) // 64 * 64
+        dev = tensors[0].device if tensors else torch.device("cpu")
+        self.flat = {dt: torch.zeros(n, dtype=dt, device=dev) for dt, n in sizes.items()}
+        offs = {dt: 0 for dt in sizes}
+        self._slots = []
         with torch.no_grad():
             for t in tensors:
-                n = t.numel()
-                t.copy_(flat[off:off + n].view_as(t))
-                off += n
+                n, off = t.numel(), offs[t.dtype]
+                view = self.flat[t.dtype][off:off + n].view(t.shape)
+                view.copy_(t)
+                t.data = view
+                self._slots.append((t, t.dtype, off, n))
+                offs[t.dtype] = off + (n + 63) // 64 * 64
+
+    def attached(self) -> bool:
+        tensors = self._tensors()
+        if len(tensors) != len(self._slots):
+            return False
+        for t, (t0, dt, off, n) in zip(tensors, self._slots):
+            if t is not t0 or t.dtype != dt or t.numel() != n or \
+                    t.data_ptr() != self.flat[dt].data_ptr() + off * self.flat[dt].element_size():
+                return False
+        return True
+
+    @property
+    def nbytes(self) -> int:
+        return sum(sum(n for _, d, _, n in self._slots if d == dt) * f.element_size()
+                   for dt, f in self.flat.items())
+
+    def broadcast(self, src: int = 0) -> int:
+        """One collective per dtype (float32 weights + the int64 BatchNorm counters)."""
+        if not self.attached():
+            self.attach()
+        sent = 0
+        for f in self.flat.values():
+            dist.broadcast(f, src=src)
+            sent += f.numel() * f.element_size()
+        return sent
+
+
+_FLAT: "weakref.WeakKeyDictionary[torch.nn.Module, FlatParams]" = weakref.WeakKeyDictionary()
+
+
+def flat_params(module: torch.nn.Module) -> FlatParams:
+    fp = _FLAT.get(module)
+    if fp is None:
+        fp = _FLAT[module] = FlatParams(module)
+    return fp
+
+
+def broadcast_weights(module: torch.nn.Module, src: int = 0, evaluators=()) -> int:
+    """Broadcast every parameter and buffer of ``module`` from ``src`` in place through its
+    persistent flat buffer (24,634,141 fp32 parameters = 98.5 MB for ChessNet).  ``evaluators``:
+    objects with ``refresh()`` (``NetEvaluator``) that wrap ``module`` — the collective writes
+    through the flat buffer, which does not bump the parameters' version counters, so their
+    folded copies are invalidated explicitly.  Returns the bytes sent."""
+    if not _active():
+        return 0
+    sent = flat_params(module).broadcast(src)
+    for ev in evaluators:
+        if ev is not None and hasattr(ev, "refresh"):
+            ev.refresh()
     return sent
 
 
 def gather_samples(samples: Dict[str, torch.Tensor], dst: int = 0) -> Optional[Dict[str, torch.Tensor]]:
     """Concatenate per-rank sample tensors (same keys, ragged first dimension) on ``dst`` in rank
-    order.  One all_gather of counts + one padded all_gather per key."""
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+    order.  One tiny all_gather of the row counts, then every rank sends ONE packed byte buffer
+    to ``dst`` only (round 1 padded each key to the longest rank and all-gathered it to every
+    rank: world x the bytes, although only ``dst`` reads them)."""
+    if not _active():
         return samples
     world, rank = dist.get_world_size(), dist.get_rank()
-    first = next(iter(samples.values()))
-    cnt = torch.tensor([first.shape[0]], dtype=torch.int64, device=first.device)
-    counts = [torch.zeros_like(cnt) for _ in range(world)]
-    dist.all_gather(counts, cnt)
-    counts = [int(c) for c in counts]
-    mx = max(counts)
-    out = {}
-    for k, t in samples.items():
-        pad = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        pad[:t.shape[0]] = t
-        bufs = [torch.empty_like(pad) for _ in range(world)]
-        dist.all_gather(bufs, pad)
-        if rank == dst:
-            out[k] = torch.cat([b[:c] for b, c in zip(bufs, counts)])
-    return out if rank == dst else None
+    # widest element type first, so that every section of the packed buffer starts aligned
+    keys = sorted(samples.keys(), key=lambda k: -samples[k].element_size())
+    first = samples[keys[0]]
+    dev = first.device
+    cnt = torch.tensor([first.shape[0]], dtype=torch.int64, device=dev)
+    counts_t = torch.zeros(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts_t, cnt)
+    counts = [int(c) for c in counts_t.tolist()]
+    per_row = [math.prod(samples[k].shape[1:]) * samples[k].element_size() for k in keys]
+
+    def pack(n_rows: int, src: Optional[Dict[str, torch.Tensor]]) -> torch.Tensor:
+        buf = torch.empty(sum(per_row) * n_rows, dtype=torch.uint8, device=dev)
+        if src is not None:
+            off = 0
+            for k, b in zip(keys, per_row):
+                buf[off:off + b * n_rows].copy_(src[k].contiguous().view(torch.uint8).reshape(-1))
+                off += b * n_rows
+        return buf
+
+    def unpack(buf: torch.Tensor, n_rows: int) -> Dict[str, torch.Tensor]:
+        out, off = {}, 0
+        for k, b in zip(keys, per_row):
+            t = samples[k]
+            out[k] = buf[off:off + b * n_rows].view(t.dtype).reshape((n_rows,) + tuple(t.shape[1:]))
+            off += b * n_rows
+        return out
+
+    mine = pack(counts[rank], samples)
+    if rank != dst:
+        if counts[rank] > 0:
+            dist.send(mine, dst=dst)
+        return None
+    parts = []
+    ops, bufs = [], {}
+    for r in range(world):
+        if r == dst or counts[r] == 0:
+            continue
+        bufs[r] = pack(counts[r], None)
+        ops.append(dist.P2POp(dist.irecv, bufs[r], r))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    for r in range(world):
+        if counts[r] == 0:
+            continue
+        parts.append(unpack(mine if r == dst else bufs[r], counts[r]))
+    if not parts:
+        return {k: samples[k][:0] for k in keys}
+    return {k: torch.cat([p[k] for p in parts]) for k in keys}
 
 
 def distributed_self_play(evaluator, num_games: int, num_simulations: int, temperature: float = 1.0,
                           seed: int = 0, network: Optional[torch.nn.Module] = None, dst: int = 0,
-                          opponent=None):
+                          opponent=None, net_dtype: torch.dtype = torch.float32):
     """One self-play phase on all ranks (one process per GPU): broadcast ``network``'s weights
     from ``dst`` (if given), play this rank's block of game ids as one device batch, gather the
     training samples on ``dst``.  Replaces parallel_self_play's process pool + pickles
     (self_play.py:386-408); there is no collective inside the game loop.
+    ``evaluator`` may be the network itself (an ``nn.Module``, evaluated at ``net_dtype``), a
+    ``NetEvaluator`` around it, or any callable evaluator.
     Returns (samples dict on ``dst`` / None elsewhere, this rank's BatchedSelfPlay)."""
     from .samples import training_tensors
     from .self_play import BatchedSelfPlay
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
     if network is not None:
-        broadcast_weights(network, src=dst)
+        network.eval()
+        broadcast_weights(network, src=dst, evaluators=(evaluator, opponent))
     lo, hi = shard_range(num_games, rank, world)
     sp = BatchedSelfPlay(evaluator, hi - lo, num_simulations, temperature, opponent_network=opponent,
-                         seed=seed, first_game_id=lo)
+                         seed=seed, first_game_id=lo, net_dtype=net_dtype)
     sp.play()
     mine = training_tensors(sp, red_only=opponent is not None)
     mine["game"] = mine["game"] + lo

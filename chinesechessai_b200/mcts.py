@@ -163,24 +163,55 @@ class NetEvaluator:
     """encode_board -> ChessNet.forward -> gather+softmax, all on device
     (neural_network.py:96-126 without the per-sample D2H of :120-124).
 
-    ``dtype=float32`` runs the module as given (the reference's precision).  A lower-precision
-    dtype builds a folded inference copy (BN folded, ``dtype`` weights, channels-last); call
-    ``refresh()`` after the weights change (once per training iteration)."""
+    ``dtype=float32`` runs the module as given (the reference's precision; ``tf32=True`` lets
+    cuDNN/cuBLAS use TF32 tensor cores for it).  A lower-precision dtype builds a folded
+    inference copy (BN folded, ``dtype`` weights, channels-last).  The copy is rebuilt whenever
+    the module's weights have changed since it was made — optimizer steps, ``load_state_dict``
+    and the NCCL weight broadcast all bump the tensors' version counters, which is what
+    ``version`` watches — so an evaluator kept across training iterations never plays with stale
+    weights.  The module must be in eval mode (the reference's workers force it,
+    self_play.py:339,346): BatchNorm batch statistics must not leak into the search."""
 
-    def __init__(self, net: torch.nn.Module, dtype: torch.dtype = torch.float32):
+    def __init__(self, net: torch.nn.Module, dtype: torch.dtype = torch.float32, tf32: bool = False):
         self.net = net
         self.dtype = dtype
+        self.tf32 = bool(tf32)
         self._fast = None
-        self.version = 0  # bumped by refresh(); captured CUDA graphs of a search are keyed on it
+        self._seen = None     # weight fingerprint the folded copy / captured graphs belong to
+        self._version = 0
+
+    def _fingerprint(self):
+        return tuple(t._version for t in self.net.state_dict(keep_vars=True).values())
+
+    @property
+    def version(self) -> int:
+        """Changes whenever the weights do; captured CUDA graphs of a search are keyed on it."""
+        fp = self._fingerprint()
+        if fp != self._seen:
+            self._seen = fp
+            self._fast = None
+            self._version += 1
+        return self._version
 
     def refresh(self) -> None:
-        self._fast = None
-        self.version += 1
+        """Force a rebuild of the folded copy (kept for callers that modify weights through
+        ``.data`` or other paths that bypass the version counters)."""
+        self._seen = None
 
     @torch.no_grad()
     def __call__(self, leaf_board, leaf_player, leaf_moves, leaf_n):
+        if self.net.training:
+            raise RuntimeError("NetEvaluator: the network is in train() mode; call network.eval() before "
+                               "self-play (BatchNorm would use and update batch statistics)")
+        _ = self.version
         if self.dtype == torch.float32:
-            logits, value = self.net(encode_planes(leaf_board, leaf_player, dtype=self.dtype))
+            planes = encode_planes(leaf_board, leaf_player, dtype=self.dtype)
+            if self.tf32:
+                with _tf32(True):
+                    logits, value = self.net(planes)
+            else:
+                with _tf32(False):
+                    logits, value = self.net(planes)
         else:
             if self._fast is None:
                 self._fast = _FoldedNet(self.net, self.dtype)
@@ -191,6 +222,22 @@ class NetEvaluator:
             logits = logits.float()
         pri = policy_priors(logits, leaf_moves, leaf_n)
         return pri, value.reshape(-1).float().contiguous()
+
+
+class _tf32:
+    """Scope for the TF32 switches of cuDNN convolutions and cuBLAS matmuls."""
+
+    def __init__(self, on: bool):
+        self.on = bool(on)
+
+    def __enter__(self):
+        self.prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        torch.backends.cudnn.allow_tf32 = self.on
+        torch.backends.cuda.matmul.allow_tf32 = self.on
+
+    def __exit__(self, *exc):
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = self.prev
+        return False
 
 
 class BatchedMCTS:

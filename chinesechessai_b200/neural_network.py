@@ -16,6 +16,21 @@ from .engine import encode_planes, pack_move, policy_priors
 Move = Tuple[int, int, int, int]
 
 
+def _pack_checked(legal_moves) -> List[int]:
+    """Policy indices (from*90+to, neural_network.py:160) of a caller-supplied move list.  The
+    kernels index the logits with them, so off-board moves and lists longer than the engine's
+    128-move capacity are refused here instead of reaching the device."""
+    if len(legal_moves) > 128:
+        raise ValueError(f"{len(legal_moves)} legal moves exceed the engine's capacity of 128")
+    out = []
+    for m in legal_moves:
+        fr, fc, tr, tc = (int(x) for x in m)
+        if not (0 <= fr < 10 and 0 <= tr < 10 and 0 <= fc < 9 and 0 <= tc < 9):
+            raise ValueError(f"move {tuple(m)} is off the 10x9 board")
+        out.append(pack_move((fr, fc, tr, tc)))
+    return out
+
+
 class ResidualBlock(nn.Module):
     def __init__(self, num_channels: int):
         super().__init__()
@@ -82,7 +97,7 @@ class ChessNet(nn.Module):
         counts = np.zeros(n, np.int16)
         for i, (_, _, lm) in enumerate(items):
             counts[i] = len(lm)
-            moves[i, :len(lm)] = [pack_move(m) for m in lm]
+            moves[i, :len(lm)] = _pack_checked(lm)
         tb, tp = torch.from_numpy(boards).to(d), torch.from_numpy(players).to(d)
         tm, tn = torch.from_numpy(moves).to(d), torch.from_numpy(counts).to(d)
         logits, values = self.forward(encode_planes(tb, tp))
@@ -100,7 +115,18 @@ class ChessNet(nn.Module):
         d = self._device()
         lg = torch.from_numpy(np.ascontiguousarray(logits, dtype=np.float32).reshape(1, -1)).to(d)
         mv = torch.zeros((1, 128), dtype=torch.int16, device=d)
-        mv[0, :len(legal_moves)] = torch.tensor([pack_move(m) for m in legal_moves], dtype=torch.int16)
+        mv[0, :len(legal_moves)] = torch.tensor(_pack_checked(legal_moves), dtype=torch.int16)
         cnt = torch.tensor([len(legal_moves)], dtype=torch.int16, device=d)
         pri = policy_priors(lg, mv, cnt)[0].cpu().numpy()
         return {tuple(m): pri[j] for j, m in enumerate(legal_moves)}
+
+
+def test_network():
+    """``python main.py test`` calls this (main.py:177): one forward pass and the parameter count."""
+    print("测试神经网络...")
+    net = ChessNet().to("cuda")
+    x = torch.randn(4, 15, 10, 9, device="cuda")
+    policy, value = net(x)
+    print(f"输入形状: {x.shape}  策略输出形状: {policy.shape}  价值输出形状: {value.shape}")
+    print(f"价值范围: {value.min().item():.2f} ~ {value.max().item():.2f}")
+    print(f"总参数量: {sum(p.numel() for p in net.parameters()):,}")

@@ -15,18 +15,20 @@ from .self_play import BatchedSelfPlay
 
 
 def _final_reward(winner: torch.Tensor, player: torch.Tensor, length: torch.Tensor) -> torch.Tensor:
-    """self_play.py:268-298, vectorised in float64 (same constants, same branches)."""
-    f64 = torch.float64
+    """self_play.py:268-298, vectorised in float64 (same constants, same branches).  Every constant
+    is a float64 tensor: ``torch.where(cond, 0.3, 0.1)`` on Python scalars would come out as
+    float32 and 1.0 + 0.3 would no longer equal the reference's double."""
+    dev = winner.device
+
+    def c(x: float) -> torch.Tensor:
+        return torch.tensor(x, dtype=torch.float64, device=dev)
     long_game = length >= 60
-    draw = torch.where(long_game,
-                       torch.where(player == 1, torch.tensor(-0.15, dtype=f64, device=winner.device),
-                                   torch.tensor(0.05, dtype=f64, device=winner.device)),
-                       torch.where(player == 1, torch.tensor(-0.1, dtype=f64, device=winner.device),
-                                   torch.tensor(0.1, dtype=f64, device=winner.device)))
-    bonus = torch.where(length <= 30, 0.5, torch.where(length <= 50, 0.3,
-                        torch.where(length <= 70, 0.1, 0.0))).to(f64)
-    win = 1.0 + bonus
-    lose = torch.where(long_game, -1.2, -1.0).to(f64)
+    draw = torch.where(long_game, torch.where(player == 1, c(-0.15), c(0.05)),
+                       torch.where(player == 1, c(-0.1), c(0.1)))
+    bonus = torch.where(length <= 30, c(0.5), torch.where(length <= 50, c(0.3),
+                        torch.where(length <= 70, c(0.1), c(0.0))))
+    win = c(1.0) + bonus
+    lose = torch.where(long_game, c(-1.2), c(-1.0))
     return torch.where(winner == 0, draw, torch.where(winner == player, win, lose))
 
 

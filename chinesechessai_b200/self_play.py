@@ -10,6 +10,8 @@
 """
 from __future__ import annotations
 
+import gc
+import sys
 from typing import Dict, List, Optional, Tuple
 
 import numpy as np
@@ -22,6 +24,7 @@ from .config import MAX_MOVES as MAX_PLIES, MCTS_SIMULATIONS
 from .engine import BoardBatch, _ptr, _stream, pack_move, unpack_move
 from .mcts import WAVE, BatchedMCTS, HashEvaluator, NetEvaluator
 
+PROGRESS_EVERY_PLIES = 10  # parallel_self_play refreshes its progress line this often
 GRAPH_MAX_GAMES = 1024  # measured (scripts/single_game_latency.py): a ply is 4x
                         # faster at 1-64 games, 1.3x at 1,024, 1.05x at 4,096 — but the capture
                         # costs ~10 ms per BatchedSelfPlay instance, which a 70-ply batch only
@@ -182,6 +185,9 @@ class BatchedSelfPlay:
         self.lib = _lib.load()
         self.boards = BoardBatch(self.n, device=d, hist_cap=MAX_PLIES + 2)
         self.mcts = BatchedMCTS(self.n, self.n_sims, device=d)
+        for net in (network, opponent_network):  # the reference's workers force eval mode (:339,:346)
+            if isinstance(net, torch.nn.Module):
+                net.eval()
         self.eval_red = network if callable(network) and not isinstance(network, torch.nn.Module) \
             else NetEvaluator(network, net_dtype)
         self.eval_black = None
@@ -203,6 +209,8 @@ class BatchedSelfPlay:
         self.rec_move = torch.full((P, self.n), -1, dtype=torch.int16, device=d)
         self.rec_played = torch.zeros((P, self.n), dtype=torch.bool, device=d)
         self.plies = 0
+        self._flag = None      # pinned host copy of any_active, one word per ply
+        self.finished = False  # set by play() once it has seen every game over
         # game-loop state on the device: active[g] = 1 while game g is running, the move about to
         # be played, and a one-word "any game still running" flag (xq_selfplay_commit / _finish)
         self.active = torch.ones(self.n, dtype=torch.uint8, device=d)
@@ -279,7 +287,11 @@ class BatchedSelfPlay:
         # past the end are no-ops (every game inactive) and are not counted
         lag = 2
         first = self.plies
-        flag = torch.ones((MAX_PLIES,), dtype=torch.int32).pin_memory() if check_done else None
+        flag = None
+        if check_done:
+            if self._flag is None:
+                self._flag = torch.ones((MAX_PLIES,), dtype=torch.int32).pin_memory()
+            flag = self._flag
         events = {}
         for ply in range(self.plies, min(MAX_PLIES, self.plies + max_plies)):
             mv, vis, nc = self._search()
@@ -311,12 +323,14 @@ class BatchedSelfPlay:
                     events.pop(q).synchronize()
                     if int(flag[q]) == 0:
                         self.plies = q + 1
+                        self.finished = True
                         break
         if check_done:  # the last `lag` plies were not looked at inside the loop
             for q in sorted(events):
                 events[q].synchronize()
                 if int(flag[q]) == 0:
                     self.plies = min(self.plies, q + 1)
+                    self.finished = True
                     break
 
     def stats(self) -> Dict[str, int]:
@@ -326,53 +340,191 @@ class BatchedSelfPlay:
     def materialise(self, red_only: bool = False) -> List[Tuple[list, int, str]]:
         """-> [(game_data, winner, end_reason)] in the reference's format (self_play.py:312)."""
         P = self.plies
-        rb = self.rec_board[:P].cpu().numpy()
-        rp = self.rec_player[:P].cpu().numpy()
-        rm = self.rec_moves[:P].cpu().numpy()
-        rv = self.rec_visits[:P].cpu().numpy()
-        rn = self.rec_n[:P].cpu().numpy()
-        rr = self.rec_reward[:P].cpu().numpy()
-        played = self.rec_played[:P].cpu().numpy()
         meta = self.boards.meta_host()
-        out = []
-        for g in range(self.n):
-            game_data, step_rewards = [], []
-            for p in range(P):
-                if not played[p, g]:
-                    break
-                k = int(rn[p, g])
-                counts = rv[p, g, :k].astype(np.int64)
-                if self.temperature < 0.01:
-                    probs = np.zeros(k)
-                    probs[np.argmax(counts)] = 1
-                else:
-                    c = counts ** (1.0 / self.temperature)
-                    probs = c / c.sum()
-                player = int(rp[p, g])
-                if player == 1 or not red_only:
-                    game_data.append((rb[p, g].reshape(10, 9).copy(),
-                                      {unpack_move(m): pr for m, pr in zip(rm[p, g, :k].tolist(), probs)},
-                                      player))
-                step_rewards.append(float(rr[p, g]))
-            w = int(meta["winner"][g])
-            winner = 0 if w == _lib.WINNER_NONE else w
-            reason = format_end_reason(int(meta["reason"][g]), int(meta["player"][g]),
-                                       int(meta["move_count"][g])) or "未知原因"
-            out.append((_shape_rewards(game_data, step_rewards, winner), winner, reason))
+        return materialise_arrays(
+            self.rec_board[:P].cpu().numpy(), self.rec_player[:P].cpu().numpy(),
+            self.rec_moves[:P].cpu().numpy(), self.rec_visits[:P].cpu().numpy(),
+            self.rec_n[:P].cpu().numpy(), self.rec_reward[:P].cpu().numpy(),
+            self.rec_played[:P].cpu().numpy(), meta["winner"], meta["reason"], meta["player"],
+            meta["move_count"], self.temperature, red_only)
+
+
+_MOVE_TUPLES: List[Move] = []
+
+
+def _move_tuples() -> List[Move]:
+    if not _MOVE_TUPLES:
+        _MOVE_TUPLES.extend(unpack_move(m) for m in range(_lib.POLICY))
+    return _MOVE_TUPLES
+
+
+class _LazyMoveProbs(dict):
+    """The ``{move: prob}`` dict of one sample (self_play.py:236), filled on first use.
+
+    ``Trainer`` stores these dicts in its replay buffer and never reads them (trainer.py:311-321
+    trains on boards and rewards only), so building 40-entry dicts of numpy scalars for every
+    sample of a large batch would cost more host time than the games took on the GPU.  The
+    packed moves and visit counts of the ply are kept instead; any read access, comparison, copy
+    or pickle fills the dict with exactly the keys, order and float64 values the eager path
+    produced."""
+    __slots__ = ("_src",)
+
+    def _fill(self) -> None:
+        # _src = (moves int16[P,128], visits int32[P,128], ply, n_moves, temperature) or unset
+        src = getattr(self, "_src", None)
+        if src is None:
+            return
+        self._src = None
+        moves, visits, p, k, temperature = src
+        moves_row = moves[p, :k]
+        counts = visits[p, :k].astype(np.int64)
+        if temperature < 0.01:                                   # self_play.py:225-228
+            probs = np.zeros(len(counts))
+            probs[np.argmax(counts)] = 1
+        else:                                                    # :230-231
+            c = counts ** (1.0 / temperature)
+            probs = c / c.sum()
+        tup = _move_tuples()
+        dict.update(self, zip((tup[m] for m in moves_row.tolist()), probs))
+
+    def _filled(name):  # noqa: N805 — builds the forwarding methods below
+        base = getattr(dict, name)
+
+        def method(self, *a, **k):
+            self._fill()
+            return base(self, *a, **k)
+        method.__name__ = name
+        return method
+
+    for _n in ("__getitem__", "__iter__", "__len__", "__contains__", "__eq__", "__ne__", "__repr__",
+               "__reversed__", "__or__", "__ror__", "__setitem__", "__delitem__", "__ior__",
+               "get", "items", "keys", "values", "copy", "pop", "popitem", "setdefault", "update", "clear"):
+        locals()[_n] = _filled(_n)
+    del _n, _filled
+
+    def __bool__(self) -> bool:
+        return self.__len__() > 0
+
+    def __reduce__(self):  # pickles (data/best_games.pkl, trainer.py:487-497) as a plain dict
+        self._fill()
+        return (dict, (dict(self),))
+
+
+def materialise_arrays(rb, rp, rm, rv, rn, rr, played, winner_m, reason_m, player_m, move_count_m,
+                       temperature: float, red_only: bool = False, lazy: bool = True
+                       ) -> List[Tuple[list, int, str]]:
+    """Recorded plies of a batch (arrays [P, n, ...]) -> the reference's
+    ``[(game_data, winner, end_reason)]`` (self_play.py:203-312), vectorised over all samples:
+    reward shaping in float64 with the reference's constants and operation order, boards as
+    views of one array, move-prob dicts lazily (``lazy=False`` builds them eagerly)."""
+    P, n = played.shape
+    out: List[Tuple[list, int, str]] = []
+    if n == 0:
         return out
+    played = played.astype(bool)
+    # a game's plies are a prefix (a game never resumes): count instead of scanning for the gap
+    n_plies = np.where(played.all(0), P, np.argmin(played, axis=0)) if P else np.zeros(n, np.int64)
+    prefix = np.arange(P)[:, None] < n_plies[None, :]
+    keep = prefix & ((rp == 1) if red_only else True)                        # :234
+    n_samples = keep.sum(0)
+    winner = np.where(winner_m == _lib.WINNER_NONE, 0, winner_m).astype(np.int64)   # :259
+    # final reward by (winner, player, game_length = samples of the game) — :264-298
+    L = n_samples[None, :]
+    pl = rp.astype(np.int64)
+    w = winner[None, :]
+    draw = np.where(L >= 60, np.where(pl == 1, -0.15, 0.05), np.where(pl == 1, -0.1, 0.1))
+    win = 1.0 + np.where(L <= 30, 0.5, np.where(L <= 50, 0.3, np.where(L <= 70, 0.1, 0.0)))
+    lose = np.where(L >= 60, -1.2, -1.0)
+    fin = np.where(w == 0, draw, np.where(w == pl, win, lose))
+    # step_rewards is indexed by SAMPLE index (:303-304): the i-th kept sample of a game takes
+    # the reward of the game's i-th ply
+    sidx = np.cumsum(keep, axis=0) - 1
+    imm = np.take_along_axis(rr, np.clip(sidx, 0, max(P - 1, 0)), axis=0) if P else rr
+    imm = np.where(sidx < n_plies[None, :], imm, 0.0)
+    total = fin + imm * 0.01                                                  # :308
+    boards = np.ascontiguousarray(rb.transpose(1, 0, 2)).reshape(n, P, 10, 9)  # [n, P, 10, 9]
+    total_t, keep_t = np.ascontiguousarray(total.T), np.ascontiguousarray(keep.T)
+    rm_t, rv_t, rn_t = rm.transpose(1, 0, 2), rv.transpose(1, 0, 2), rn.T
+    # millions of small containers are created below; the cyclic collector would rescan them
+    # again and again (measured: 1.5 s with it, 0.24 s without, for 4,096 games x 70 plies)
+    gc_was_on = gc.isenabled()
+    gc.disable()
+    try:
+        _build_games(out, n, keep_t, total_t, boards, rm_t, rv_t, rn_t, temperature, lazy, winner,
+                     reason_m, player_m, move_count_m)
+    finally:
+        if gc_was_on:
+            gc.enable()
+    return out
+
+
+def _build_games(out, n, keep_t, total_t, boards, rm_t, rv_t, rn_t, temperature, lazy, winner,
+                 reason_m, player_m, move_count_m) -> None:
+    for g in range(n):
+        ps = np.flatnonzero(keep_t[g]).tolist()
+        rew = total_t[g].tolist()
+        bg, mg, vg, kg = boards[g], rm_t[g], rv_t[g], rn_t[g].tolist()
+        game_data = []
+        for p in ps:
+            probs = _LazyMoveProbs()
+            probs._src = (mg, vg, p, kg[p], temperature)
+            if not lazy:
+                probs._fill()
+            game_data.append((bg[p], probs, rew[p]))
+        reason = format_end_reason(int(reason_m[g]), int(player_m[g]), int(move_count_m[g])) or "未知原因"
+        out.append((game_data, int(winner[g]), reason))
+
+
+def _progress(done: int, total: int, valid: int) -> None:
+    """The reference's progress line (self_play.py:411-431): a 50-column bar, games finished and
+    the share of them that produced data."""
+    frac = done / total if total else 1.0
+    bar = "=" * int(50 * frac) + " " * (50 - int(50 * frac))
+    rate = valid / done * 100 if done else 0
+    tail = f" | 有效:{valid} ({rate:.0f}%)" if done else ""
+    print(f"\r   进度: [{bar}] {done}/{total} ({frac * 100:.1f}%){tail}", end="", flush=True)
 
 
 def parallel_self_play(network, num_games, temperature=1.0, num_simulations=None, num_workers=4,
                        opponent_network=None):
     """Reference signature (self_play.py:368).  ``num_workers`` is accepted for compatibility;
-    the games run as one device batch instead of a process pool.  Raises
-    ``InterruptedWithResults`` on Ctrl-C with the games finished so far."""
+    the games run as one device batch instead of a process pool.  Like the reference's workers
+    (:339,:346) the networks are put in eval mode.  Progress is printed in the reference's format
+    as games finish; Ctrl-C raises ``InterruptedWithResults`` carrying the games that had
+    finished (:433-452)."""
     n_sims = num_simulations if num_simulations else MCTS_SIMULATIONS
+    for net in (network, opponent_network):
+        if isinstance(net, torch.nn.Module):
+            net.eval()
+    red_only = opponent_network is not None
     sp = BatchedSelfPlay(network, num_games, n_sims, temperature, opponent_network)
+    _progress(0, num_games, 0)
     try:
-        sp.play()
+        # a few plies per slice so that the progress line moves and Ctrl-C is honoured promptly
+        while sp.plies < MAX_PLIES and not sp.finished:
+            sp.play(max_plies=PROGRESS_EVERY_PLIES)
+            done = int((sp.active == 0).sum())
+            _progress(done, num_games, done)
     except KeyboardInterrupt:
-        done = sp.boards.meta_host()["done"].astype(bool)
-        res = sp.materialise(red_only=opponent_network is not None)
-        raise InterruptedWithResults([r for r, d in zip(res, done) if d])
-    return sp.materialise(red_only=opponent_network is not None)
+        print("\n\n⚠️  检测到Ctrl+C，正在停止对弈...", flush=True)
+        torch.cuda.synchronize(sp.device)
+        done = (sp.active == 0).cpu().numpy().astype(bool)
+        res = sp.materialise(red_only=red_only)
+        results = [r for r, d in zip(res, done) if d]
+        print("✓ 已停止对弈", flush=True)
+        print(f"提示: 已完成 {len(results)} 局对弈，数据将被保存", flush=True)
+        raise InterruptedWithResults(results)
+    _progress(num_games, num_games, num_games)
+    print()
+    return sp.materialise(red_only=red_only)
+
+
+def test_self_play():
+    """``python main.py test`` calls this (main.py:182): one rendered game with few simulations."""
+    from .neural_network import ChessNet
+    print("测试自我对弈系统...")
+    network = ChessNet().to(torch.device("cuda"))
+    network.eval()
+    game_data, winner, end_reason = self_play_game(network, render=True, num_simulations=10)
+    print(f"\n对局结束！ 总步数: {len(game_data)}  胜者: {['和局', '红方', '黑方'][winner]}  "
+          f"结束原因: {end_reason}  训练样本: {len(game_data)}")

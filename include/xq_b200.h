@@ -145,6 +145,11 @@ int xq_pick_moves(const int8_t *board, const xq_meta *meta, const int16_t *moves
                   uint32_t ply, int capture_bias, int16_t *picked, int n_games,
                   void *stream);
 
+/* Diagnostics for the fused playout's per-lane kernels: while `device_buf` (3 uint64 per warp of
+ * the launch, zero-filled by the caller) is registered, each warp records {first start ns, last
+ * end ns, SM id}.  NULL (the default) switches it off.  Not part of the reference's surface. */
+int xq_debug_playout_timing(uint64_t *device_buf);
+
 /* Fused random playout: up to max_plies x (get_legal_moves -> pick ->
  * make_move) per game in ONE launch, state in shared memory
  * (the loop of self_play.py:203-256 with the search replaced by the pick rule).
