@@ -58,6 +58,7 @@ SIGNATURES = {
     "xq_legal_moves": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "xq_query_checks": (_i, [_vp, _vp, _vp, _i, _vp]),
     "xq_step": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "xq_step_pick": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _u64, _u32, _u32, _i, _vp, _vp, _vp, _i, _vp]),
     "xq_pick_moves": (_i, [_vp, _vp, _vp, _vp, _u64, _u32, _u32, _i, _vp, _i, _vp]),
     "xq_playout": (_i, [_vp, _vp, _vp, _i, _u64, _u32, _i, _i, _vp,
                         _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
@@ -72,6 +73,9 @@ SIGNATURES = {
     "xq_mcts_init": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp]),
     "xq_mcts_select": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "xq_mcts_backup": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "xq_mcts_backup_rows": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp]),
+    "xq_compact_leaves": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
+    "xq_gather_leaves": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "xq_mcts_root_visits": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp]),
     "xq_sample_moves": (_i, [_vp, _vp, _vp, C.c_double, _u64, _u32, _u32, _vp, _i, _vp]),
     "xq_selfplay_commit": (_i, [_vp] * 15 + [_i, _vp]),

@@ -276,11 +276,14 @@ __global__ void __launch_bounds__(kThreadsM, 4)
   }
 }
 
+// row_of_game (optional): priors / values are COMPACT arrays that hold only the games whose wave
+// reached a network leaf; row_of_game[g] is game g's row in them (xq_compact_leaves).
 template <typename V>
 __global__ void __launch_bounds__(kThreadsM)
     mcts_backup_kernel(void* trees, int n_sims, const int16_t* __restrict__ leaf_moves,
                        const int16_t* __restrict__ leaf_n, const float* __restrict__ priors,
-                       const V* __restrict__ values, int values_per_game, int n_games) {
+                       const V* __restrict__ values, int values_per_game,
+                       const int32_t* __restrict__ row_of_game, int n_games) {
   const int g = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   if (g >= n_games) return;
   const int lane = threadIdx.x & 31;
@@ -290,6 +293,7 @@ __global__ void __launch_bounds__(kThreadsM)
   const int node = h.pending_node;
   if (node < 0) return;
   const int n = leaf_n[g];
+  const size_t row = row_of_game ? (size_t)row_of_game[g] : (size_t)g;
   if (t.nodes[node].first_child < 0) {  // expand (:61-68); idempotent
     const int first = h.n_nodes;
     if (first + n > h.node_cap) {
@@ -302,7 +306,7 @@ __global__ void __launch_bounds__(kThreadsM)
     }
     for (int i = lane; i < n; i += 32) {
       Node c = {};
-      c.prior = priors[(size_t)g * XQ_MAX_MOVES + i];
+      c.prior = priors[row * XQ_MAX_MOVES + i];
       c.first_child = -1;
       c.parent = node;
       c.move = leaf_moves[(size_t)g * XQ_MAX_MOVES + i];
@@ -318,7 +322,7 @@ __global__ void __launch_bounds__(kThreadsM)
   __syncwarp();
   if (lane == 0) {  // one update per queued simulation, in queue order (:146-148)
     for (int k = 0; k < h.pending_m; ++k) {
-      const double v = (double)values[values_per_game == 1 ? (size_t)g : (size_t)g * kWave + k];
+      const double v = (double)values[values_per_game == 1 ? row : row * kWave + k];
       backup_path(t, node, v);
     }
     h.pending_node = -1;
@@ -456,7 +460,76 @@ __global__ void __launch_bounds__(256)
   if (!active[g]) return;
   const bool on = move[g] >= 0 && !(step_flags[g] & XQ_STEP_DONE);
   active[g] = on ? 1 : 0;
-  if (on) *any_active = 1;  // same value from every writer
+  // number of games still running (zeroed by selfplay_commit_kernel): the host reads it a few
+  // plies late as "any game left?" and as the upper bound for leaf compaction
+  const unsigned m = __ballot_sync(__activemask(), on);
+  if (on && (threadIdx.x & 31) == (unsigned)(__ffs(m) - 1)) atomicAdd(any_active, __popc(m));
+}
+
+// Leaf compaction (ragged batches): ordered list of the games whose wave ended on a network
+// leaf (leaf_n > 0), and each game's row in that list.  One CTA; every thread owns a contiguous
+// slice, a block-wide exclusive scan of the slice counts places them in game order.
+__global__ void __launch_bounds__(1024)
+    compact_leaves_kernel(const int16_t* __restrict__ leaf_n, int n_games, int32_t* __restrict__ idx,
+                          int32_t* __restrict__ row_of_game, int32_t* __restrict__ count) {
+  __shared__ int warp_sums[32];
+  const int tid = threadIdx.x, per = (n_games + 1023) / 1024;
+  const int lo = min(tid * per, n_games), hi = min(lo + per, n_games);
+  int mine = 0;
+  for (int g = lo; g < hi; ++g) mine += leaf_n[g] > 0;
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(kFull, incl, o);
+    if ((tid & 31) >= o) incl += v;
+  }
+  if ((tid & 31) == 31) warp_sums[tid >> 5] = incl;
+  __syncthreads();
+  if (tid < 32) {
+    int w = warp_sums[tid];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(kFull, w, o);
+      if (tid >= o) w += v;
+    }
+    warp_sums[tid] = w;
+  }
+  __syncthreads();
+  int pos = incl - mine + ((tid >> 5) ? warp_sums[(tid >> 5) - 1] : 0);
+  for (int g = lo; g < hi; ++g) {
+    if (leaf_n[g] > 0) {
+      idx[pos] = g;
+      row_of_game[g] = pos++;
+    } else {
+      row_of_game[g] = -1;
+    }
+  }
+  if (tid == 1023) *count = warp_sums[31];
+}
+
+// Rows idx[0..count) of the leaf arrays copied into compact arrays of `rows` rows; the padding
+// rows (count..rows) get an empty position (no legal moves -> all-zero priors, ignored values).
+__global__ void __launch_bounds__(128)
+    gather_leaves_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ count, int rows,
+                         const int8_t* __restrict__ leaf_board, const int8_t* __restrict__ leaf_player,
+                         const int16_t* __restrict__ leaf_moves, const int16_t* __restrict__ leaf_n,
+                         int8_t* __restrict__ out_board, int8_t* __restrict__ out_player,
+                         int16_t* __restrict__ out_moves, int16_t* __restrict__ out_n) {
+  const int r = blockIdx.x, k = threadIdx.x;
+  if (r >= rows) return;
+  const bool live = r < *count;
+  const int g = live ? idx[r] : 0;
+  // 96 board bytes = 24 words, 128 moves = 64 words
+  if (k < XQ_BOARD_STRIDE / 4)
+    reinterpret_cast<uint32_t*>(out_board + (size_t)r * XQ_BOARD_STRIDE)[k] =
+        live ? reinterpret_cast<const uint32_t*>(leaf_board + (size_t)g * XQ_BOARD_STRIDE)[k] : 0u;
+  if (k >= 32 && k < 32 + XQ_MAX_MOVES / 2)
+    reinterpret_cast<uint32_t*>(out_moves + (size_t)r * XQ_MAX_MOVES)[k - 32] =
+        live ? reinterpret_cast<const uint32_t*>(leaf_moves + (size_t)g * XQ_MAX_MOVES)[k - 32] : 0u;
+  if (k == 127) {
+    out_player[r] = live ? leaf_player[g] : (int8_t)1;
+    out_n[r] = live ? leaf_n[g] : (int16_t)0;
+  }
 }
 
 // Mirror of the oracle's deterministic evaluator (order-independent arithmetic).
@@ -547,12 +620,49 @@ int xq_mcts_backup(void* trees, int num_simulations, const int16_t* leaf_moves,
   if (values_f32)
     mcts_backup_kernel<float><<<ctas_m(n_games), kThreadsM, 0, (cudaStream_t)stream>>>(
         trees, num_simulations, leaf_moves, leaf_n, priors, (const float*)values, values_per_game,
-        n_games);
+        nullptr, n_games);
   else
     mcts_backup_kernel<double><<<ctas_m(n_games), kThreadsM, 0, (cudaStream_t)stream>>>(
         trees, num_simulations, leaf_moves, leaf_n, priors, (const double*)values, values_per_game,
-        n_games);
+        nullptr, n_games);
   return check_launch("xq_mcts_backup");
+}
+
+int xq_mcts_backup_rows(void* trees, int num_simulations, const int16_t* leaf_moves,
+                        const int16_t* leaf_n, const float* priors, const void* values, int values_f32,
+                        const int32_t* row_of_game, int n_games, void* stream) {
+  if (n_games == 0) return 0;
+  XQM_REQUIRE(trees && leaf_moves && leaf_n && priors && values && row_of_game && n_games > 0,
+              "null pointer or non-positive size");
+  if (values_f32)
+    mcts_backup_kernel<float><<<ctas_m(n_games), kThreadsM, 0, (cudaStream_t)stream>>>(
+        trees, num_simulations, leaf_moves, leaf_n, priors, (const float*)values, 1, row_of_game, n_games);
+  else
+    mcts_backup_kernel<double><<<ctas_m(n_games), kThreadsM, 0, (cudaStream_t)stream>>>(
+        trees, num_simulations, leaf_moves, leaf_n, priors, (const double*)values, 1, row_of_game, n_games);
+  return check_launch("xq_mcts_backup_rows");
+}
+
+int xq_compact_leaves(const int16_t* leaf_n, int n_games, int32_t* idx, int32_t* row_of_game,
+                      int32_t* count, void* stream) {
+  if (n_games == 0) return 0;
+  XQM_REQUIRE(leaf_n && idx && row_of_game && count && n_games > 0, "null pointer or non-positive size");
+  compact_leaves_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(leaf_n, n_games, idx, row_of_game, count);
+  return check_launch("xq_compact_leaves");
+}
+
+int xq_gather_leaves(const int32_t* idx, const int32_t* count, int rows, const int8_t* leaf_board,
+                     const int8_t* leaf_player, const int16_t* leaf_moves, const int16_t* leaf_n,
+                     int8_t* out_board, int8_t* out_player, int16_t* out_moves, int16_t* out_n,
+                     void* stream) {
+  if (rows == 0) return 0;
+  XQM_REQUIRE(idx && count && leaf_board && leaf_player && leaf_moves && leaf_n && out_board &&
+                  out_player && out_moves && out_n && rows > 0,
+              "null pointer or non-positive size");
+  gather_leaves_kernel<<<rows, 128, 0, (cudaStream_t)stream>>>(idx, count, rows, leaf_board, leaf_player,
+                                                              leaf_moves, leaf_n, out_board, out_player,
+                                                              out_moves, out_n);
+  return check_launch("xq_gather_leaves");
 }
 
 int xq_mcts_root_visits(const void* trees, int num_simulations, int16_t* moves, int32_t* visits,

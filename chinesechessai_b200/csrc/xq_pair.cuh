@@ -87,8 +87,8 @@ __device__ __forceinline__ int pair_movegen(ThreadBoard& w, Game& g, const uint3
   int my_own = 0;
   int ex = 0;
   {
-    const int okr = (ownK < 0 ? 0 : ownK) / 9;
-    const int lo = (okr - 3 < 0 ? 0 : okr - 3) * 9, hi = (okr + 4 > 10 ? 10 : okr + 4) * 9;
+    int lo, hi;
+    exotic_window(player, ownK < 0 ? 0 : ownK, &lo, &hi);
     const uint32_t* sw = reinterpret_cast<const uint32_t*>(w.sq);
     const int i_end = sub ? 23 : 12;
 #pragma unroll 1
@@ -100,7 +100,7 @@ __device__ __forceinline__ int pair_movegen(ThreadBoard& w, Game& g, const uint3
       const uint32_t pos = (l7 + 0x7F7F7F7Fu) & ~x & 0x80808080u;
       uint32_t own = player == 1 ? pos : neg;
       const uint32_t kab = player == 1 ? ((l7 + 0x03030303u) & neg) : (pos & ~(l7 + 0x7C7C7C7Cu));
-      if (kab) {  // a word spans 4 squares, the row window >= 36: testing both ends is exact
+      if (kab) {  // a word spans 4 squares, the window >= 27: testing both ends is exact
         const int a = 4 * i + ((__ffs(kab) - 1) >> 3), b = 4 * i + ((31 - __clz(kab)) >> 3);
         ex |= ((a >= lo && a < hi) || (b >= lo && b < hi)) ? 1 : 0;
       }

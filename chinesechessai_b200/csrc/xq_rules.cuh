@@ -603,15 +603,35 @@ XQ_HD Item gen_item(const W& w, const uint32_t* __restrict__ leap, int player, i
   return it;
 }
 
-// Warp-uniform hint for suicide(): can an enemy K/A/B ever matter?  They only
-// reach squares within two rows of themselves and a king steps one row at most,
-// so in a regular position (exactly one own king piece, standing on its cached
-// square) they are irrelevant unless one stands within 3 rows of that king.
-// Poked boards (several kings, stale or missing cache, :448-451 re-creates the
-// cache wherever a king piece moves) always take the full test.
+// Warp-uniform hint for suicide(): can an enemy K/A/B ever matter?  They reach squares within
+// two rows of themselves (bishop 2, advisor / king 1).  The squares that count in a regular
+// position (exactly one own king piece, standing on its cached square) are the king's own square
+// and the squares it can step to — one row away at most and, because _king_moves only generates
+// targets inside the mover's palace (chess_env.py:127-131), never outside the palace rows.  An
+// enemy K/A/B is therefore irrelevant unless it stands within two rows of those rows.  In play
+// that never happens (K/A stay in their palace, B on its side of the river), so games from the
+// start position never leave the fast path; round 1 used a flat 3-row window around the king,
+// which a bishop on the river row next to an advanced king tripped in 0.4 % of all plies — and a
+// pair on the slow path holds up its whole warp (38 % of the plies of the slowest groups).
+// Poked boards (several kings, stale or missing cache, :448-451 re-creates the cache wherever a
+// king piece moves) always take the full test.
+XQ_HD void exotic_window(int player, int own_king, int* lo_sq, int* hi_sq) {
+  const int kr = own_king / 9;
+  const int pal_lo = player == 1 ? 7 : 0, pal_hi = player == 1 ? 9 : 2;
+  int rmin = kr, rmax = kr;
+  const int a = xq_max(kr - 1, pal_lo), b = xq_min(kr + 1, pal_hi);
+  if (a <= b) {  // rows of the palace squares next to the king
+    rmin = xq_min(rmin, a);
+    rmax = xq_max(rmax, b);
+  }
+  *lo_sq = xq_max(rmin - 2, 0) * 9;
+  *hi_sq = (xq_min(rmax + 2, 9) + 1) * 9;  // exclusive; always >= 3 rows wide
+}
 XQ_HD bool exotic_piece(int p, int s, int player, int own_king) {
   const int ap = p < 0 ? -p : p;
-  return (p * player < 0) && ap <= BISHOP && xq_abs(s / 9 - own_king / 9) <= 3;
+  int lo, hi;
+  exotic_window(player, own_king, &lo, &hi);
+  return (p * player < 0) && ap <= BISHOP && s >= lo && s < hi;
 }
 template <class W>
 XQ_HD bool regular_king(const W& w, int player, int own_king, int n_own_kings) {

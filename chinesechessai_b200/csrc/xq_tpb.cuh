@@ -91,8 +91,8 @@ __device__ __forceinline__ int tpb_movegen(ThreadBoard& w, Game& g, const uint32
   // pieces (any code of the mover's sign) and the enemy K/A/B (|code| <= 3) of exotic_piece()
   int n_own = 0;
   bool ex = false;
-  const int okr = (ownK < 0 ? 0 : ownK) / 9;
-  const int lo = (okr - 3 < 0 ? 0 : okr - 3) * 9, hi = (okr + 4 > 10 ? 10 : okr + 4) * 9;
+  int lo, hi;
+  exotic_window(player, ownK < 0 ? 0 : ownK, &lo, &hi);
   const uint32_t* sw = reinterpret_cast<const uint32_t*>(w.sq);
 #pragma unroll 1
   for (int i = 0; i < 23; ++i) {
@@ -103,7 +103,7 @@ __device__ __forceinline__ int tpb_movegen(ThreadBoard& w, Game& g, const uint32
     const uint32_t pos = (l7 + 0x7F7F7F7Fu) & ~x & 0x80808080u;
     uint32_t own = player == 1 ? pos : neg;
     const uint32_t kab = player == 1 ? ((l7 + 0x03030303u) & neg) : (pos & ~(l7 + 0x7C7C7C7Cu));
-    if (kab) {  // a word spans 4 squares, the row window >= 36: testing both ends is exact
+    if (kab) {  // a word spans 4 squares, the window >= 27: testing both ends is exact
       const int a = 4 * i + ((__ffs(kab) - 1) >> 3), b = 4 * i + ((31 - __clz(kab)) >> 3);
       ex |= (a >= lo && a < hi) || (b >= lo && b < hi);
     }
@@ -279,7 +279,8 @@ __device__ __forceinline__ void tpb_finish(const ThreadBoard& w, Game& g, TpbSte
   } else {
     int cnt = 0;
 #pragma unroll 1
-    for (int i = PAIR ? Pair::sub() : 0; i < g.hist_len; i += PAIR ? 2 : 1) cnt += hist[i] == o.key_next;
+    // __ldcg: in the queue-fed kernel earlier entries were appended by warps on other SMs
+    for (int i = PAIR ? Pair::sub() : 0; i < g.hist_len; i += PAIR ? 2 : 1) cnt += __ldcg(hist + i) == o.key_next;
     if (PAIR) cnt += Pair::other(cnt);
     if (cnt >= 3) {
       o.done = 1; o.reward = 0.0; o.is_int = 1;

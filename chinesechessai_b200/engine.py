@@ -115,6 +115,18 @@ class BoardBatch:
                                    _ptr(self.n_moves) if want_next else None, self.n, _stream()))
         return self.reward, self.flags
 
+    def step_pick(self, seed: int, ply: int, first_game_id: int = 0, capture_bias: int = 0,
+                  picked: Optional[torch.Tensor] = None):
+        """One ply of the random-playout loop in ONE launch (xq_step_pick): pick from the legal
+        list in ``self.moves`` (left by ``legal_moves()`` or the previous call), make_move, next
+        legal list written back.  -> (reward f64[n], flags u8[n])."""
+        with torch.cuda.device(self.device):
+            check(self.lib.xq_step_pick(_ptr(self.board), _ptr(self.meta), _ptr(self.pos_hist),
+                                        self.hist_cap, _ptr(self.moves), _ptr(self.n_moves), seed,
+                                        first_game_id, ply, capture_bias, _ptr(self.reward),
+                                        _ptr(self.flags), _ptr(picked), self.n, _stream()))
+        return self.reward, self.flags
+
     def pick(self, seed: int, ply: int, first_game_id: int = 0, capture_bias: int = 0,
              out: Optional[torch.Tensor] = None) -> torch.Tensor:
         if out is None:

@@ -258,6 +258,8 @@ class BatchedMCTS:
         self.root_moves = torch.zeros((self.n, MAX_MOVES), dtype=torch.int16, device=d)
         self.root_visits = torch.zeros((self.n, MAX_MOVES), dtype=torch.int32, device=d)
         self.root_n = torch.zeros((self.n,), dtype=torch.int16, device=d)
+        self._cbuf = None
+        self.rows_evaluated = 0   # rows the evaluator has been run on (n per wave without compaction)
 
     # -- the three kernels ---------------------------------------------------------------
     def init(self, board: torch.Tensor, meta: torch.Tensor, active: Optional[torch.Tensor] = None):
@@ -288,15 +290,64 @@ class BatchedMCTS:
                                                _ptr(self.root_n), self.n, _stream()))
         return self.root_moves, self.root_visits, self.root_n
 
+    # -- leaf compaction (ragged batches) ------------------------------------------------------
+    def _compact_buffers(self):
+        if self._cbuf is None:
+            d, n = self.device, self.n
+            self._cbuf = dict(
+                idx=torch.zeros((n,), dtype=torch.int32, device=d),
+                row=torch.zeros((n,), dtype=torch.int32, device=d),
+                count=torch.zeros((1,), dtype=torch.int32, device=d),
+                board=torch.zeros((n, BOARD_STRIDE), dtype=torch.int8, device=d),
+                player=torch.ones((n,), dtype=torch.int8, device=d),
+                moves=torch.zeros((n, MAX_MOVES), dtype=torch.int16, device=d),
+                n=torch.zeros((n,), dtype=torch.int16, device=d))
+        return self._cbuf
+
+    def bucket(self, bound: int) -> int:
+        """Rows to evaluate for at most ``bound`` live leaves: rounded up to one of <= 16 sizes,
+        so that cuDNN / cuBLAS / the allocator see a handful of shapes, not one per ply."""
+        q = max(64, self.n // 16)
+        return self.n if bound >= self.n else max(q, min(self.n, -(-int(bound) // q) * q))
+
+    def evaluate_and_backup(self, evaluator: Callable, rows: Optional[int] = None) -> None:
+        """The evaluator call and xq_mcts_backup of one wave.  ``rows`` (an upper bound of the
+        number of games with a network leaf, from ``bucket()``) < n compacts the leaves first:
+        the reference never sends a finished game or a terminal leaf to the network
+        (self_play.py:126-139), a batch would otherwise run the forward on all n rows."""
+        if rows is None or rows >= self.n:
+            self.rows_evaluated += self.n
+            priors, values = evaluator(self.leaf_board, self.leaf_player, self.leaf_moves, self.leaf_n)
+            self.backup(priors, values)
+            return
+        c = self._compact_buffers()
+        with torch.cuda.device(self.device):
+            st = _stream()
+            check(self.lib.xq_compact_leaves(_ptr(self.leaf_n), self.n, _ptr(c["idx"]), _ptr(c["row"]),
+                                             _ptr(c["count"]), st))
+            check(self.lib.xq_gather_leaves(_ptr(c["idx"]), _ptr(c["count"]), rows, _ptr(self.leaf_board),
+                                            _ptr(self.leaf_player), _ptr(self.leaf_moves), _ptr(self.leaf_n),
+                                            _ptr(c["board"]), _ptr(c["player"]), _ptr(c["moves"]),
+                                            _ptr(c["n"]), st))
+        self.rows_evaluated += rows
+        priors, values = evaluator(c["board"][:rows], c["player"][:rows], c["moves"][:rows], c["n"][:rows])
+        assert priors.dtype == torch.float32 and priors.is_contiguous() and values.is_contiguous()
+        with torch.cuda.device(self.device):
+            check(self.lib.xq_mcts_backup_rows(_ptr(self.trees), self.num_simulations, _ptr(self.leaf_moves),
+                                               _ptr(self.leaf_n), _ptr(priors), _ptr(values),
+                                               1 if values.dtype == torch.float32 else 0, _ptr(c["row"]),
+                                               self.n, _stream()))
+
     # -- MCTS.search for the whole batch ---------------------------------------------------
     def search(self, board: torch.Tensor, meta: torch.Tensor, evaluator: Callable,
-               active: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+               active: Optional[torch.Tensor] = None, rows: Optional[int] = None
+               ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """Returns (moves int16[n,128], visit counts int32[n,128], n_children int16[n]); rows are
-        the root's children in ``get_legal_moves()`` order, like the dict of self_play.py:151-154."""
+        the root's children in ``get_legal_moves()`` order, like the dict of self_play.py:151-154.
+        ``rows``: see ``evaluate_and_backup`` (the caller guarantees that at most ``rows`` games
+        reach a network leaf in any wave, e.g. the number of games still running)."""
         self.init(board, meta, active)
         for start in range(0, self.num_simulations, WAVE):
             self.select(min(WAVE, self.num_simulations - start))
-            priors, values = evaluator(self.leaf_board, self.leaf_player, self.leaf_moves, self.leaf_n)
-            self.backup(priors, values)
+            self.evaluate_and_backup(evaluator, rows)
         return self.visits()
-

@@ -176,7 +176,7 @@ class BatchedSelfPlay:
     def __init__(self, network, n_games: int, num_simulations: int, temperature: float = 1.0,
                  opponent_network=None, device: Optional[torch.device] = None,
                  net_dtype: torch.dtype = torch.float32, seed: Optional[int] = None,
-                 first_game_id: int = 0, use_graph: Optional[bool] = None):
+                 first_game_id: int = 0, use_graph: Optional[bool] = None, compact: bool = True):
         self.n = int(n_games)
         self.n_sims = int(num_simulations)
         self.temperature = float(temperature)
@@ -209,6 +209,10 @@ class BatchedSelfPlay:
         self.rec_move = torch.full((P, self.n), -1, dtype=torch.int16, device=d)
         self.rec_played = torch.zeros((P, self.n), dtype=torch.bool, device=d)
         self.plies = 0
+        # number of games still running, as last seen by the host (read a few plies late from
+        # `any_active`); games only ever finish, so it bounds the live games of every later ply
+        self.live_bound = self.n
+        self.compact = bool(compact)
         self._flag = None      # pinned host copy of any_active, one word per ply
         self.finished = False  # set by play() once it has seen every game over
         # game-loop state on the device: active[g] = 1 while game g is running, the move about to
@@ -231,6 +235,24 @@ class BatchedSelfPlay:
     @property
     def done(self) -> torch.Tensor:
         return self.active == 0
+
+    def restart(self, opening_seed: Optional[int] = None, opening_plies: int = 4,
+                capture_bias: int = 0) -> None:
+        """Start a fresh batch in place: every game back to the initial position and, if
+        ``opening_seed`` is given, ``opening_plies`` random plies (the shared counter-based pick
+        rule, xq_playout) so that the games of the batch differ.  With few simulations the visit
+        distribution of a fresh search is a delta on the arg-max-prior child, so games that start
+        from the same position with the same network are all one trajectory (SURVEY §8d cfg 3)."""
+        self.boards.reset()
+        if opening_seed is not None and opening_plies > 0:
+            self.boards.playout(int(opening_seed), int(opening_plies), first_game_id=self.first_game_id,
+                                capture_bias=capture_bias)
+        self.plies = 0
+        self.finished = False
+        self.live_bound = self.n
+        self.active.fill_(1)
+        self.any_active.fill_(self.n)
+        self.rec_played.zero_()
 
     def _search(self):
         active = self.active
@@ -261,10 +283,14 @@ class BatchedSelfPlay:
         m, b = self.mcts, self.boards
         m.init(b.board, b.meta, active)
         if self.eval_black is None:
+            # leaf compaction: at most `live_bound` games are still running, so at most that many
+            # rows can carry a network leaf (never inside a captured graph: its shapes are fixed)
+            rows = None
+            if self.compact and self._graph is None and not torch.cuda.is_current_stream_capturing():
+                rows = m.bucket(self.live_bound)
             for start in range(0, self.n_sims, WAVE):
                 m.select(min(WAVE, self.n_sims - start))
-                pri, val = self.eval_red(m.leaf_board, m.leaf_player, m.leaf_moves, m.leaf_n)
-                m.backup(pri, val)
+                m.evaluate_and_backup(self.eval_red, rows)
         else:  # red's tree uses `network`, black's uses the opponent (self_play.py:195-211)
             red = (b.meta[:, 0].view(torch.int8) == 1)
             for start in range(0, self.n_sims, WAVE):
@@ -321,6 +347,7 @@ class BatchedSelfPlay:
                 q = ply - lag
                 if q >= first:
                     events.pop(q).synchronize()
+                    self.live_bound = min(self.live_bound, int(flag[q]))
                     if int(flag[q]) == 0:
                         self.plies = q + 1
                         self.finished = True
@@ -328,6 +355,7 @@ class BatchedSelfPlay:
         if check_done:  # the last `lag` plies were not looked at inside the loop
             for q in sorted(events):
                 events[q].synchronize()
+                self.live_bound = min(self.live_bound, int(flag[q]))
                 if int(flag[q]) == 0:
                     self.plies = min(self.plies, q + 1)
                     self.finished = True

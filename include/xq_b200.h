@@ -137,6 +137,18 @@ int xq_step(int8_t *board, xq_meta *meta, uint64_t *pos_hist, int hist_cap,
             const int16_t *move, double *reward, uint8_t *flags,
             int16_t *next_moves, int16_t *next_n, int n_games, void *stream);
 
+/* One ply of the random-playout game loop (self_play.py:203-256 with the search replaced by
+ * the shared pick rule) in ONE launch: choose a move from the legal list that the previous call
+ * (or xq_legal_moves) left in moves / n_moves, make_move it (chess_env.py:253-406), and write the
+ * next position's legal list back into moves / n_moves.  Equivalent to xq_pick_moves followed by
+ * xq_step with next_moves = moves; finished games and games without legal moves are frozen.
+ * picked (optional): the move played, -1 for frozen games. */
+int xq_step_pick(int8_t *board, xq_meta *meta, uint64_t *pos_hist, int hist_cap,
+                 int16_t *moves, int16_t *n_moves, uint64_t seed,
+                 uint32_t first_game_id, uint32_t ply, int capture_bias,
+                 double *reward, uint8_t *flags, int16_t *picked, int n_games,
+                 void *stream);
+
 /* Counter-based uniform move pick shared with the oracle:
  * philox4x32-10(key=seed, ctr=(first_game_id+g, ply,0,0)); see DESIGN.md.
  * picked[g] = -1 when n_moves[g]==0 or the game is done. */
@@ -258,6 +270,25 @@ int xq_mcts_backup(void *trees, int num_simulations, const int16_t *leaf_moves, 
                    const float *priors, const void *values, int values_f32,
                    int values_per_game, int n_games, void *stream);
 
+/* Leaf compaction for ragged batches.  The reference only sends simulations that reached a
+ * non-terminal leaf to the network (self_play.py:126-139: terminal leaves are backed up on the
+ * spot); in a batch, finished games and waves that ended on terminal leaves have leaf_n == 0.
+ * xq_compact_leaves lists the games with leaf_n > 0 in game order (idx int32[n_games], *count)
+ * and gives every game its row in that list (row_of_game int32[n_games], -1 if none);
+ * xq_gather_leaves copies those rows of the four leaf arrays into compact arrays of `rows` rows
+ * (rows >= *count; padding rows are empty positions); the evaluator then runs on `rows` rows and
+ * xq_mcts_backup_rows = xq_mcts_backup reading priors float32[rows][XQ_MAX_MOVES] / values[rows]
+ * (one per game) through row_of_game.  Visit counts are identical to the uncompacted search. */
+int xq_compact_leaves(const int16_t *leaf_n, int n_games, int32_t *idx, int32_t *row_of_game,
+                      int32_t *count, void *stream);
+int xq_gather_leaves(const int32_t *idx, const int32_t *count, int rows, const int8_t *leaf_board,
+                     const int8_t *leaf_player, const int16_t *leaf_moves, const int16_t *leaf_n,
+                     int8_t *out_board, int8_t *out_player, int16_t *out_moves, int16_t *out_n,
+                     void *stream);
+int xq_mcts_backup_rows(void *trees, int num_simulations, const int16_t *leaf_moves,
+                        const int16_t *leaf_n, const float *priors, const void *values,
+                        int values_f32, const int32_t *row_of_game, int n_games, void *stream);
+
 /* {move: child.visit_count} of the root (self_play.py:151-154), legal-move order. */
 int xq_mcts_root_visits(const void *trees, int num_simulations, int16_t *moves, int32_t *visits,
                         int16_t *n_children, int n_games, void *stream);
@@ -280,8 +311,9 @@ int xq_sample_moves(const int32_t *visits, const int16_t *n_children, const uint
  * per-ply rows, resolves chosen[g] to the move to play (move[g] = -1 for a game that is
  * inactive or has no legal move) and clears *any_active;
  * xq_selfplay_finish, called after xq_step(move), retires games: active[g] stays 1 only if
- * the game was stepped and the step did not end it (:254-255), and *any_active is set to 1 if
- * any game is still running.
+ * the game was stepped and the step did not end it (:254-255), and *any_active receives the
+ * NUMBER of games still running (0 = the batch is over; the count also bounds the rows the
+ * next searches have to evaluate, see xq_compact_leaves).
  * rec_board int8[n][90], rec_player int8[n], rec_moves int16[n][XQ_MAX_MOVES],
  * rec_visits int32[n][XQ_MAX_MOVES], rec_n int16[n], rec_played uint8[n], rec_move int16[n]. */
 int xq_selfplay_commit(const int16_t *root_moves, const int32_t *root_visits,

@@ -356,6 +356,37 @@ def gen_positions(pool, n_jobs, per_job):
     return out
 
 
+
+# ---- compare_models.play_match --------------------------------------------------------------
+def play_match_job(args):
+    """The reference's UNCHANGED compare_models.play_match (compare_models.py:13-92) with two
+    injected evaluators; the simulation count is the module default MCTS(network) picks up
+    (self_play.MCTS_SIMULATIONS, set to `n_sims` here — a configuration value, not code).  Every
+    make_move is logged through a wrapper so that the goldens hold the move sequences too."""
+    seed, n_games, n_sims = args
+    chess_env, self_play = import_reference()
+    with contextlib.redirect_stdout(io.StringIO()):
+        import compare_models
+    self_play.MCTS_SIMULATIONS = n_sims
+    log = []
+    orig = chess_env.ChineseChess.make_move
+
+    def logged(self, move):
+        log.append(pack(move))
+        return orig(self, move)
+    chess_env.ChineseChess.make_move = logged
+    try:
+        np.random.seed(seed)
+        res = compare_models.play_match(StubNet(False), StubNet(True), num_games=n_games, verbose=False)
+    finally:
+        chess_env.ChineseChess.make_move = orig
+    return dict(seed=seed, n_games=n_games, n_sims=n_sims, result=res, moves=log)
+
+
+def gen_play_match(pool, quick):
+    jobs = [(11, 2, 15)] if quick else [(11, 3, 15), (12, 2, 20)]
+    return pool.map(play_match_job, jobs, chunksize=1)
+
 # ---- MCTS ---------------------------------------------------------------------------
 class StubNet:
     """Deterministic evaluator injected into the reference MCTS: priors are
@@ -594,8 +625,15 @@ def main():
     from oracle import xq_oracle as xo
     xo.build()
     t0 = time.time()
+    # The reference's PUCT arithmetic follows NumPy's scalar promotion: float32 under NumPy >= 2
+    # (NEP 50), float64 under NumPy 1.x (its requirements.txt allows >= 1.24).  The goldens, the
+    # oracle and the CUDA kernels are pinned to the NumPy >= 2 behaviour.
+    assert int(np.__version__.split(".")[0]) >= 2, "goldens must be generated under NumPy >= 2 (NEP 50)"
     manifest = {"reference": REF, "numpy": np.__version__, "seed": SEED,
-                "generated_by": "tests/golden/gen_golden.py"}
+                "generated_by": "tests/golden/gen_golden.py",
+                "numpy_semantics": "NumPy >= 2 (NEP 50): MCTSNode.select_child computes PUCT in float32; "
+                                   "under NumPy 1.x the same code promotes to float64 and near-ties may "
+                                   "resolve differently (not covered by these goldens)"}
     only = set(a.only.split(",")) if a.only else None
     with mp.Pool(a.procs) as pool:
         if not only or "kats" in only:
@@ -612,6 +650,11 @@ def main():
             np.savez_compressed(os.path.join(HERE, "mcts.npz"), **mc)
             manifest["mcts_searches"] = int(len(mc["player"]))
             print("mcts", len(mc["player"]), time.time() - t0, flush=True)
+        if not only or "play_match" in only:
+            pm = gen_play_match(pool, a.quick)
+            json.dump(pm, open(os.path.join(HERE, "play_match.json"), "w"), ensure_ascii=False)
+            manifest["play_match_runs"] = len(pm)
+            print("play_match", len(pm), time.time() - t0, flush=True)
         if not only or "selfplay" in only:
             sp = gen_selfplay(pool, a.quick)
             json.dump(sp, open(os.path.join(HERE, "selfplay.json"), "w"), ensure_ascii=False)

@@ -146,17 +146,137 @@ def test_search_cfg3_size_properties(mods, xo):
             assert np.array_equal(mv1[g, :c[g]].cpu().numpy(), om) and np.array_equal(v[g, :c[g]], ov), g
 
 
-def test_opponent_mode_runs_and_records_red_only(mods):
+def test_batched_opponent_mode_vs_oracle_game_loop(mods, xo):
+    """Opponent mode of the batched game loop (self_play.py:190-198,211,234: red searches with
+    `network`, black with `opponent_network`, only red's positions become samples, step rewards
+    indexed by SAMPLE index) against the same loop on the oracle with the two hashed evaluators:
+    move by move, outcome and shaped sample rewards."""
+    eng, mcts = mods
+    from chinesechessai_b200 import self_play
+    for n, n_sims, temp, seed, first in ((20, 15, 1.0, 3, 0), (8, 30, 0.5, 4, 500)):
+        sp = self_play.BatchedSelfPlay(mcts.HashEvaluator(False), n, n_sims, temperature=temp,
+                                       opponent_network=mcts.HashEvaluator(True), seed=seed, first_game_id=first)
+        sp.play()
+        res = sp.materialise(red_only=True)
+        P = sp.plies
+        rm, rv, rn = (t[:P].cpu().numpy() for t in (sp.rec_moves, sp.rec_visits, sp.rec_n))
+        played, rmove = sp.rec_played[:P].cpu().numpy(), sp.rec_move[:P].cpu().numpy()
+        meta = sp.boards.meta_host()
+        for g, (data, winner, reason) in enumerate(res):
+            e = xo.Env()
+            rewards, red_boards = [], []
+            for p in range(70):
+                red = e.current_player == 1
+                om, ov, _ = xo.mcts_search(e, n_sims, flat=not red)     # red: hashed priors, black: flat
+                if len(e.legal_moves_packed()) == 0 or len(om) == 0:
+                    break
+                assert played[p, g], (g, p)
+                k = int(rn[p, g])
+                assert np.array_equal(rm[p, g, :k], om) and np.array_equal(rv[p, g, :k], ov), (g, p)
+                idx = xo.sample_move(ov, temp, seed, first + g, p)
+                assert int(rmove[p, g]) == int(om[idx]), (g, p)
+                if red:
+                    red_boards.append(e.board.copy())
+                rw, _, done = e.make_move(int(om[idx]))
+                rewards.append(rw)
+                if done:
+                    break
+            assert not played[len(rewards):, g].any() and played[:len(rewards), g].all(), g
+            w = 0 if e.winner is None else e.winner
+            assert winner == w and meta["reason"][g] == e.s.reason, g
+            assert len(data) == len(red_boards)
+            for i, (b, probs, total) in enumerate(data):
+                assert np.array_equal(b, red_boards[i])
+                # game_length = number of SAMPLES, immediate reward = step_rewards[sample index]
+                assert repr(total) == repr(self_play.final_reward(w, 1, len(data)) + rewards[i] * 0.01), (g, i)
+
+
+def test_batched_play_match_vs_oracle_loop(mods, xo):
+    """chinesechessai_b200.compare_models.play_match (all games of a match as one device batch)
+    against compare_models.py:35-92 restated on the oracle: same winners and move counts, hence
+    the same result dict."""
+    eng, mcts = mods
+    from chinesechessai_b200.compare_models import MATCH_TEMPERATURE, play_match
+    n, n_sims, seed = 10, 15, 21
+    got = play_match(mcts.HashEvaluator(False), mcts.HashEvaluator(True), num_games=n, verbose=False,
+                     num_simulations=n_sims, seed=seed)
+    wins1 = wins2 = draws = total_moves = 0
+    for g in range(n):
+        e = xo.Env()
+        for p in range(100):
+            if len(e.legal_moves_packed()) == 0 or e.winner is not None:
+                break
+            om, ov, _ = xo.mcts_search(e, n_sims, flat=e.current_player != 1)
+            if len(om) == 0:
+                break
+            e.make_move(int(om[xo.sample_move(ov, MATCH_TEMPERATURE, seed, g, p)]))
+        total_moves += e.s.move_count
+        wins1 += e.winner == 1
+        wins2 += e.winner == -1
+        draws += e.winner not in (1, -1)
+    assert got["model1_wins"] == wins1 and got["model2_wins"] == wins2 and got["draws"] == draws
+    assert got["avg_moves"] == total_moves / n
+    assert got["model1_winrate"] == wins1 / n * 100 and got["draw_rate"] == draws / n * 100
+
+
+def test_leaf_compaction_keeps_visit_counts(mods, xo):
+    """BatchedMCTS with leaf compaction (only the games whose wave reached a network leaf go
+    through the evaluator) gives the same trees as the full-batch search, on a ragged batch:
+    finished games, inactive games and end-of-game positions where whole waves end on terminal
+    leaves."""
+    import torch
+    eng, mcts = mods
+    n, n_sims = 600, 50
+    bb = eng.BoardBatch(n)
+    bb.playout(7, 40, capture_bias=200)             # some games are already over
+    late = eng.BoardBatch(n)
+    late.playout(8, 67)                             # 3 plies before the cap: terminal children everywhere
+    bb.board[n // 2:] = late.board[n // 2:]
+    bb.meta[n // 2:] = late.meta[n // 2:]
+    active = torch.ones(n, dtype=torch.uint8, device=bb.board.device)
+    active[::7] = 0
+    full = mcts.BatchedMCTS(n, n_sims)
+    mv0, vis0, nc0 = [t.clone() for t in full.search(bb.board, bb.meta, mcts.HashEvaluator(), active)]
+    meta = bb.meta_host()
+    over = int((meta["winner"] != 2).sum())
+    assert over > 10                                # the batch really is ragged
+    comp = mcts.BatchedMCTS(n, n_sims)
+    # a bound of n (no compaction), a loose one and the tight one
+    live = int(((meta["winner"] == 2) & (active.cpu().numpy() != 0)).sum())
+    for bound in (n, n - 1, live):
+        comp.rows_evaluated = 0
+        mv, vis, nc = comp.search(bb.board, bb.meta, mcts.HashEvaluator(), active, rows=comp.bucket(bound))
+        assert torch.equal(mv, mv0) and torch.equal(vis, vis0) and torch.equal(nc, nc0), bound
+        assert comp.rows_evaluated == comp.bucket(bound) * 7
+    assert comp.bucket(live) < n
+
+
+def test_self_play_with_and_without_compaction(mods):
+    """The batched game loop records the same games whether or not finished games are compacted
+    out of the evaluator's batch; staggered openings make the batch ragged (games end at
+    different plies)."""
     import torch
     eng, mcts = mods
     from chinesechessai_b200.self_play import BatchedSelfPlay
-    sp = BatchedSelfPlay(mcts.HashEvaluator(False), 12, 15, temperature=1.0,
-                         opponent_network=mcts.HashEvaluator(True), seed=3)
-    sp.play(12)
-    out = sp.materialise(red_only=True)
-    assert len(out) == 12
-    for gd, winner, reason in out:
-        assert len(gd) == 6 and all((b != 0).sum() >= 30 for b, _, _ in gd)
+    runs = []
+    for compact in (False, True):
+        sp = BatchedSelfPlay(mcts.HashEvaluator(), 160, 15, temperature=1.0, seed=11, compact=compact,
+                             use_graph=False)
+        sp.restart(opening_seed=5, opening_plies=0)
+        lib, b = sp.lib, sp.boards
+        for k in range(4):                            # game g starts after (g // 40) * 16 random plies
+            lo = k * 40
+            res = torch.zeros((40, 40), dtype=torch.uint8, device=b.board.device)
+            from chinesechessai_b200._lib import check
+            check(lib.xq_playout(b.board[lo:].data_ptr(), b.meta[lo:].data_ptr(), b.pos_hist[lo:].data_ptr(),
+                                 b.hist_cap, 5, lo, 16 * k, 0, res.data_ptr(), None, None, None, None, None,
+                                 None, 40, torch.cuda.current_stream().cuda_stream))
+        sp.play()
+        runs.append((sp.plies, sp.rec_move[:sp.plies].clone(), sp.rec_visits[:sp.plies].clone(),
+                     sp.rec_played[:sp.plies].clone(), sp.boards.board.clone(), sp.mcts.rows_evaluated))
+    a, b = runs
+    assert a[0] == b[0] and all(torch.equal(x, y) for x, y in zip(a[1:5], b[1:5]))
+    assert b[5] < a[5]                               # fewer rows went through the evaluator
 
 
 def test_bias_residual_relu_kernel(mods):

@@ -302,3 +302,80 @@ def test_batched_self_play_cuda_graph_with_network():
     expect = int(ref.rec_visits[0, 0].sum())
     # 15 sims = a wave of 8 that expands the root + a wave of 7 through its children (B.2)
     assert expect == 7 and bool((tot[played] == expect).all())
+
+
+def test_parallel_self_play_interrupt_carries_finished_games(pkg, monkeypatch, capsys):
+    """Ctrl-C during parallel_self_play raises InterruptedWithResults with exactly the games that
+    had finished (self_play.py:433-452), each a complete (game_data, winner, end_reason) equal to
+    the same game of an uninterrupted run; the progress line has the reference's format."""
+    _, self_play = pkg
+    from chinesechessai_b200.mcts import HashEvaluator
+    np.random.seed(123)
+    full = self_play.parallel_self_play(HashEvaluator(), 96, temperature=1.0, num_simulations=15)
+    out = capsys.readouterr().out
+    assert "进度: [" in out and "96/96 (100.0%)" in out and "有效:96 (100%)" in out
+    lengths = sorted(len(gd) for gd, _, _ in full)
+    calls = {"n": 0}
+    real = self_play._progress
+
+    def progress(done, total, valid):
+        calls["n"] += 1
+        real(done, total, valid)
+        if calls["n"] == 7:                 # after 60 plies: the shortest games are over, most are not
+            raise KeyboardInterrupt
+    monkeypatch.setattr(self_play, "_progress", progress)
+    np.random.seed(123)                     # same engine seed as the full run
+    with pytest.raises(self_play.InterruptedWithResults) as ei:
+        self_play.parallel_self_play(HashEvaluator(), 96, temperature=1.0, num_simulations=15)
+    part = ei.value.results
+    assert isinstance(part, list) and len(part) < 96
+    if lengths[0] <= 50:                    # some game was certainly over when the interrupt came
+        assert len(part) > 0
+    keyed = {(w, r, len(gd), gd[0][0].tobytes(), gd[-1][0].tobytes(), gd[-1][2]) for gd, w, r in full}
+    for gd, w, r in part:
+        assert (w, r, len(gd), gd[0][0].tobytes(), gd[-1][0].tobytes(), gd[-1][2]) in keyed
+
+
+def test_reference_play_match_on_shims_equals_reference_golden(pkg, xo, tmp_path):
+    """The reference's UNCHANGED compare_models.play_match, imported from the reference checkout
+    but running on the drop-in ChineseChess / MCTS classes, reproduces the result dict AND the
+    move sequences that the same function produced on the reference's own classes (golden
+    recorded by tests/golden/gen_golden.py with the same injected evaluators and np.random seed)."""
+    import subprocess
+    import sys
+    from baseline import reference as R
+    if R.locate() is None:
+        pytest.skip("no reference checkout (baseline/_ref, XQ_REFERENCE)")
+    gold = json.load(open(os.path.join(GOLDEN, "play_match.json"), encoding="utf-8"))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, json, io, contextlib\n"
+        "import numpy as np\n"
+        f"sys.path.insert(0, {root!r})\n"
+        "from oracle import xq_oracle as xo\n"
+        "from tests.test_shims_gpu import StubNet\n"
+        "with contextlib.redirect_stdout(io.StringIO()):\n"
+        "    import chess_env, self_play, compare_models\n"
+        "import chinesechessai_b200.self_play as ours\n"
+        "assert self_play.MCTS is ours.MCTS and compare_models.__file__.startswith(sys.argv[1])\n"
+        "out = []\n"
+        "for seed, n_games, n_sims in json.loads(sys.argv[2]):\n"
+        "    ours.MCTS_SIMULATIONS = n_sims\n"
+        "    log = []\n"
+        "    orig = chess_env.ChineseChess.make_move\n"
+        "    def logged(self, mv, orig=orig, log=log):\n"
+        "        log.append((mv[0] * 9 + mv[1]) * 90 + mv[2] * 9 + mv[3]); return orig(self, mv)\n"
+        "    chess_env.ChineseChess.make_move = logged\n"
+        "    np.random.seed(seed)\n"
+        "    res = compare_models.play_match(StubNet(xo, False), StubNet(xo, True), num_games=n_games, verbose=False)\n"
+        "    chess_env.ChineseChess.make_move = orig\n"
+        "    out.append(dict(result=res, moves=log))\n"
+        "print(json.dumps(out))\n")
+    jobs = json.dumps([(g["seed"], g["n_games"], g["n_sims"]) for g in gold])
+    p = subprocess.run([sys.executable, "-c", code, os.path.realpath(R.locate()), jobs], env=R.env_for_shims(),
+                       cwd=tmp_path, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stderr[-3000:]
+    got = json.loads([ln for ln in p.stdout.splitlines() if ln.startswith("[")][-1])
+    for a, g in zip(got, gold):
+        assert a["moves"] == g["moves"]
+        assert a["result"] == g["result"]
