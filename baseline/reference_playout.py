@@ -147,3 +147,49 @@ def playout_many(game_ids: List[int], seed: int, max_plies: int = 70, bias: int 
     for i, r in enumerate(rows):
         out[i] = r
     return {"results": out, "seconds": dt, "plies": int(out["plies"].sum()), "procs": procs}
+
+
+def run_subprocess(first: int, count: int, seed: int, max_plies: int = 70, bias: int = 0,
+                   procs: Optional[int] = None, timeout: float = 900.0) -> Dict[str, object]:
+    """playout_many() in a FRESH interpreter with CUDA hidden: a process that has already
+    initialised CUDA (bench.py's GPU arm) cannot fork workers that import the reference's
+    config.py (it probes torch.cuda at import)."""
+    import json
+    import subprocess
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ)
+    env["PYTHONPATH"] = root
+    env["CUDA_VISIBLE_DEVICES"] = ""
+    env["PYTHONDONTWRITEBYTECODE"] = "1"
+    with tempfile.TemporaryDirectory(prefix="xq_refplay_") as tmp:
+        out = os.path.join(tmp, "res.npy")
+        cmd = [sys.executable, "-m", "baseline.reference_playout", "--first", str(first), "--count", str(count),
+               "--seed", str(seed), "--max-plies", str(max_plies), "--bias", str(bias), "--out", out]
+        if procs:
+            cmd += ["--procs", str(procs)]
+        p = subprocess.run(cmd, env=env, cwd=root, capture_output=True, text=True, timeout=timeout)
+        lines = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+        if p.returncode != 0 or not lines:
+            raise RuntimeError("reference playout subprocess failed: " + (p.stderr or p.stdout)[-800:])
+        info = json.loads(lines[-1])
+        info["results"] = np.load(out)
+    return info
+
+
+if __name__ == "__main__":
+    import argparse
+    import json
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--first", type=int, default=0)
+    ap.add_argument("--count", type=int, default=8)
+    ap.add_argument("--seed", type=int, default=0x5EED)
+    ap.add_argument("--max-plies", type=int, default=70)
+    ap.add_argument("--bias", type=int, default=0)
+    ap.add_argument("--procs", type=int, default=0)
+    ap.add_argument("--out", default="")
+    a = ap.parse_args()
+    r = playout_many(list(range(a.first, a.first + a.count)), a.seed, a.max_plies, a.bias, a.procs or None)
+    if a.out:
+        np.save(a.out, r["results"])
+    print(json.dumps({"seconds": r["seconds"], "plies": r["plies"], "procs": r["procs"], "games": a.count}))

@@ -148,11 +148,11 @@ def py_reference(seconds: float, seed: int = SEED, first: int = 0):
         return None
     from baseline import reference_playout as rp
     procs = os.cpu_count() or 1
-    cal = rp.playout_many(list(range(first, first + procs)), seed, PLIES)      # one game per core
+    # fresh interpreters with CUDA hidden (this process may already hold a CUDA context)
+    cal = rp.run_subprocess(first, procs, seed, PLIES)                         # one game per core
     per_round = max(cal["seconds"], 1e-3)
     rounds = int(max(1, min(8, round(seconds / per_round) - 1)))
-    ids = list(range(first + procs, first + procs * (1 + rounds)))
-    run = rp.playout_many(ids, seed, PLIES)
+    run = rp.run_subprocess(first + procs, procs * rounds, seed, PLIES)
     import numpy as np
     results = np.concatenate([cal["results"], run["results"]])
     plies, dt = cal["plies"] + run["plies"], cal["seconds"] + run["seconds"]
@@ -322,7 +322,7 @@ def make_evaluator(torch, net, precision):
     from chinesechessai_b200.mcts import NetEvaluator
     if precision == "bf16":
         return NetEvaluator(net, torch.bfloat16)
-    return NetEvaluator(net, torch.float32, tf32=(precision == "tf32"))
+    return NetEvaluator(net, torch.float32, tf32=(precision == "tf32"))   # fp32 leg: TF32 forced OFF
 
 
 def precision_agreement(torch, dev, net, n_pos=4096):

@@ -24,6 +24,14 @@ from .engine import _ptr, _stream, pack_move, unpack_move
 Move = Tuple[int, int, int, int]
 
 _RED, _BLACK = "红方", "黑方"
+_MOVE_TUPLES: List[Move] = []
+
+
+def _move_tuples() -> List[Move]:
+    """(from_r, from_c, to_r, to_c) of every packed move from*90+to, built once."""
+    if not _MOVE_TUPLES:
+        _MOVE_TUPLES.extend(unpack_move(m) for m in range(_lib.POLICY))
+    return _MOVE_TUPLES
 
 
 def format_end_reason(reason: int, side_to_move: int, move_count: int) -> Optional[str]:
@@ -46,30 +54,50 @@ def format_end_reason(reason: int, side_to_move: int, move_count: int) -> Option
 
 
 class _Device1:
-    """Device + pinned staging buffers for a single board (shared by all envs of a process)."""
+    """Device + pinned staging for ONE board (shared by all envs of a process).
+
+    Everything a call exchanges with the GPU lives in one byte arena, mirrored in pinned host
+    memory: a rules call is ONE host->device copy, ONE kernel and ONE device->host copy (round 1
+    paid a separate synchronising copy per field — five per make_move — which is what the
+    reference's callers feel: evaluate.py / compare_models.py make ~1,400 such calls per match).
+
+    Arena layout (bytes): board 0:96 | meta 96:128 | move 128:130 | reward 136:144 | flags 144 |
+    query 152:156 | key 160:168 | n_moves 168:170 | moves 176:432 | position history 432:..."""
     _inst = None
+    O_BOARD, O_META, O_MOVE, O_REWARD, O_FLAGS, O_Q, O_KEY, O_NMOVES, O_MOVES, O_HIST = \
+        0, 96, 128, 136, 144, 152, 160, 168, 176, 432
 
     def __init__(self):
         self.lib = _lib.load()
         _lib.require_device()
         if not torch.cuda.is_available():
             raise _lib.XqError("torch sees no CUDA device; ChineseChess has no CPU fallback")
-        d = self.dev = torch.device("cuda", torch.cuda.current_device())
-        self.board = torch.zeros((1, BOARD_STRIDE), dtype=torch.int8, device=d)
-        self.meta = torch.zeros((1, 32), dtype=torch.uint8, device=d)
-        self.moves = torch.zeros((1, MAX_MOVES), dtype=torch.int16, device=d)
-        self.n_moves = torch.zeros((1,), dtype=torch.int16, device=d)
-        self.move = torch.zeros((1,), dtype=torch.int16, device=d)
-        self.reward = torch.zeros((1,), dtype=torch.float64, device=d)
-        self.flags = torch.zeros((1,), dtype=torch.uint8, device=d)
-        self.q = torch.zeros((1, 4), dtype=torch.uint8, device=d)
-        self.key = torch.zeros((1,), dtype=torch.int64, device=d)
-        self.hist_cap = 256
-        self.hist = torch.zeros((1, self.hist_cap), dtype=torch.int64, device=d)
-        init_b = torch.zeros((1, BOARD_STRIDE), dtype=torch.int8, device=d)
-        init_m = torch.zeros((1, 32), dtype=torch.uint8, device=d)
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+        self.hist_cap = 0
+        self._alloc(256)
+        init_b = torch.zeros((1, BOARD_STRIDE), dtype=torch.int8, device=self.dev)
+        init_m = torch.zeros((1, 32), dtype=torch.uint8, device=self.dev)
         check(self.lib.xq_reset(_ptr(init_b), _ptr(init_m), 1, _stream()))
         self.init_board = init_b[0, :90].cpu().numpy().reshape(BOARD_SIZE, BOARD_WIDTH).copy()
+
+    def _alloc(self, hist_cap: int) -> None:
+        self.hist_cap = hist_cap
+        size = self.O_HIST + 8 * hist_cap
+        self.d = torch.zeros(size, dtype=torch.uint8, device=self.dev)
+        self.h = torch.zeros(size, dtype=torch.uint8).pin_memory()
+        self.hn = self.h.numpy()
+        base = self.d.data_ptr()
+        self.p = {k: base + getattr(self, "O_" + k) for k in
+                  ("BOARD", "META", "MOVE", "REWARD", "FLAGS", "Q", "KEY", "NMOVES", "MOVES", "HIST")}
+        # typed host views of the pinned mirror
+        self.h_board = self.hn[self.O_BOARD:self.O_BOARD + BOARD_STRIDE].view(np.int8)
+        self.h_meta = self.hn[self.O_META:self.O_META + 32].view(META_DTYPE)
+        self.h_move = self.hn[self.O_MOVE:self.O_MOVE + 2].view(np.int16)
+        self.h_reward = self.hn[self.O_REWARD:self.O_REWARD + 8].view(np.float64)
+        self.h_nmoves = self.hn[self.O_NMOVES:self.O_NMOVES + 2].view(np.int16)
+        self.h_moves = self.hn[self.O_MOVES:self.O_MOVES + 2 * MAX_MOVES].view(np.int16)
+        self.h_key = self.hn[self.O_KEY:self.O_KEY + 8].view(np.uint64)
+        self.h_hist = self.hn[self.O_HIST:].view(np.uint64)
 
     @classmethod
     def get(cls) -> "_Device1":
@@ -79,8 +107,14 @@ class _Device1:
 
     def need_hist(self, n: int) -> None:
         if n + 1 > self.hist_cap:
-            self.hist_cap = max(2 * self.hist_cap, n + 64)
-            self.hist = torch.zeros((1, self.hist_cap), dtype=torch.int64, device=self.dev)
+            self._alloc(max(2 * self.hist_cap, n + 64))
+
+    def up(self, lo: int, hi: int) -> None:
+        self.d[lo:hi].copy_(self.h[lo:hi], non_blocking=True)
+
+    def down(self, lo: int, hi: int) -> None:
+        self.h[lo:hi].copy_(self.d[lo:hi], non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
 
 
 class ChineseChess:
@@ -112,10 +146,14 @@ class ChineseChess:
     def _sq(pos) -> int:
         return -1 if pos is None else int(pos[0]) * 9 + int(pos[1])
 
-    def _upload(self, dev: _Device1, with_hist: bool = False) -> None:
-        b = np.zeros((1, BOARD_STRIDE), np.int8)
-        b[0, :90] = np.asarray(self.board, dtype=np.int8).reshape(90)
-        m = np.zeros(1, META_DTYPE)
+    def _stage(self, dev: _Device1, with_hist: bool = False) -> int:
+        """Write this env into the pinned arena; returns the end offset of what has to go up."""
+        if with_hist:
+            dev.need_hist(len(self.position_history))
+        dev.h_board[:90] = np.asarray(self.board, dtype=np.int8).reshape(90)
+        dev.h_board[90:] = 0
+        m = dev.h_meta
+        m[:] = 0
         m["player"] = 1 if self.current_player == 1 else -1
         m["winner"] = _lib.WINNER_NONE if self.winner is None else int(self.winner)
         m["red_king"], m["black_king"] = self._sq(self.red_king_pos), self._sq(self.black_king_pos)
@@ -124,27 +162,26 @@ class ChineseChess:
         ck = self.check_history
         m["check_len"] = len(ck)
         m["check_bits"] = sum((1 << i) for i, v in enumerate(ck[-32:][::-1]) if v)
-        m["hist_len"] = len(self.position_history) if with_hist else 0
-        dev.board.copy_(torch.from_numpy(b))
-        dev.meta.copy_(torch.from_numpy(m.view(np.uint8).reshape(1, 32)))
-        if with_hist and self.position_history:
-            dev.need_hist(len(self.position_history))
-            h = np.array(self.position_history, dtype=np.uint64).view(np.int64)
-            dev.hist[0, :len(h)].copy_(torch.from_numpy(h))
-        elif with_hist:
-            dev.need_hist(0)
+        n_hist = len(self.position_history) if with_hist else 0
+        m["hist_len"] = n_hist
+        if n_hist:
+            dev.h_hist[:n_hist] = np.array(self.position_history, dtype=np.uint64)
+        return dev.O_HIST + 8 * n_hist if with_hist else dev.O_META + 32
 
     # -- chess_env.py:76-121 -----------------------------------------------------------------
     def get_legal_moves(self) -> List[Move]:
         dev = _Device1.get()
-        self._upload(dev)
-        check(dev.lib.xq_legal_moves(_ptr(dev.board), _ptr(dev.meta), _ptr(dev.moves),
-                                     _ptr(dev.n_moves), None, 1, _stream()))
-        n = int(dev.n_moves[0])
-        if int(dev.meta[0, 6]) & _lib.F_OVERFLOW:
+        self._stage(dev)
+        dev.up(0, dev.O_META + 32)
+        p = dev.p
+        check(dev.lib.xq_legal_moves(p["BOARD"], p["META"], p["MOVES"], p["NMOVES"], None, 1, _stream()))
+        dev.down(dev.O_META, dev.O_MOVES + 2 * MAX_MOVES)
+        if int(dev.h_meta["flags"][0]) & _lib.F_OVERFLOW:
             raise _lib.XqError("position exceeds the engine's capacity (>128 legal moves or >256 "
                                "pseudo-legal candidates)")
-        return [unpack_move(m) for m in dev.moves[0, :n].cpu().tolist()]
+        n = int(dev.h_nmoves[0])
+        tup = _move_tuples()
+        return [tup[m] for m in dev.h_moves[:n].tolist()]
 
     # -- chess_env.py:253-406 ----------------------------------------------------------------
     def make_move(self, move: Move):
@@ -152,22 +189,28 @@ class ChineseChess:
         if not (0 <= fr < BOARD_SIZE and 0 <= tr < BOARD_SIZE and 0 <= fc < BOARD_WIDTH and 0 <= tc < BOARD_WIDTH):
             raise IndexError(f"move {move} is off the 10x9 board")  # numpy raises here too (>= size)
         dev = _Device1.get()
-        self._upload(dev, with_hist=True)
-        dev.move.fill_(pack_move(move))
-        check(dev.lib.xq_step(_ptr(dev.board), _ptr(dev.meta), _ptr(dev.hist), dev.hist_cap,
-                              _ptr(dev.move), _ptr(dev.reward), _ptr(dev.flags), None, None, 1,
-                              _stream()))
-        m = dev.meta.cpu().numpy().view(META_DTYPE).reshape(-1)[0]
-        flags = int(dev.flags[0])
-        reward = float(dev.reward[0])
-        self.board = dev.board[0, :90].cpu().numpy().reshape(BOARD_SIZE, BOARD_WIDTH).copy()
+        end = self._stage(dev, with_hist=True)
+        dev.h_move[0] = pack_move((fr, fc, tr, tc))
+        dev.up(0, end)
+        p = dev.p
+        check(dev.lib.xq_step(p["BOARD"], p["META"], p["HIST"], dev.hist_cap, p["MOVE"], p["REWARD"],
+                              p["FLAGS"], None, None, 1, _stream()))
+        n_before = len(self.position_history)
+        dev.down(0, dev.O_HIST + 8 * (n_before + 1))
+        m = dev.h_meta[0]
+        if int(m["flags"]) & _lib.F_OVERFLOW:
+            raise _lib.XqError("position exceeds the engine's capacity (>128 legal moves, >256 "
+                               "pseudo-legal candidates or a full position history)")
+        flags = int(dev.hn[dev.O_FLAGS])
+        reward = float(dev.h_reward[0])
+        self.board = dev.h_board[:90].reshape(BOARD_SIZE, BOARD_WIDTH).copy()
         pos = lambda s: None if s < 0 else (int(s) // 9, int(s) % 9)
         self.red_king_pos, self.black_king_pos = pos(m["red_king"]), pos(m["black_king"])
         self.no_capture_count = int(m["no_capture"])
         self.consecutive_checks = int(m["consecutive_checks"])
         n_hist = int(m["hist_len"])
-        if n_hist > len(self.position_history):
-            self.position_history.append(int(np.uint64(dev.hist[0, n_hist - 1].item() & 0xFFFFFFFFFFFFFFFF)))
+        if n_hist > n_before:
+            self.position_history.append(int(dev.h_hist[n_hist - 1]))
         self.check_history.append(bool(int(m["check_bits"]) & 1))
         self.chase_history.append([])
         self.current_player = int(m["player"])
@@ -183,9 +226,11 @@ class ChineseChess:
     # -- private helpers the reference's own scripts call -------------------------------------
     def _query(self):
         dev = _Device1.get()
-        self._upload(dev)
-        check(dev.lib.xq_query_checks(_ptr(dev.board), _ptr(dev.meta), _ptr(dev.q), 1, _stream()))
-        return dev.q[0].cpu().tolist()
+        self._stage(dev)
+        dev.up(0, dev.O_META + 32)
+        check(dev.lib.xq_query_checks(dev.p["BOARD"], dev.p["META"], dev.p["Q"], 1, _stream()))
+        dev.down(dev.O_Q, dev.O_Q + 4)
+        return dev.hn[dev.O_Q:dev.O_Q + 4].tolist()
 
     def _is_in_check(self, player) -> bool:
         q = self._query()
@@ -196,9 +241,11 @@ class ChineseChess:
 
     def _get_position_hash(self) -> int:
         dev = _Device1.get()
-        self._upload(dev)
-        check(dev.lib.xq_position_hash(_ptr(dev.board), _ptr(dev.meta), _ptr(dev.key), 1, _stream()))
-        return int(dev.key[0].item()) & 0xFFFFFFFFFFFFFFFF
+        self._stage(dev)
+        dev.up(0, dev.O_META + 32)
+        check(dev.lib.xq_position_hash(dev.p["BOARD"], dev.p["META"], dev.p["KEY"], 1, _stream()))
+        dev.down(dev.O_KEY, dev.O_KEY + 8)
+        return int(dev.h_key[0])
 
     def _check_draw_by_repetition(self) -> bool:  # :598-605
         return self.position_history.count(self._get_position_hash()) >= 3

@@ -163,8 +163,10 @@ class NetEvaluator:
     """encode_board -> ChessNet.forward -> gather+softmax, all on device
     (neural_network.py:96-126 without the per-sample D2H of :120-124).
 
-    ``dtype=float32`` runs the module as given (the reference's precision; ``tf32=True`` lets
-    cuDNN/cuBLAS use TF32 tensor cores for it).  A lower-precision dtype builds a folded
+    ``dtype=float32`` runs the module as given (the reference's precision).  ``tf32`` = True /
+    False forces TF32 tensor cores on / off for cuDNN and cuBLAS during the forward; None leaves
+    PyTorch's switches alone, which is what the reference itself gets on a GPU (convolutions in
+    TF32 by default, matmuls in strict fp32).  A lower-precision dtype builds a folded
     inference copy (BN folded, ``dtype`` weights, channels-last).  The copy is rebuilt whenever
     the module's weights have changed since it was made — optimizer steps, ``load_state_dict``
     and the NCCL weight broadcast all bump the tensors' version counters, which is what
@@ -172,10 +174,11 @@ class NetEvaluator:
     weights.  The module must be in eval mode (the reference's workers force it,
     self_play.py:339,346): BatchNorm batch statistics must not leak into the search."""
 
-    def __init__(self, net: torch.nn.Module, dtype: torch.dtype = torch.float32, tf32: bool = False):
+    def __init__(self, net: torch.nn.Module, dtype: torch.dtype = torch.float32,
+                 tf32: Optional[bool] = None):
         self.net = net
         self.dtype = dtype
-        self.tf32 = bool(tf32)
+        self.tf32 = tf32      # None: PyTorch's own switches (cuDNN TF32 on, cuBLAS off by default)
         self._fast = None
         self._seen = None     # weight fingerprint the folded copy / captured graphs belong to
         self._version = 0
@@ -206,11 +209,10 @@ class NetEvaluator:
         _ = self.version
         if self.dtype == torch.float32:
             planes = encode_planes(leaf_board, leaf_player, dtype=self.dtype)
-            if self.tf32:
-                with _tf32(True):
-                    logits, value = self.net(planes)
+            if self.tf32 is None:
+                logits, value = self.net(planes)
             else:
-                with _tf32(False):
+                with _tf32(self.tf32):
                     logits, value = self.net(planes)
         else:
             if self._fast is None:

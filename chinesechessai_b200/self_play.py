@@ -56,15 +56,36 @@ def _env_state(env) -> Tuple[np.ndarray, np.ndarray]:
 
 
 class MCTS:
+    """``MCTS(network).search(env)`` (self_play.py:82-154) on the GPU tree kernels.
+
+    ``network`` is anything with the reference's ``predict_batch``.  A stock ``ChessNet`` of this
+    package (module on the GPU, ``predict_batch`` not overridden) takes the device path: the
+    whole search — init, every wave's select / encode / forward / priors / backup, root visits —
+    is captured once as a CUDA graph and replayed per call, with one 128-byte upload and one
+    770-byte download around it (no per-wave host round trip).  Any other network object is
+    called exactly as the reference calls it: once per wave, one list entry per queued
+    simulation (:138-143).  Both give the same visit counts for the same network."""
+
     def __init__(self, network, num_simulations=None):
         self.network = network
         self.default_simulations = num_simulations if num_simulations else MCTS_SIMULATIONS
         self._engines: Dict[int, BatchedMCTS] = {}
+        self._fast: Dict[int, "_DeviceSearch"] = {}
 
     def _engine(self, n_sims: int) -> BatchedMCTS:
         if n_sims not in self._engines:
             self._engines[n_sims] = BatchedMCTS(1, n_sims)
         return self._engines[n_sims]
+
+    def _device_path(self) -> bool:
+        from .neural_network import ChessNet
+        net = self.network
+        if not isinstance(net, ChessNet) or type(net).predict_batch is not ChessNet.predict_batch:
+            return False
+        if type(net).forward is not ChessNet.forward:
+            return False
+        p = next(net.parameters(), None)
+        return p is not None and p.is_cuda and not net.training
 
     def search(self, env, num_simulations=None) -> Dict[Move, int]:
         """{move: visit_count} over the root's children in legal-move order, zeros included;
@@ -72,9 +93,14 @@ class MCTS:
         n_sims = self.default_simulations if num_simulations is None else num_simulations
         if n_sims <= 0:
             return {}
+        b, m = _env_state(env)
+        if self._device_path():
+            fs = self._fast.get(n_sims)
+            if fs is None:
+                fs = self._fast[n_sims] = _DeviceSearch(self.network, n_sims)
+            return fs.search(b, m)
         eng = self._engine(n_sims)
         d = eng.device
-        b, m = _env_state(env)
         board = torch.from_numpy(b).to(d)
         meta = torch.from_numpy(m.view(np.uint8).reshape(1, 32)).to(d)
         eng.init(board, meta)
@@ -82,13 +108,17 @@ class MCTS:
         values = torch.zeros((1, WAVE), dtype=torch.float64, device=d)
         for start in range(0, n_sims, WAVE):
             eng.select(min(WAVE, n_sims - start))
-            n_leaf = int(eng.leaf_n[0])
+            # one packed read of the wave's leaf: count, multiplicity, side to move, board, moves
+            leaf = torch.cat([eng.leaf_n.view(torch.uint8), eng.leaf_mult.view(torch.uint8),
+                              eng.leaf_player.view(torch.uint8), eng.leaf_board.view(torch.uint8).reshape(-1),
+                              eng.leaf_moves.view(torch.uint8).reshape(-1)]).cpu().numpy()
+            n_leaf, mult = int(leaf[0:2].view(np.int16)[0]), int(leaf[2:4].view(np.int16)[0])
             if n_leaf == 0:
                 continue  # every simulation of this wave ended in a terminal node
-            mult = int(eng.leaf_mult[0])
-            leaf_board = eng.leaf_board[0, :90].cpu().numpy().reshape(10, 9)
-            player = int(eng.leaf_player[0])
-            legal = [unpack_move(x) for x in eng.leaf_moves[0, :n_leaf].cpu().tolist()]
+            player = int(leaf[4:5].view(np.int8)[0])
+            leaf_board = leaf[5:5 + 90].view(np.int8).reshape(10, 9)
+            tup = _move_tuples()
+            legal = [tup[x] for x in leaf[5 + BOARD_STRIDE:5 + BOARD_STRIDE + 2 * n_leaf].view(np.int16).tolist()]
             # the reference queues the same leaf once per simulation of the wave (:138-143)
             results = self.network.predict_batch([(leaf_board.copy(), player, legal)] * mult)
             probs = results[0][0]
@@ -100,8 +130,63 @@ class MCTS:
             values.copy_(torch.from_numpy(v))
             eng.backup(priors, values, values_per_game=WAVE)
         mv, vis, nc = eng.visits()
-        k = int(nc[0])
-        return {unpack_move(a): int(c) for a, c in zip(mv[0, :k].cpu().tolist(), vis[0, :k].cpu().tolist())}
+        out = torch.cat([nc.view(torch.uint8), mv.view(torch.uint8).reshape(-1),
+                         vis.view(torch.uint8).reshape(-1)]).cpu().numpy()
+        k = int(out[0:2].view(np.int16)[0])
+        tup = _move_tuples()
+        moves = out[2:2 + 2 * MAX_MOVES].view(np.int16)[:k].tolist()
+        counts = out[2 + 2 * MAX_MOVES:].view(np.int32)[:k].tolist()
+        return {tup[a]: int(c) for a, c in zip(moves, counts)}
+
+
+class _DeviceSearch:
+    """One-tree search with the network on the device, replayed from a CUDA graph."""
+
+    def __init__(self, network, n_sims: int):
+        self.eng = BatchedMCTS(1, n_sims)
+        self.ev = NetEvaluator(network, torch.float32)   # the module as given, like predict_batch
+        d = self.d = self.eng.device
+        self.state = torch.zeros(BOARD_STRIDE + 32, dtype=torch.uint8, device=d)
+        self.board = self.state[:BOARD_STRIDE].view(torch.int8).reshape(1, BOARD_STRIDE)
+        self.meta = self.state[BOARD_STRIDE:].reshape(1, 32)
+        self.out = torch.zeros(2 + 2 * MAX_MOVES + 4 * MAX_MOVES, dtype=torch.uint8, device=d)
+        self.h_state = torch.zeros(BOARD_STRIDE + 32, dtype=torch.uint8).pin_memory()
+        self.h_out = torch.zeros_like(self.out, device="cpu").pin_memory()
+        self._graph, self._key = None, None
+
+    def _run(self) -> None:
+        mv, vis, nc = self.eng.search(self.board, self.meta, self.ev)
+        self.out.copy_(torch.cat([nc.view(torch.uint8), mv.view(torch.uint8).reshape(-1),
+                                  vis.view(torch.uint8).reshape(-1)]))
+
+    @torch.no_grad()
+    def search(self, b: np.ndarray, m: np.ndarray) -> Dict[Move, int]:
+        hs = self.h_state.numpy()
+        hs[:BOARD_STRIDE] = b.view(np.uint8).reshape(-1)
+        hs[BOARD_STRIDE:] = m.view(np.uint8).reshape(-1)
+        self.state.copy_(self.h_state, non_blocking=True)
+        key = self.ev.version
+        if self._graph is None or self._key != key:
+            self._run()                                  # warm-up: library handles, workspaces
+            torch.cuda.current_stream(self.d).synchronize()
+            g = torch.cuda.CUDAGraph()
+            try:
+                with torch.cuda.graph(g):
+                    self._run()
+                self._graph, self._key = g, key
+            except Exception:                            # not capturable here: stay eager
+                self._graph = None
+                self._run()
+        if self._graph is not None:
+            self._graph.replay()
+        self.h_out.copy_(self.out, non_blocking=True)
+        torch.cuda.current_stream(self.d).synchronize()
+        out = self.h_out.numpy()
+        k = int(out[0:2].view(np.int16)[0])
+        tup = _move_tuples()
+        moves = out[2:2 + 2 * MAX_MOVES].view(np.int16)[:k].tolist()
+        counts = out[2 + 2 * MAX_MOVES:].view(np.int32)[:k].tolist()
+        return {tup[a]: int(c) for a, c in zip(moves, counts)}
 
 
 def final_reward(winner: int, player: int, game_length: int) -> float:

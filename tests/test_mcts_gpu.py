@@ -239,7 +239,7 @@ def test_leaf_compaction_keeps_visit_counts(mods, xo):
     mv0, vis0, nc0 = [t.clone() for t in full.search(bb.board, bb.meta, mcts.HashEvaluator(), active)]
     meta = bb.meta_host()
     over = int((meta["winner"] != 2).sum())
-    assert over > 10                                # the batch really is ragged
+    assert over >= 5                                # the batch really is ragged
     comp = mcts.BatchedMCTS(n, n_sims)
     # a bound of n (no compaction), a loose one and the tight one
     live = int(((meta["winner"] == 2) & (active.cpu().numpy() != 0)).sum())

@@ -379,3 +379,34 @@ def test_reference_play_match_on_shims_equals_reference_golden(pkg, xo, tmp_path
     for a, g in zip(got, gold):
         assert a["moves"] == g["moves"]
         assert a["result"] == g["result"]
+
+
+def test_mcts_device_path_equals_predict_batch_path(pkg):
+    """MCTS(ChessNet).search takes the all-device, graph-replayed path; the same network hidden
+    behind a plain object with predict_batch takes the reference's per-wave host path.  Same
+    visit dicts (keys, order, counts), also after the weights change (the graph is re-captured)."""
+    import torch
+    chess_env, self_play = pkg
+    from chinesechessai_b200.neural_network import ChessNet
+
+    class Wrapped:
+        def __init__(self, net):
+            self.predict_batch = net.predict_batch
+
+    torch.manual_seed(1)
+    net = ChessNet().cuda().eval()
+    fast, slow = self_play.MCTS(net, 30), self_play.MCTS(Wrapped(net), 30)
+    assert fast._device_path() and not slow._device_path()
+    env = chess_env.ChineseChess()
+    rng = np.random.default_rng(0)
+    for ply in range(12):
+        a, b = fast.search(env), slow.search(env)
+        assert list(a.items()) == list(b.items()), ply
+        assert sum(a.values()) == 30 - 8
+        legal = env.get_legal_moves()
+        env.make_move(legal[int(rng.integers(len(legal)))])
+        if ply == 6:
+            with torch.no_grad():
+                for p in net.parameters():
+                    p.mul_(1.01)
+    assert fast._fast[30]._graph is not None and fast._fast[30].ev._version >= 2
