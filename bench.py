@@ -737,7 +737,7 @@ def run_ours(args):
             cpu_baseline["reference_unavailable"] = "Python reference not timed (absent, --no-python or N>1)"
 
     kc = kernel_counts()
-    mode = os.environ.get("XQ_PLAYOUT_MODE") or ("pair" if n >= 40960 else "warp")
+    mode = os.environ.get("XQ_PLAYOUT_MODE") or ("pairs" if n >= 32768 else "warp")
     kinfo = kc.get(mode, {})
     plies_per_launch = total_plies / (args.steps * world)
     kern_s = kern_ms * 1e-3 / args.steps
@@ -801,7 +801,7 @@ def run_ours(args):
         out["gpu_launches"] += 11
         # the other mappings of the same fused loop
         out["other_mappings"] = {}
-        for m2 in ("pair", "pairq", "tpb", "warp"):
+        for m2 in ("pairs", "pair", "pairq", "tpb", "warp"):
             if m2 == mode:
                 continue
             os.environ["XQ_PLAYOUT_MODE"] = m2

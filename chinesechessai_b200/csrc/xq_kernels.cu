@@ -39,6 +39,9 @@ constexpr int kThreads = kWarpsPerCta * 32;
 #ifndef XQ_PAIR_MIN_GAMES
 #define XQ_PAIR_MIN_GAMES 40960
 #endif
+#ifndef XQ_SM_MIN_GAMES
+#define XQ_SM_MIN_GAMES 32768
+#endif
 
 // ---------------------------------------------------------------------------
 // reset (chess_env.py:14-67): one thread per 4 squares.
@@ -816,7 +819,7 @@ __global__ void __launch_bounds__(kLaneThreads, 7)
       unsigned lsum = 0;
       if (!kingcap) n = pair_movegen(w, G, g_leap, pending, checking, n0, lsum);
       if (pending) {
-        tpb_finish<true>(w, G, o, n, checking, hist);
+        tpb_finish<true, true>(w, G, o, n, checking, hist);
         pending = false;
         rsum = __dadd_rn(rsum, o.reward);
         const uint64_t word_c = (uint64_t)(o.done & 1) | ((uint64_t)(G.winner + 2) << 8) |
@@ -863,6 +866,217 @@ __global__ void __launch_bounds__(kLaneThreads, 7)
       uint4* cp = reinterpret_cast<uint4*>(carry + g);
       cp[0] = make_uint4((uint32_t)word_a, (uint32_t)(word_a >> 32), (uint32_t)rw, (uint32_t)(rw >> 32));
       cp[1] = make_uint4((uint32_t)G.bkey, (uint32_t)(G.bkey >> 32), bits, 0u);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Fused random playout, lane pair per board, scheduled INSIDE each SM.
+//
+// Measured on the one-wave kernel (scripts/playout_timing.py): the SM's warp arbiter serves its
+// warp slots by priority, so the 28 co-resident warps of an SM finish their 70-ply games between
+// 3.8 and 6.5 ms after a common start, and the launch ends with the SMs three-quarters occupied
+// on average — work that a fair arbiter would have spread evenly.  Moving whole groups between
+// SMs through a global queue (playout_queue_kernel) costs more than it returns.  Here fairness
+// is restored where the unfairness arises: ONE CTA of 28 warps per SM keeps kSmSlots = 29 groups
+// of 16 boards resident in shared memory — one more group than warps — and after EVERY ply a warp
+// puts its group back and takes the resident group that has made the least progress (one 32-lane
+// read of the slot table, a min-reduction and one shared-memory CAS).  Fast warp slots simply
+// play more plies; all groups of an SM advance together and finish together, and a slot whose
+// group is over is refilled with the SM's next group.  Boards never leave shared memory during
+// a game; the per-pair scalars travel through the caller's meta / results rows and a 32 B carry
+// (the hand-over format of the queue kernel).  A group never leaves its SM, so the hand-over needs
+// CTA-scope ordering only: __threadfence_block() + the slot's busy flag, plain loads.  Rules code and results are those of
+// playout_lane_kernel<false, true>.
+constexpr int kSmWarps = 28;   // 7 CTAs x 4 warps of the one-wave kernel: the same occupancy
+constexpr int kSmSlots = 29;   // resident groups per SM (29 x 16 x 428 B = 198.6 KB of shared memory)
+constexpr int kSlotDead = 0x7fffffff;
+
+struct SmSched {
+  int prog[32];  // loop iterations done by the slot's group; kSlotDead = no group
+  int busy[32];  // 1 while a warp works on the slot
+  int gid[32];   // group id in the slot
+  int next;      // how many groups this CTA has taken from its list so far
+  int pad[3];
+};
+
+__global__ void __launch_bounds__(kSmWarps * 32, 1)
+    playout_sm_kernel(int8_t* __restrict__ board, xq_meta* __restrict__ meta,
+                      uint64_t* __restrict__ pos_hist, int hist_cap, uint64_t seed,
+                      uint32_t first_game_id, int max_plies, int capture_bias,
+                      xq_playout_result* __restrict__ results, int n_games,
+                      PlayoutCarry* __restrict__ carry) {
+  extern __shared__ __align__(16) unsigned char tpb_smem[];
+  SmSched& sc = *reinterpret_cast<SmSched*>(tpb_smem);
+  ThreadBoard* slabs = reinterpret_cast<ThreadBoard*>(tpb_smem + sizeof(SmSched));
+  const int sub = Pair::sub();
+  const int lane = (int)(threadIdx.x & 31u);
+  const int n_groups = (n_games + kQueueGroup - 1) / kQueueGroup;
+  const int iters = max_plies + 1;  // the loop runs movegen once more than it applies moves
+  // this CTA's groups: blockIdx.x, blockIdx.x + gridDim.x, ... ; the first kSmSlots are resident
+  if (threadIdx.x < 32) {
+    const int gi = (int)blockIdx.x + (int)threadIdx.x * (int)gridDim.x;
+    const bool on = threadIdx.x < kSmSlots && gi < n_groups;
+    sc.gid[threadIdx.x] = on ? gi : -1;
+    sc.prog[threadIdx.x] = on ? 0 : kSlotDead;
+    sc.busy[threadIdx.x] = 0;
+    if (threadIdx.x == 0) sc.next = kSmSlots;
+  }
+  __syncthreads();
+  volatile int* vprog = sc.prog;
+  volatile int* vbusy = sc.busy;
+  volatile int* vgid = sc.gid;
+  for (;;) {
+    // ---- take the free resident group with the least progress
+    int slot = -1;
+    for (;;) {
+      const int pr = vprog[lane];
+      int key = (vbusy[lane] || pr == kSlotDead) ? kSlotDead : pr;
+      const bool live = __any_sync(0xffffffffu, pr != kSlotDead);
+      int who = lane;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const int ok = __shfl_xor_sync(0xffffffffu, key, o), ow = __shfl_xor_sync(0xffffffffu, who, o);
+        if (ok < key || (ok == key && ow < who)) { key = ok; who = ow; }
+      }
+      if (key == kSlotDead) {
+        if (!live) return;  // every group of this SM is over
+        __nanosleep(200);
+        continue;
+      }
+      int won = 0;
+      if (lane == 0) won = atomicCAS(&sc.busy[who], 0, 1) == 0 ? 1 : 0;
+      if (__shfl_sync(0xffffffffu, won, 0)) { slot = who; break; }
+    }
+    __threadfence_block();
+    const int gi = vgid[slot], it = vprog[slot];
+    ThreadBoard& w = slabs[slot * kQueueGroup + (lane >> 1)];
+    const int g = gi * kQueueGroup + (lane >> 1);
+    bool fin = true;  // pairs without a game count as finished
+    if (g < n_games) {
+      // ---- restore (or start) the game
+      uint64_t digest = 0, word_a = 0;
+      double rsum = 0.0;
+      int max_legal = 0, ply = 0;
+      bool pending = false, kingcap = false;
+      TpbStep o;
+      o.done = 0; o.reward = 0.0; o.is_int = 1; o.from = o.to = 0; o.moving = o.captured = 0; o.key_next = 0;
+      Game G;
+      bool live_game = true;
+      if (it == 0) {
+        pair_load(w, board + (size_t)g * XQ_BOARD_STRIDE);
+        G = load_meta(meta + g);
+        G.bkey = pair_board_key(w);
+      } else {
+        const uint4* cp = reinterpret_cast<const uint4*>(carry + g);
+        const uint4 c0 = cp[0], c1 = cp[1];  // written by a warp of this CTA (CTA-scope fence)
+        const uint32_t bits = c1.z;
+        live_game = !(bits & 4u);  // a finished game's rows are final
+        if (live_game) {
+          word_a = (uint64_t)c0.x | ((uint64_t)c0.y << 32);
+          o.reward = __longlong_as_double((long long)((uint64_t)c0.z | ((uint64_t)c0.w << 32)));
+          pending = bits & 1u;
+          kingcap = (bits >> 1) & 1u;
+          o.is_int = (bits >> 3) & 1u;
+          o.done = kingcap ? 1 : 0;  // between iterations o.done can only be the king-capture flag
+          o.from = (bits >> 5) & 0x7Fu;
+          o.to = (bits >> 12) & 0x7Fu;
+          o.moving = (int)((bits >> 19) & 0xFu) - 8;
+          o.captured = (int)((bits >> 23) & 0xFu) - 8;
+          const unsigned long long* rp = reinterpret_cast<const unsigned long long*>(results + g);
+          const unsigned long long r0 = rp[0], r1 = rp[1];
+          ply = (int)(uint32_t)r0;
+          max_legal = (int)(uint32_t)(r1 >> 32);
+          rsum = __longlong_as_double((long long)rp[2]);
+          digest = rp[3];
+          G = load_meta(meta + g);
+          G.bkey = (uint64_t)c1.x | ((uint64_t)c1.y << 32);
+        }
+      }
+      if (live_game) {
+        o.key_next = G.bkey ^ side_key(G.player);
+        uint64_t* hist = pos_hist + (size_t)g * hist_cap;
+        const uint32_t gid = first_game_id + (uint32_t)g;
+        fin = false;
+        // ---- ONE iteration of the loop of playout_lane_kernel<false, true>
+        {
+          bool checking = false;
+          int n = -1, n0 = 0;
+          unsigned lsum = 0;
+          if (!kingcap) n = pair_movegen(w, G, g_leap, pending, checking, n0, lsum);
+          if (pending) {
+            tpb_finish<true>(w, G, o, n, checking, hist);
+            pending = false;
+            rsum = __dadd_rn(rsum, o.reward);
+            const uint64_t word_c = (uint64_t)(o.done & 1) | ((uint64_t)(G.winner + 2) << 8) |
+                                    ((uint64_t)G.reason << 16) | ((uint64_t)(o.is_int & 1) << 24);
+            const uint64_t t = word_a * 0x9E3779B97F4A7C15ULL + dbits(o.reward) * 0xC2B2AE3D27D4EB4FULL +
+                               word_c * 0x165667B19E3779F9ULL + o.key_next * 0x27D4EB2F165667C5ULL;
+            digest = mix64(digest ^ t);
+            ++ply;
+            if (o.done) fin = true;
+          }
+          if (!fin && (ply >= max_plies || n == 0)) fin = true;  // self_play.py:203,207
+          if (!fin) {
+            max_legal = max(max_legal, n);
+            const unsigned cm = pair_move_at(w, pair_pick(w, n, n0, seed, gid, (uint32_t)ply, capture_bias), n0);
+            const int mv = tpb_packed(cm);
+            word_a = (uint64_t)lsum | ((uint64_t)n << 32) | ((uint64_t)mv << 40) | ((uint64_t)(ply + 1) << 54);
+            o = tpb_apply<true>(w, G, (int)(cm >> 8), (int)(cm & 0x7fu), hist, hist_cap);
+            kingcap = o.done != 0;
+            pending = true;
+          }
+        }
+        // ---- hand the scalars over (and, once the game is over, the final board)
+        Pair::sync();
+        if (fin) {
+          uint32_t* bo = reinterpret_cast<uint32_t*>(board + (size_t)g * XQ_BOARD_STRIDE);
+          const uint32_t* bi = reinterpret_cast<const uint32_t*>(w.sq);
+#pragma unroll
+          for (int i = 0; i < XQ_BOARD_STRIDE / 8; ++i) bo[2 * i + sub] = bi[2 * i + sub];
+        }
+        if (sub == 0) {
+          pair_store_meta(meta + g, G);
+          xq_playout_result r;
+          r.plies = ply;
+          r.winner = G.winner;
+          r.reason = G.reason;
+          r.max_legal = max_legal;
+          r.reward_sum = rsum;
+          r.digest = digest;
+          r.final_hash = G.bkey ^ side_key(G.player);
+          results[g] = r;
+        } else {
+          const uint64_t rw = dbits(o.reward);
+          const uint32_t bits = (pending ? 1u : 0u) | (kingcap ? 2u : 0u) | (fin ? 4u : 0u) |
+                                ((uint32_t)(o.is_int & 1) << 3) | ((uint32_t)(o.from & 0x7F) << 5) |
+                                ((uint32_t)(o.to & 0x7F) << 12) | ((uint32_t)((o.moving + 8) & 0xF) << 19) |
+                                ((uint32_t)((o.captured + 8) & 0xF) << 23);
+          uint4* cp = reinterpret_cast<uint4*>(carry + g);
+          cp[0] = make_uint4((uint32_t)word_a, (uint32_t)(word_a >> 32), (uint32_t)rw, (uint32_t)(rw >> 32));
+          cp[1] = make_uint4((uint32_t)G.bkey, (uint32_t)(G.bkey >> 32), bits, 0u);
+        }
+      }
+    }
+    // ---- put the group back, or refill the slot when every game of the group is over
+    const bool group_over = __all_sync(0xffffffffu, fin) || it + 1 >= iters;
+    __threadfence_block();
+    if (lane == 0) {
+      if (group_over) {
+        const int k = atomicAdd(&sc.next, 1);
+        const int ng = (int)blockIdx.x + k * (int)gridDim.x;
+        if (k < (1 << 20) && ng < n_groups) {
+          vgid[slot] = ng;
+          vprog[slot] = 0;
+        } else {
+          vgid[slot] = -1;
+          vprog[slot] = kSlotDead;
+        }
+      } else {
+        vprog[slot] = it + 1;
+      }
+      __threadfence_block();
+      vbusy[slot] = 0;
     }
   }
 }
@@ -1231,6 +1445,32 @@ static int launch_playout_queue(int8_t* board, xq_meta* meta, uint64_t* pos_hist
   return rc;
 }
 
+static int launch_playout_sm(int8_t* board, xq_meta* meta, uint64_t* pos_hist, int hist_cap,
+                             uint64_t seed, uint32_t first_game_id, int max_plies, int capture_bias,
+                             xq_playout_result* results, int n_games, cudaStream_t st) {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  keep_pool_cached(dev);
+  const int n_groups = (n_games + kQueueGroup - 1) / kQueueGroup;
+  const size_t smem = sizeof(SmSched) + sizeof(ThreadBoard) * kQueueGroup * kSmSlots;
+  static thread_local int attr_dev = -1;
+  if (attr_dev != dev) {
+    cudaError_t e1 = cudaFuncSetAttribute(playout_sm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e1 != cudaSuccess) return fail(XQ_E_CUDA, "xq_playout: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e1));
+    attr_dev = dev;
+  }
+  PlayoutCarry* carry = nullptr;
+  cudaError_t e = cudaMallocAsync(&carry, (size_t)n_games * sizeof(PlayoutCarry), st);
+  if (e != cudaSuccess) return fail(XQ_E_CUDA, "xq_playout: cudaMallocAsync: %s", cudaGetErrorString(e));
+  const int ctas = n_groups < sms ? n_groups : sms;
+  playout_sm_kernel<<<ctas, kSmWarps * 32, smem, st>>>(board, meta, pos_hist, hist_cap, seed, first_game_id,
+                                                      max_plies, capture_bias, results, n_games, carry);
+  const int rc = check_launch("xq_playout");
+  cudaFreeAsync(carry, st);
+  return rc;
+}
+
 // Diagnostics: while a device buffer of 3 * ceil(threads / 32) uint64 (zero-filled by the caller)
 // is registered, the per-lane fused playout kernels record every warp's first start / last end
 // time (ns) and SM id in it.  NULL switches the recording off (the default).
@@ -1274,6 +1514,12 @@ int xq_playout(int8_t* board, xq_meta* meta, uint64_t* pos_hist, int hist_cap, u
   // (opt-in: measured slower than the one-wave kernel at every batch size once the slow legality
   // path stopped firing in play — 6.7 vs 6.5 ms at 65,536 boards)
   const bool pairq = !trace && mode_env != nullptr && strcmp(mode_env, "pairq") == 0;
+  // "pairs": lane pairs scheduled inside each SM (playout_sm_kernel) — the default once the batch
+  // gives every SM a full set of groups (measured: 4.5e8 vs 4.1e8 for the warp mapping at 32,768
+  // boards, 8.1e8 vs 7.1e8 for the one-wave pair kernel at 65,536)
+  const bool pairs = !trace && (mode_env ? strcmp(mode_env, "pairs") == 0 : n_games >= XQ_SM_MIN_GAMES);
+  if (pairs) return launch_playout_sm(board, meta, pos_hist, hist_cap, seed, first_game_id, max_plies,
+                                      capture_bias, results, n_games, st);
   if (pairq) return launch_playout_queue(board, meta, pos_hist, hist_cap, seed, first_game_id, max_plies,
                                          capture_bias, results, n_games, st);
   if (pair || tpb) {

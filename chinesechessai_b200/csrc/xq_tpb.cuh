@@ -250,7 +250,10 @@ __device__ __forceinline__ TpbStep tpb_apply(ThreadBoard& w, Game& g, int from, 
 }
 
 // make_move part 2 (:318-345, :352-404), sequential twin of step_finish<L>.
-template <bool PAIR = false>
+// HIST_CG: read the history through L2 (the queue-fed kernel, where earlier entries were appended
+// by warps on other SMs); otherwise plain loads (entries written by this thread or, in the
+// SM-scheduled kernel, by other warps of the same CTA behind a CTA-scope fence).
+template <bool PAIR = false, bool HIST_CG = false>
 __device__ __forceinline__ void tpb_finish(const ThreadBoard& w, Game& g, TpbStep& o, int n_legal,
                                            bool checking, const uint64_t* __restrict__ hist) {
   const int mover = -g.player;
@@ -279,8 +282,8 @@ __device__ __forceinline__ void tpb_finish(const ThreadBoard& w, Game& g, TpbSte
   } else {
     int cnt = 0;
 #pragma unroll 1
-    // __ldcg: in the queue-fed kernel earlier entries were appended by warps on other SMs
-    for (int i = PAIR ? Pair::sub() : 0; i < g.hist_len; i += PAIR ? 2 : 1) cnt += __ldcg(hist + i) == o.key_next;
+    for (int i = PAIR ? Pair::sub() : 0; i < g.hist_len; i += PAIR ? 2 : 1)
+      cnt += (HIST_CG ? __ldcg(hist + i) : hist[i]) == o.key_next;
     if (PAIR) cnt += Pair::other(cnt);
     if (cnt >= 3) {
       o.done = 1; o.reward = 0.0; o.is_int = 1;

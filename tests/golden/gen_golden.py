@@ -372,7 +372,9 @@ def play_match_job(args):
     orig = chess_env.ChineseChess.make_move
 
     def logged(self, move):
-        log.append(pack(move))
+        # only the game's own moves: the reference's MCTS also calls make_move, on env copies
+        if sys._getframe(1).f_code.co_name == "play_match":
+            log.append(pack(move))
         return orig(self, move)
     chess_env.ChineseChess.make_move = logged
     try:

@@ -196,15 +196,19 @@ def test_fused_playout_vs_oracle(eng, xo, bias, first):
     assert int(res["plies"].sum()) == total
 
 
-@pytest.mark.parametrize("lpb", [1, 2, "2q", "2q5", "2q71", 8, 16, 32])
+@pytest.mark.parametrize("lpb", [1, 2, "2q", "2q5", "2q71", "2s", 8, 16, 32])
 def test_fused_playout_tile_widths(eng, xo, lpb, monkeypatch):
     """The fused kernel with 1 (thread per board), 2 (pair; "2q*" = the persistent queue-fed
-    kernel with its default / 5 / 71 loop iterations per chunk), 8, 16 or 32 lanes per board is
+    kernel with its default / 5 / 71 loop iterations per chunk, "2s" = the kernel that schedules
+    the pairs' groups inside each SM), 8, 16 or 32 lanes per board is
     bit-exact, traces included, for uniform and capture-biased games and ragged batch sizes."""
     if lpb == 1:
         monkeypatch.setenv("XQ_PLAYOUT_MODE", "tpb")
     elif lpb == 2:
         monkeypatch.setenv("XQ_PLAYOUT_MODE", "pair")
+    elif lpb == "2s":
+        monkeypatch.setenv("XQ_PLAYOUT_MODE", "pairs")
+        lpb = 3
     elif isinstance(lpb, str):
         monkeypatch.setenv("XQ_PLAYOUT_MODE", "pairq")
         if lpb[2:]:
@@ -234,7 +238,7 @@ def test_fused_playout_tile_widths(eng, xo, lpb, monkeypatch):
             assert np.array_equal(moves[g, q, :n_arr[g, q]], t["moves"][q, :t["n"][q]])
 
 
-@pytest.mark.parametrize("mode", ["warp", "tpb", "pair", "pairq"])
+@pytest.mark.parametrize("mode", ["warp", "tpb", "pair", "pairq", "pairs"])
 def test_fused_playout_from_arbitrary_positions(eng, xo, golden, mode, monkeypatch):
     """Playouts that START from the poked golden positions (stale or missing king caches, several
     kings, enemy K/A/B next to the king, mid-game counters): every mapping of the fused kernel

@@ -364,7 +364,9 @@ def test_reference_play_match_on_shims_equals_reference_golden(pkg, xo, tmp_path
         "    log = []\n"
         "    orig = chess_env.ChineseChess.make_move\n"
         "    def logged(self, mv, orig=orig, log=log):\n"
-        "        log.append((mv[0] * 9 + mv[1]) * 90 + mv[2] * 9 + mv[3]); return orig(self, mv)\n"
+        "        if sys._getframe(1).f_code.co_name == 'play_match':\n"
+        "            log.append((mv[0] * 9 + mv[1]) * 90 + mv[2] * 9 + mv[3])\n"
+        "        return orig(self, mv)\n"
         "    chess_env.ChineseChess.make_move = logged\n"
         "    np.random.seed(seed)\n"
         "    res = compare_models.play_match(StubNet(xo, False), StubNet(xo, True), num_games=n_games, verbose=False)\n"
