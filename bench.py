@@ -493,6 +493,32 @@ def measure_mcts_multi(torch, dist, dev, world, rank, games=16384, sims=50, min_
                          "note": "per GPU; sustained bf16 peak (leg timed >= 2 s)"}}
 
 
+def measure_cfg5_multi(torch, dist, dev, world, rank, games_per_gpu=MCTS_GAMES, sims=MCTS_SIMS):
+    """cfg 5 at N GPUs: ONE full iteration — NCCL weight broadcast, games sharded over the ranks
+    (no collective inside self-play), sample gather to rank 0, the value-loss update of
+    Trainer.train_network on rank 0 from device-resident samples (chinesechessai_b200.iteration).
+    Wall seconds, max over ranks.  The single-GPU line times the same iteration through the
+    reference's UNCHANGED trainer.py instead (`cfg5`)."""
+    from chinesechessai_b200.iteration import self_play_iteration
+    from chinesechessai_b200.neural_network import ChessNet
+    torch.manual_seed(0)
+    net = ChessNet().to(dev).eval()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    self_play_iteration(net, opt, 64 * world, sims, seed=1, net_dtype=torch.bfloat16)      # warm-up
+    dist.barrier()
+    it = self_play_iteration(net, opt, games_per_gpu * world, sims, seed=2, net_dtype=torch.bfloat16)
+    t = torch.tensor([it["seconds"], it["self_play_s"], it["train_s"]], dtype=torch.float64, device=dev)
+    c = torch.tensor([it["plies"], it["samples"]], dtype=torch.int64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    return {"workload": f"cfg5: one iteration, {games_per_gpu} games per GPU x {world} GPUs, {sims} sims/move, "
+                        "bf16 inference copy for the search, fp32 update (min(50, samples//64) batches of 64) "
+                        "on rank 0",
+            "seconds": float(t[0]), "self_play_s": float(t[1]), "train_s": float(t[2]),
+            "games": games_per_gpu * world, "plies": int(c[0]), "samples_on_trainer": int(c[1]),
+            "games_per_s": games_per_gpu * world / float(t[0]), "loss": it["loss"]}
+
+
 def measure_selfplay_iteration(torch, dev, games=MCTS_GAMES, sims=MCTS_SIMS):
     """The self-play half of cfg 5: `games` complete games (to a terminal state or the 70-ply cap,
     all rules active) with `sims` simulations per move through the drop-in batch loop, plus the
@@ -699,9 +725,10 @@ def run_ours(args):
     if same_results(dev_res0, e2e_res0):
         raise SystemExit(f"bench.py rank {rank}: xq_playout_host and xq_playout disagree on step 0")
 
-    mc_multi = None
+    mc_multi = cfg5_multi = None
     if world > 1 and not args.fast:
         mc_multi = measure_mcts_multi(torch, dist, dev, world, rank, peaks=peaks)
+        cfg5_multi = measure_cfg5_multi(torch, dist, dev, world, rank)
 
     if rank != 0:
         if world > 1:
@@ -780,6 +807,8 @@ def run_ours(args):
         out["cpu_baseline"] = cpu_baseline
     if mc_multi is not None:
         out["mcts_cfg4"] = mc_multi
+    if cfg5_multi is not None:
+        out["cfg5"] = cfg5_multi
     if world == 1 and not args.fast:
         # cfg 1 (the reference's own CPU-runnable case): 1,024 games from the initial position
         b1 = BoardBatch(1024, device=dev, hist_cap=PLIES + 2)

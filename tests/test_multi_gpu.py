@@ -38,6 +38,31 @@ def _worker(rank, world, port, out):
         ok = ok and float(both[0]) == float(both[1]) and len(want["reward"]) > 41 * 10
     else:
         ok = samples is None
+    # a bf16 evaluator kept across two iterations must play the SECOND one with the weights of the
+    # second broadcast (its folded inference copy is rebuilt): the trainer rank changes the
+    # weights in between, every rank's visit counts change with them, and the ranks agree
+    from chinesechessai_b200.mcts import NetEvaluator
+    torch.manual_seed(7)                      # same initial weights everywhere
+    net2 = ChessNet().cuda().eval()
+    ev = NetEvaluator(net2, torch.bfloat16)
+    first, _ = xd.distributed_self_play(ev, 16, 15, 1.0, seed=9, network=net2)
+    if rank == 0:
+        with torch.no_grad():
+            for p in net2.parameters():
+                p.add_(torch.randn_like(p) * 0.05)
+    second, sp2 = xd.distributed_self_play(ev, 16, 15, 1.0, seed=9, network=net2)
+    mine = sp2.rec_move[:8].to(torch.int64).sum().reshape(1)      # depends on the weights used
+    alone = BatchedSelfPlay(NetEvaluator(net2, torch.bfloat16), 8, 15, 1.0, seed=9, first_game_id=rank * 8)
+    alone.play()
+    fresh = alone.rec_move[:8].to(torch.int64).sum().reshape(1)
+    ok = ok and bool(torch.equal(mine, fresh))                    # = a fresh evaluator on the new weights
+    if rank == 0:
+        ok = ok and not torch.equal(first["board"], second["board"])   # and the games did change
+    # one full iteration (broadcast -> sharded self-play -> gather -> update on rank 0)
+    from chinesechessai_b200.iteration import self_play_iteration
+    opt = torch.optim.Adam(net2.parameters(), lr=1e-3)
+    it = self_play_iteration(net2, opt, 24, 15, seed=3, net_dtype=torch.bfloat16)
+    ok = ok and it["plies"] > 0 and (rank != 0 or (it["samples"] >= 24 * 10 and it["loss"] == it["loss"]))
     out.put((rank, bool(ok)))
     dist.barrier()
     dist.destroy_process_group()
