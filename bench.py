@@ -414,6 +414,57 @@ def measure_mcts(torch, dev, precision, games=MCTS_GAMES, sims=MCTS_SIMS, label=
     return out
 
 
+def measure_mcts_ragged(torch, dev, games=MCTS_GAMES, sims=MCTS_SIMS, strata=8, step=8):
+    """Leaf compaction on a RAGGED batch: game g starts after (g * strata // games) * step random
+    opening plies, so the 70-ply cap retires one eighth of the batch every 8 plies (7/8 of the
+    games end before the batch's last ply; average live fraction 56 %).  The reference never sends
+    a finished game or a terminal leaf to the network (self_play.py:126-139); without compaction a
+    batch runs the forward on all rows every wave.  Same games, same visit counts either way
+    (tests/test_mcts_gpu.py); bf16 network, complete batch timed with CUDA events, host loop with
+    its two-ply-late 'games still running' read included."""
+    from chinesechessai_b200._lib import check
+    from chinesechessai_b200.neural_network import ChessNet
+    from chinesechessai_b200.self_play import BatchedSelfPlay
+    torch.manual_seed(0)
+    net = ChessNet().to(dev).eval()
+    ev = make_evaluator(torch, net, "bf16")
+    out = {"workload": f"{games} games x {sims} sims/move, openings of 0,{step},..,{step * (strata - 1)} random plies "
+                       f"by stratum ({strata} strata): games retire at batch plies 70,{70 - step},..; bf16"}
+    for compact in (False, True):
+        sp = BatchedSelfPlay(ev, games, sims, temperature=1.0, device=dev, seed=0, compact=compact, use_graph=False)
+
+        def start():
+            sp.restart(None)
+            b = sp.boards
+            per = games // strata
+            for k in range(1, strata):
+                lo = k * per
+                cnt = games - lo if k == strata - 1 else per
+                res = torch.zeros((cnt, 40), dtype=torch.uint8, device=dev)
+                check(sp.lib.xq_playout(b.board[lo:].data_ptr(), b.meta[lo:].data_ptr(), b.pos_hist[lo:].data_ptr(),
+                                        b.hist_cap, SEED, lo, step * k, 0, res.data_ptr(), None, None, None, None,
+                                        None, None, cnt, torch.cuda.current_stream().cuda_stream))
+        start()
+        sp.play()                                   # warm-up batch (shapes of every bucket size)
+        start()
+        sp.mcts.rows_evaluated = 0
+        torch.cuda.synchronize()
+        a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        sp.play()
+        b2.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b2)
+        st = sp.stats()
+        waves = (sims + 7) // 8
+        out["compact" if compact else "full_batch"] = {
+            "ms": ms, "batch_plies": sp.plies, "game_plies": st["plies"], "sims_per_s": st["sims"] / (ms * 1e-3),
+            "rows_evaluated": int(sp.mcts.rows_evaluated), "live_rows": st["plies"] * waves,
+            "rows_evaluated_per_live_row": sp.mcts.rows_evaluated / max(1, st["plies"] * waves)}
+    out["speedup"] = out["full_batch"]["ms"] / out["compact"]["ms"]
+    return out
+
+
 def measure_mcts_multi(torch, dist, dev, world, rank, games=16384, sims=50, min_seconds=2.0, peaks=None):
     """cfg 4: 16,384 games per GPU x 50 sims/move on every rank, weights broadcast by NCCL once
     (the per-iteration collective), no collective inside the game loop, then the per-iteration
@@ -880,6 +931,7 @@ def run_ours(args):
         out["mcts_precision_agreement"] = precision_agreement(torch, dev, ChessNet().to(dev).eval())
         out["mcts"] = {p: measure_mcts(torch, dev, p, peaks=peaks) for p in PRECISIONS}
         out["mcts"]["tree_only"] = measure_tree_only(torch, dev, MCTS_GAMES, MCTS_SIMS)
+        out["mcts"]["ragged_batch"] = measure_mcts_ragged(torch, dev)
         if not args.no_cfg4:
             out["mcts_cfg4"] = {p: measure_mcts(torch, dev, p, games=16384, sims=50,
                                                 label="cfg4 (one GPU's shard)", peaks=peaks)
