@@ -193,6 +193,7 @@ __device__ __forceinline__ int pair_movegen(ThreadBoard& w, Game& g, const uint3
   Pair::sync();
 
   // legality (:118): verdicts are MARKED in place (kCandIllegal), nothing moves yet
+  int chk = 0, q_first = 0;  // q_first = 1: the check test (probe item 0) is already answered
   if (!exotic) {
     // non-king moves, bitmask test: the list is cut in two equal runs, so the lanes' trip counts
     // match however the pieces fell (a rook's 17 candidates vs a pawn's 1)
@@ -205,6 +206,12 @@ __device__ __forceinline__ int pair_movegen(ThreadBoard& w, Game& g, const uint3
       const int from = (int)(c >> 8), to = (int)(c & 0x7fu);
       if (from != ownK && suicide_fast(f, from, to)) w.mv[a] = (uint16_t)(c | kCandIllegal);
     }
+    // make_move's check test from the same masks (both lanes, no divergence); the probe round
+    // below then only has the king's own moves left
+    if (want_check) {
+      chk = check_fast(f, player) ? 1 : 0;
+      q_first = 1;
+    }
   } else {
 #pragma unroll 1
     for (int j = 0; j < nc; ++j) {  // irregular boards: the general test, king moves included
@@ -214,14 +221,13 @@ __device__ __forceinline__ int pair_movegen(ThreadBoard& w, Game& g, const uint3
   }
   // probe round: item 0 = make_move's check test (:317), items 1.. = the king's candidates
   // (:448-451); the lanes take alternating items
-  int chk = 0;
   {
     // one attacked() call site serves both kinds of item: the check test looks at the king where
     // it stands under the previous mover's geometry with the K/A/B probes on (:317, A.3); a king
     // move looks at the target square with the move applied, then at the two kings' file
     const int ek = player == 1 ? g.black_king : g.red_king;
 #pragma unroll 1
-    for (int q = sub; q <= k_total; q += 2) {
+    for (int q = q_first + sub; q <= k_total; q += 2) {
       const bool is_check = q == 0;
       if (is_check && !(want_check && ownK >= 0)) continue;
       int from = -1, to = -1, a = 0;

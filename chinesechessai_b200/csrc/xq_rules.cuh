@@ -539,6 +539,20 @@ XQ_HD bool suicide_fast(const FastCtx& f, int from, int to) {
   return hit;
 }
 
+// make_move's check test (chess_env.py:317: is the side now to move in check, geometry of the
+// side that just moved) for a REGULAR position, from the masks of the legality test: flip the
+// pawn geometry to the attackers' own (they are the previous mover's pieces, so here the
+// geometry is the correct one, quirk A.3) and drop the kings-facing term, which is not part of
+// _is_in_check.  Regular also means no enemy K/A/B within reach of the king's row, so R, C, N, P
+// are the only possible attackers, exactly the ones the masks hold.
+XQ_HD bool check_fast(const FastCtx& f, int player) {
+  FastCtx c = f;
+  c.geo = -player;
+  c.side_ok = player == 1 ? f.kr >= 5 : f.kr < 5;  // a crossed pawn of the OTHER side (:242,:247)
+  c.same_file = false;
+  return suicide_fast(c, -1, -1);
+}
+
 // ---- move generation --------------------------------------------------------
 // One work item of candidate generation: (own piece at `from`, direction d of
 // the reference's per-piece generator order).  Produces, in generator order,

@@ -148,3 +148,23 @@ extern "C" int xqh_in_check(const int8_t* board, int player, int current_player,
 extern "C" double xqh_position_change(int type, int player, int from, int to, int enemy_king) {
   return position_change(type, player, from, to, enemy_king);
 }
+
+// check_fast(): the check test of make_move for regular positions.  -1 when the position is not
+// regular (the kernels then use the general probes).
+extern "C" int xqh_check_fast(const int8_t* board, int player, int red_king, int black_king) {
+  WarpSmem w;
+  stage(w, board);
+  Game g{};
+  g.player = player;
+  g.red_king = red_king;
+  g.black_king = black_king;
+  const int ownK = player == 1 ? red_king : black_king;
+  int n_kings = 0;
+  bool exotic = false;
+  for (int s = 0; s < XQ_NSQ; ++s) {
+    n_kings += w.sq[s] == player * KING;
+    exotic |= exotic_piece(w.sq[s], s, player, ownK < 0 ? 0 : ownK);
+  }
+  if (exotic || !regular_king(w, player, ownK, n_kings)) return -1;
+  return check_fast(make_fast_ctx(w, g), player) ? 1 : 0;
+}

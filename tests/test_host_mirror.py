@@ -14,6 +14,7 @@ def hm():
     lib.xqh_legal_moves.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
     lib.xqh_in_check.argtypes = [C.c_void_p] + [C.c_int] * 4
     lib.xqh_in_check_dirs.argtypes = [C.c_void_p] + [C.c_int] * 4
+    lib.xqh_check_fast.argtypes = [C.c_void_p] + [C.c_int] * 3
     lib.xqh_position_change.argtypes = [C.c_int] * 5
     lib.xqh_position_change.restype = C.c_double
     return lib
@@ -52,6 +53,7 @@ def test_golden_positions(hm, golden):
 @pytest.mark.parametrize("bias", [0, 200])
 def test_fuzz_playouts_vs_oracle(hm, xo, bias):
     max_cand = 0
+    n_fast = [0]
     for g in range(150):
         e = xo.Env()
         for ply in range(70):
@@ -66,13 +68,18 @@ def test_fuzz_playouts_vs_oracle(hm, xo, bias):
                     int(e.is_in_check(who)), (g, ply, who)
                 assert hm.xqh_in_check_dirs(b.ctypes.data, who, e.s.player, e.s.red_king, e.s.black_king) == \
                     int(e.is_in_check(who)), (g, ply, who)
+            # make_move's check test (:317) = the side to move's king under the PREVIOUS mover's
+            # geometry: the mask form used on regular positions against the general probes
+            fast = hm.xqh_check_fast(b.ctypes.data, e.s.player, e.s.red_king, e.s.black_king)
+            assert fast == hm.xqh_in_check(b.ctypes.data, e.s.player, -e.s.player, e.s.red_king, e.s.black_king), (g, ply)
+            n_fast[0] += fast >= 0
             if len(lm) == 0:
                 break
             idx = xo.lib().xqo_pick_move(e.s, lm.ctypes.data, len(lm), 99, g, ply, bias)
             _, _, done = e.make_move(int(lm[idx]))
             if done:
                 break
-    assert max_cand <= 128
+    assert max_cand <= 128 and n_fast[0] > 5000       # play never leaves the regular path
 
 
 def test_fuzz_arbitrary_boards_vs_oracle(hm, xo):
@@ -99,3 +106,6 @@ def test_fuzz_arbitrary_boards_vs_oracle(hm, xo):
             continue
         mv, _ = _legal(hm, board, player, red, black)
         assert np.array_equal(mv, e.legal_moves_packed()), it
+        fast = hm.xqh_check_fast(board.ctypes.data, player, red, black)
+        if fast >= 0:
+            assert fast == hm.xqh_in_check(board.ctypes.data, player, -player, red, black), it
