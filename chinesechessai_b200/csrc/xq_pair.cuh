@@ -197,7 +197,7 @@ __device__ __forceinline__ int pair_movegen(ThreadBoard& w, Game& g, const uint3
   if (!exotic) {
     // non-king moves, bitmask test: the list is cut in two equal runs, so the lanes' trip counts
     // match however the pieces fell (a rook's 17 candidates vs a pawn's 1)
-    const FastCtx f = make_fast_ctx(w, g);
+    const FastCtx f = make_fast_ctx(w, g, g_touch);
     const int cut = (total + 1) >> 1, j_end = sub ? total : cut;
 #pragma unroll 1
     for (int j = sub ? cut : 0; j < j_end; ++j) {

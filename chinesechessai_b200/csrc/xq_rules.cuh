@@ -409,17 +409,32 @@ struct FastCtx {
   unsigned legocc;                  // bit diag: leg K+(a,b) occupied or off-board
   unsigned between;                 // rows strictly between the two cached kings (same file)
   bool same_file, side_ok;
+  const uint32_t* touch;            // row K of the touch table (xq_touch_table.inc)
 };
+
+// Touch table (generated, xq_touch_table.inc): entry [K][s] = what a piece leaving or landing on
+// square s changes in the masks above for a king on K — the bit of s in the king's row (bits 0-8)
+// and column (9-18), the leg bit if s is a diagonal neighbour (19-22), the knight bit if s is one
+// of the eight knight squares (23-30).  32 KB; a game's kings visit a handful of rows of it.
+constexpr int kTouchEntries = 90 * 90;
+XQ_HD uint32_t touch_entry(const uint32_t* row, int s) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(row + s);
+#else
+  return row[s];
+#endif
+}
 
 // diag index of probe_diag: bit1 = (dr>0), bit0 = (dc>0)
 XQ_HD int diag_index(int dr, int dc) { return (dr > 0 ? 2 : 0) + (dc > 0 ? 1 : 0); }
 
 // Sequential construction (host mirror); the kernel builds the same masks with ballots.
 template <class W>
-XQ_HD FastCtx make_fast_ctx(const W& w, const Game& g) {
+XQ_HD FastCtx make_fast_ctx(const W& w, const Game& g, const uint32_t* touch_table) {
   FastCtx f{};
   const int player = g.player, es = -player;
   f.K = player == 1 ? g.red_king : g.black_king;
+  f.touch = touch_table + f.K * 90;
   f.kr = f.K / 9;
   f.kc = f.K - f.kr * 9;
   f.geo = player;
@@ -482,23 +497,16 @@ XQ_HD bool suicide_fast(const FastCtx& f, int from, int to) {
   unsigned er_col = f.er_col, ec_col = f.ec_col, ep_col = f.ep_col;
   unsigned ekn = f.ekn, legocc = f.legocc;
   if (from >= 0) {
-    const int fr = from / 9, fc = from - fr * 9, tr = to / 9, tc = to - tr * 9;
-    if (fr == f.kr) rowm &= ~(1u << fc);
-    if (fc == f.kc) colm &= ~(1u << fr);
-    if (tr == f.kr) {  // own piece lands on the row: occupied, whatever stood there is gone
-      const unsigned b = 1u << tc;
-      rowm |= b; er_row &= ~b; ec_row &= ~b; ep_row &= ~b;
-    }
-    if (tc == f.kc) {
-      const unsigned b = 1u << tr;
-      colm |= b; er_col &= ~b; ec_col &= ~b; ep_col &= ~b;
-    }
-    const int fdr = fr - f.kr, fdc = fc - f.kc, tdr = tr - f.kr, tdc = tc - f.kc;
-    const int afr = xq_abs(fdr), afc = xq_abs(fdc), atr = xq_abs(tdr), atc = xq_abs(tdc);
-    if (afr == 1 && afc == 1) legocc &= ~(1u << diag_index(fdr, fdc));
-    if (atr == 1 && atc == 1) legocc |= 1u << diag_index(tdr, tdc);
-    if (atr + atc == 3 && atr != 0 && atc != 0)  // lands on a knight square: that knight is gone
-      ekn &= ~(1u << (2 * diag_index(tdr, tdc) + (atr == 1 ? 1 : 0)));
+    // what leaving `from` and landing on `to` change, from the touch table (no divisions, no
+    // compares): the square's bit in the king's row / column, its leg bit, its knight bit
+    const uint32_t mf = touch_entry(f.touch, from), mt = touch_entry(f.touch, to);
+    const unsigned rt = mt & 0x1FFu, ct = (mt >> 9) & 0x3FFu;
+    rowm = (rowm & ~(mf & 0x1FFu)) | rt;        // own piece lands on the row: occupied,
+    er_row &= ~rt; ec_row &= ~rt; ep_row &= ~rt;  // whatever stood there is gone
+    colm = (colm & ~((mf >> 9) & 0x3FFu)) | ct;
+    er_col &= ~ct; ec_col &= ~ct; ep_col &= ~ct;
+    legocc = (legocc & ~((mf >> 19) & 0xFu)) | ((mt >> 19) & 0xFu);
+    ekn &= ~(mt >> 23);                         // lands on a knight square: that knight is gone
   }
   bool hit = false;
   {  // (0,+1): nearest piece toward higher columns
@@ -656,6 +664,9 @@ XQ_HD bool regular_king(const W& w, int player, int own_king, int n_own_kings) {
 static __device__ const uint32_t g_leap[kLeapEntries] = {
 #include "xq_leap_table.inc"
 };
+static __device__ const uint32_t g_touch[kTouchEntries] = {
+#include "xq_touch_table.inc"
+};
 
 // Cold paths are kept out of line: the fused loop's hot code has to stay small enough for the
 // L1.5 instruction cache (profiles/r1: v2 72 KB -> no_instruction 3.0 stalls per issue).
@@ -745,6 +756,7 @@ __device__ __forceinline__ int movegen(WarpSmem& w, Game& g, const uint32_t* __r
     {
       const int es = -player;
       f.K = ownK; f.kr = ownK / 9; f.kc = ownK - f.kr * 9; f.geo = player;
+      f.touch = g_touch + ownK * 90;
       f.rowm = w.rows[f.kr];
       f.colm = w.cols[f.kc];
       f.er_row = f.ec_row = f.ep_row = f.er_col = f.ec_col = f.ep_col = 0;

@@ -143,7 +143,7 @@ __device__ __forceinline__ int tpb_movegen(ThreadBoard& w, Game& g, const uint32
   // legality (:118), compacting in place
   int n = 0;
   if (!exotic) {
-    const FastCtx f = make_fast_ctx(w, g);
+    const FastCtx f = make_fast_ctx(w, g, g_touch);
     int kfirst = -1, kcount = 0;
 #pragma unroll 1
     for (int j = 0; j < nc; ++j) {  // non-king moves: bitmask test, uniform code for all lanes

@@ -22,6 +22,9 @@ static void stage(WarpSmem& w, const int8_t* board) {
 static const uint32_t h_leap[kLeapEntries] = {
 #include "../../chinesechessai_b200/csrc/xq_leap_table.inc"
 };
+static const uint32_t h_touch[kTouchEntries] = {
+#include "../../chinesechessai_b200/csrc/xq_touch_table.inc"
+};
 
 // mode 0: every candidate through suicide(); mode 1: the kernel's Phase B (relevance filter,
 // sentinel "no move" evaluation, flag bits) executed sequentially.
@@ -63,7 +66,7 @@ extern "C" int xqh_legal_moves(const int8_t* board, int player, int red_king, in
   }
   const int kr = ownK >= 0 ? ownK / 9 : 0, kc = ownK >= 0 ? ownK - kr * 9 : 0;
   if (mode == 2 && !exotic) {  // the kernel's regular-position path: bitmask test + king probes
-    const FastCtx f = make_fast_ctx(w, g);
+    const FastCtx f = make_fast_ctx(w, g, h_touch);
     const bool cur_bad = suicide_fast(f, -1, -1);
     if (ncand_out) ncand_out[1] = 0, ncand_out[2] = 0;
     for (int j = 0; j < ncand; ++j) {
@@ -166,5 +169,5 @@ extern "C" int xqh_check_fast(const int8_t* board, int player, int red_king, int
     exotic |= exotic_piece(w.sq[s], s, player, ownK < 0 ? 0 : ownK);
   }
   if (exotic || !regular_king(w, player, ownK, n_kings)) return -1;
-  return check_fast(make_fast_ctx(w, g), player) ? 1 : 0;
+  return check_fast(make_fast_ctx(w, g, h_touch), player) ? 1 : 0;
 }
