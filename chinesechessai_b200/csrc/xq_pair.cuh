@@ -126,13 +126,14 @@ __device__ __forceinline__ int pair_movegen(ThreadBoard& w, Game& g, const uint3
   // candidates: lane 0 takes the first half of the pieces, lane 1 the rest; the own king's
   // block of candidates (contiguous) is noted on the way
   const int dir = sub ? -1 : 1, base = sub ? kTpbMoveCap - 1 : 0;
+  const Tables tb{leap, g_ray};
   const int half = (n_own >> 1) * 4;
   const int t_end = sub ? n_own * 4 : half;
   int nc = 0, kfirst = 0, kcount = 0;
 #pragma unroll 1
   for (int t = sub ? half : 0; t < t_end; ++t) {
     const int pi = t >> 2;
-    const Item it = gen_item(w, leap, player, w.own[pi < own0 ? pi : kHalfOwn + (pi - own0)], t & 3);
+    const Item it = gen_item(w, tb, player, w.own[pi < own0 ? pi : kHalfOwn + (pi - own0)], t & 3);
     const int cnt = it.empties + (it.e1 >= 0) + (it.e2 >= 0);
     if (nc + cnt > kTpbMoveCap) {
       g.flags |= XQ_F_OVERFLOW;

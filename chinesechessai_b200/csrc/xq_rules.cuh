@@ -487,7 +487,18 @@ XQ_HD bool king_move_facing(const Game& g, const Probe& p, int to) {
 
 // isolate the lowest / highest set bit (0 if none)
 XQ_HD unsigned low_bit(unsigned x) { return x & (0u - x); }
-XQ_HD unsigned high_bit(unsigned x) { return x ? 0x80000000u >> xq_clz(x) : 0u; }
+XQ_HD unsigned high_bit(unsigned x) {
+#if defined(__CUDA_ARCH__)
+  // bfind gives the index of the leading one, or 0xFFFFFFFF for 0; shl clamps shift amounts
+  // above 31 to 32, i.e. to a zero result: two instructions, no compare / select
+  unsigned idx, r;
+  asm("bfind.u32 %0, %1;" : "=r"(idx) : "r"(x));
+  asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(1u), "r"(idx));
+  return r;
+#else
+  return x ? 0x80000000u >> xq_clz(x) : 0u;
+#endif
+}
 
 // _is_move_suicide for a non-king move of the side to move in a regular position
 // (from < 0: the position itself).  Same verdict as suicide(); pure register arithmetic.
@@ -581,30 +592,34 @@ XQ_HD int leap_index(int player, int pt, int from, int d) {
   return ((player == 1 ? 0 : 8) + pt) * 360 + from * 4 + d;
 }
 
+// Ray table (generated, xq_ray_table.inc): entry [orientation][position][occupancy mask][backward]
+// = empties | first << 4 | second << 8 for a rook / cannon ray (see gen_ray_table.py).  58 KB.
+constexpr int kRayRowEntries = 9 * 512 * 2, kRayEntries = kRayRowEntries + 10 * 1024 * 2;
+struct Tables {
+  const uint32_t* leap;
+  const uint16_t* ray;
+};
+
 template <class W>
-XQ_HD Item gen_item(const W& w, const uint32_t* __restrict__ leap, int player, int from, int d) {
+XQ_HD Item gen_item(const W& w, const Tables& tb, int player, int from, int d) {
   Item it{from, 0, 0, -1, -1};
   const int p = w.sq[from];
   const int pt = p < 0 ? -p : p;
-  const int r = from / 9, c = from - r * 9;
+  const uint32_t* __restrict__ leap = tb.leap;
   if (pt == ROOK || pt == CANNON) {  // :199-235, rays (0,1),(0,-1),(1,0),(-1,0)
-    const bool horiz = d < 2, fwd = (d & 1) == 0;
-    const int len = horiz ? 9 : 10;
-    unsigned m = horiz ? w.rows[r] : w.cols[c];
-    int x = horiz ? c : r;
-    if (!fwd) {  // mirror so the ray always runs toward higher bits
-      m = xq_brev(m) >> (32 - len);
-      x = len - 1 - x;
-    }
-    it.delta = (horiz ? 1 : 9) * (fwd ? 1 : -1);
-    const unsigned ahead = m >> (x + 1);
-    const int first = ahead ? xq_ffs(ahead) : 0;
-    it.empties = first ? first - 1 : len - 1 - x;
-    int hitd = first;
-    if (pt == CANNON) {
-      const unsigned a2 = ahead & (ahead - 1);
-      hitd = a2 ? xq_ffs(a2) : 0;
-    }
+    const int r = from / 9, c = from - r * 9;
+    const bool horiz = d < 2;
+    const int back = d & 1;
+    const int idx = horiz ? ((c * 512 + (int)w.rows[r]) * 2 + back)
+                          : (kRayRowEntries + (r * 1024 + (int)w.cols[c]) * 2 + back);
+#if defined(__CUDA_ARCH__)
+    const unsigned e = __ldg(tb.ray + idx);
+#else
+    const unsigned e = tb.ray[idx];
+#endif
+    it.delta = (horiz ? 1 : 9) * (back ? -1 : 1);
+    it.empties = (int)(e & 15u);
+    const int hitd = (int)((pt == CANNON ? e >> 8 : e >> 4) & 15u);
     if (hitd) {
       const int s = from + hitd * it.delta;
       if ((int)w.sq[s] * player <= 0) it.e1 = s;  // :116
@@ -667,6 +682,9 @@ static __device__ const uint32_t g_leap[kLeapEntries] = {
 static __device__ const uint32_t g_touch[kTouchEntries] = {
 #include "xq_touch_table.inc"
 };
+static __device__ const uint16_t g_ray[kRayEntries] = {
+#include "xq_ray_table.inc"
+};
 
 // Cold paths are kept out of line: the fused loop's hot code has to stay small enough for the
 // L1.5 instruction cache (profiles/r1: v2 72 KB -> no_instruction 3.0 stalls per issue).
@@ -695,6 +713,7 @@ static __device__ __noinline__ void legality_generic(WarpSmem* wp, const Game* g
 template <int L>
 __device__ __forceinline__ int movegen(WarpSmem& w, Game& g, const uint32_t* __restrict__ leap,
                                        bool* checked_out = nullptr) {
+  const Tables tb{leap, g_ray};
   using T = Tile<L>;
   const int lane = T::lane();
   const unsigned lt = (1u << lane) - 1u;
@@ -725,7 +744,7 @@ __device__ __forceinline__ int movegen(WarpSmem& w, Game& g, const uint32_t* __r
   for (int base = 0; base < n_items; base += L) {
     const int t = base + lane;
     Item it{0, 0, 0, -1, -1};
-    if (t < n_items) it = gen_item(w, leap, player, w.own[t >> 2], t & 3);
+    if (t < n_items) it = gen_item(w, tb, player, w.own[t >> 2], t & 3);
     const int cnt = it.empties + (it.e1 >= 0) + (it.e2 >= 0);
     int incl = cnt;
 #pragma unroll

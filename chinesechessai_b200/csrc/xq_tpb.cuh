@@ -122,9 +122,10 @@ __device__ __forceinline__ int tpb_movegen(ThreadBoard& w, Game& g, const uint32
 
   // candidates in generator order
   int nc = 0;
+  const Tables tb{leap, g_ray};
 #pragma unroll 1
   for (int t = 0; t < n_own * 4; ++t) {
-    const Item it = gen_item(w, leap, player, w.own[t >> 2], t & 3);
+    const Item it = gen_item(w, tb, player, w.own[t >> 2], t & 3);
     const int cnt = it.empties + (it.e1 >= 0) + (it.e2 >= 0);
     if (nc + cnt > kTpbMoveCap) {
       g.flags |= XQ_F_OVERFLOW;

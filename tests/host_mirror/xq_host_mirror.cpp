@@ -22,6 +22,10 @@ static void stage(WarpSmem& w, const int8_t* board) {
 static const uint32_t h_leap[kLeapEntries] = {
 #include "../../chinesechessai_b200/csrc/xq_leap_table.inc"
 };
+static const uint16_t h_ray[kRayEntries] = {
+#include "../../chinesechessai_b200/csrc/xq_ray_table.inc"
+};
+static const Tables h_tables{h_leap, h_ray};
 static const uint32_t h_touch[kTouchEntries] = {
 #include "../../chinesechessai_b200/csrc/xq_touch_table.inc"
 };
@@ -47,7 +51,7 @@ extern "C" int xqh_legal_moves(const int8_t* board, int player, int red_king, in
   exotic = exotic || !regular_king(w, player, ownK, n_kings);
   int ncand = 0;
   for (int t = 0; t < n_own * 4; ++t) {
-    const Item it = gen_item(w, h_leap, player, w.own[t >> 2], t & 3);
+    const Item it = gen_item(w, h_tables, player, w.own[t >> 2], t & 3);
     const int cnt = it.empties + (it.e1 >= 0) + (it.e2 >= 0);
     if (ncand + cnt > XQ_CAND_CAP) return -1;
     for (int k = 1; k <= it.empties; ++k) w.cand[ncand++] = (uint16_t)((it.from << 8) | (it.from + k * it.delta));
