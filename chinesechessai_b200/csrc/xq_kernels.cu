@@ -948,7 +948,10 @@ __global__ void __launch_bounds__(kSmWarps * 32, 1)
       if (lane == 0) won = atomicCAS(&sc.busy[who], 0, 1) == 0 ? 1 : 0;
       if (__shfl_sync(0xffffffffu, won, 0)) { slot = who; break; }
     }
+    // acquire: everything the previous owner wrote (slab, meta / results / carry rows, history)
+    // is ordered before this warp's reads — its release below is fence + __syncwarp + flag
     __threadfence_block();
+    __syncwarp();
     const int gi = vgid[slot], it = vprog[slot];
     ThreadBoard& w = slabs[slot * kQueueGroup + (lane >> 1)];
     const int g = gi * kQueueGroup + (lane >> 1);
@@ -1060,7 +1063,11 @@ __global__ void __launch_bounds__(kSmWarps * 32, 1)
     }
     // ---- put the group back, or refill the slot when every game of the group is over
     const bool group_over = __all_sync(0xffffffffu, fin) || it + 1 >= iters;
+    // release: every lane's writes are performed (fence), every lane has passed its fence
+    // (__syncwarp: the vote above synchronises execution but orders no memory), then lane 0
+    // publishes the slot
     __threadfence_block();
+    __syncwarp();
     if (lane == 0) {
       if (group_over) {
         const int k = atomicAdd(&sc.next, 1);

@@ -405,10 +405,15 @@ struct FastCtx {
   unsigned rowm, colm;              // occupancy of K's row (bit = column) / column (bit = row)
   unsigned er_row, ec_row, ep_row;  // enemy rooks / cannons / pawns on K's row
   unsigned er_col, ec_col, ep_col;  // ... on K's column
-  unsigned ekn;                     // bit 2*diag+t: enemy knight on K+(2a,b) [t=0] / K+(a,2b) [t=1]
+  unsigned ekn;                     // bit diag+4t: enemy knight on K+(2a,b) [t=0] / K+(a,2b) [t=1]
   unsigned legocc;                  // bit diag: leg K+(a,b) occupied or off-board
-  unsigned between;                 // rows strictly between the two cached kings (same file)
-  bool same_file, side_ok;
+  // derived once per position (finish_fast_ctx): the test itself is then mask algebra only
+  unsigned row_lo, row_hi;          // the bits below / above the king in its row
+  unsigned col_lo, col_hi;          // ... in its column
+  unsigned prow, pcol;              // squares of the row / column an enemy pawn attacks K from
+  unsigned facing;                  // rows strictly between the two kings on a shared file; all ones
+                                    // when they are on different files (the test can then never fire:
+                                    // the king's own bit is in colm)
   const uint32_t* touch;            // row K of the touch table (xq_touch_table.inc)
 };
 
@@ -427,6 +432,28 @@ XQ_HD uint32_t touch_entry(const uint32_t* row, int s) {
 
 // diag index of probe_diag: bit1 = (dr>0), bit0 = (dc>0)
 XQ_HD int diag_index(int dr, int dc) { return (dr > 0 ? 2 : 0) + (dc > 0 ? 1 : 0); }
+
+// Pawn-attack squares for geometry `geo` (chess_env.py:240-249 as seen from the attacked king):
+// sideways from the adjacent columns once the pawn has crossed the river (the king then stands
+// on the far side for `geo`), vertically from the one adjacent row the pawn moves away from.
+XQ_HD void set_pawn_masks(FastCtx& f, int geo) {
+  const bool side_ok = geo == 1 ? f.kr < 5 : f.kr >= 5;
+  f.prow = side_ok ? (((2u << f.kc) | ((1u << f.kc) >> 1)) & 0x1FFu) : 0u;
+  f.pcol = geo == 1 ? ((2u << f.kr) & 0x3FFu) : ((1u << f.kr) >> 1);
+}
+// The fields derived from K, the geometry and the enemy king's cached square.
+XQ_HD void finish_fast_ctx(FastCtx& f, int player, int enemy_king) {
+  f.row_lo = (1u << f.kc) - 1u;
+  f.row_hi = ~((2u << f.kc) - 1u) & 0x1FFu;
+  f.col_lo = (1u << f.kr) - 1u;
+  f.col_hi = ~((2u << f.kr) - 1u) & 0x3FFu;
+  set_pawn_masks(f, player);
+  f.facing = 0xFFFFFFFFu;
+  if (enemy_king >= 0 && enemy_king % 9 == f.kc) {
+    const int er = enemy_king / 9, lo = xq_min(er, f.kr), hi = xq_max(er, f.kr);
+    f.facing = ((1u << hi) - 1u) & ~((2u << lo) - 1u);
+  }
+}
 
 // Sequential construction (host mirror); the kernel builds the same masks with ballots.
 template <class W>
@@ -458,16 +485,10 @@ XQ_HD FastCtx make_fast_ctx(const W& w, const Game& g, const uint32_t* touch_tab
     const bool lon = lr >= 0 && lr <= 9 && lc >= 0 && lc <= 8;
     if (!lon || w.sq[lr * 9 + lc] != 0) f.legocc |= 1u << d;
     const int r2 = f.kr + 2 * a, c2 = f.kc + 2 * b;
-    if (lon && r2 >= 0 && r2 <= 9 && w.sq[r2 * 9 + lc] == es * KNIGHT) f.ekn |= 1u << (2 * d);
-    if (lon && c2 >= 0 && c2 <= 8 && w.sq[lr * 9 + c2] == es * KNIGHT) f.ekn |= 1u << (2 * d + 1);
+    if (lon && r2 >= 0 && r2 <= 9 && w.sq[r2 * 9 + lc] == es * KNIGHT) f.ekn |= 1u << d;
+    if (lon && c2 >= 0 && c2 <= 8 && w.sq[lr * 9 + c2] == es * KNIGHT) f.ekn |= 1u << (4 + d);
   }
-  f.side_ok = player == 1 ? f.kr < 5 : f.kr >= 5;
-  const int ek = player == 1 ? g.black_king : g.red_king;
-  if (ek >= 0 && ek % 9 == f.kc) {
-    const int er = ek / 9, lo = xq_min(er, f.kr), hi = xq_max(er, f.kr);
-    f.same_file = true;
-    f.between = ((1u << hi) - 1u) & ~((2u << lo) - 1u);
-  }
+  finish_fast_ctx(f, player, player == 1 ? g.black_king : g.red_king);
   return f;
 }
 
@@ -516,46 +537,20 @@ XQ_HD bool suicide_fast(const FastCtx& f, int from, int to) {
     er_row &= ~rt; ec_row &= ~rt; ep_row &= ~rt;  // whatever stood there is gone
     colm = (colm & ~((mf >> 9) & 0x3FFu)) | ct;
     er_col &= ~ct; ec_col &= ~ct; ep_col &= ~ct;
-    legocc = (legocc & ~((mf >> 19) & 0xFu)) | ((mt >> 19) & 0xFu);
+    legocc = (legocc & ~(mf >> 19)) | ((mt >> 19) & 0xFu);
     ekn &= ~(mt >> 23);                         // lands on a knight square: that knight is gone
   }
-  bool hit = false;
-  {  // (0,+1): nearest piece toward higher columns
-    const unsigned a = rowm >> (f.kc + 1), first = low_bit(a), second = low_bit(a ^ first);
-    hit |= (first & (er_row >> (f.kc + 1))) != 0;
-    hit |= (second & (ec_row >> (f.kc + 1))) != 0;
-    hit |= f.side_ok && (1u & a & (ep_row >> (f.kc + 1))) != 0;
-  }
-  {  // (0,-1)
-    const unsigned lowm = (1u << f.kc) - 1u;
-    const unsigned b = rowm & lowm, first = high_bit(b), second = high_bit(b ^ first);
-    hit |= (first & er_row) != 0;
-    hit |= (second & ec_row) != 0;
-    hit |= f.side_ok && f.kc > 0 && ((b & ep_row) >> (f.kc - 1)) & 1u;
-  }
-  {  // (+1,0): a pawn below K attacks iff pawns move to smaller rows (geo==1), chess_env.py:241
-    const unsigned a = colm >> (f.kr + 1), first = low_bit(a), second = low_bit(a ^ first);
-    hit |= (first & (er_col >> (f.kr + 1))) != 0;
-    hit |= (second & (ec_col >> (f.kr + 1))) != 0;
-    hit |= f.geo == 1 && (1u & a & (ep_col >> (f.kr + 1))) != 0;
-  }
-  {  // (-1,0)
-    const unsigned lowm = (1u << f.kr) - 1u;
-    const unsigned b = colm & lowm, first = high_bit(b), second = high_bit(b ^ first);
-    hit |= (first & er_col) != 0;
-    hit |= (second & ec_col) != 0;
-    hit |= f.geo == -1 && f.kr > 0 && ((b & ep_col) >> (f.kr - 1)) & 1u;
-  }
-  // knights: a free leg exposes the two knight squares behind it (:182-197)
-  const unsigned knpair = (ekn | (ekn >> 1)) & 0x55u;  // bit 2*diag: a knight on either square
-  const unsigned freeleg = ~legocc & 0xFu;
-  hit |= (((freeleg & 1u) ? knpair : 0u) & 0x01u) != 0;
-  hit |= (((freeleg & 2u) ? knpair : 0u) & 0x04u) != 0;
-  hit |= (((freeleg & 4u) ? knpair : 0u) & 0x10u) != 0;
-  hit |= (((freeleg & 8u) ? knpair : 0u) & 0x40u) != 0;
+  // nearest and second-nearest piece on each of the four rays, as bits of the row / column
+  const unsigned ra = rowm & f.row_hi, rb = rowm & f.row_lo, ca = colm & f.col_hi, cb = colm & f.col_lo;
+  const unsigned f1 = low_bit(ra), f2 = high_bit(rb), f3 = low_bit(ca), f4 = high_bit(cb);
+  const unsigned s1 = low_bit(ra ^ f1), s2 = high_bit(rb ^ f2), s3 = low_bit(ca ^ f3), s4 = high_bit(cb ^ f4);
+  // rook = nearest piece, cannon = second piece (the nearest is its screen), pawn = adjacent
+  // square on the side it attacks from; knights: a free leg exposes the two squares behind it
+  unsigned h = ((f1 | f2) & er_row) | ((s1 | s2) & ec_row) | (ep_row & f.prow) |
+               ((f3 | f4) & er_col) | ((s3 | s4) & ec_col) | (ep_col & f.pcol) |
+               ((ekn | (ekn >> 4)) & ~legocc & 0xFu);
   // kings facing (:466-495): caches are unchanged by a non-king move
-  hit |= f.same_file && (colm & f.between) == 0;
-  return hit;
+  return h != 0 || (colm & f.facing) == 0;
 }
 
 // make_move's check test (chess_env.py:317: is the side now to move in check, geometry of the
@@ -566,9 +561,8 @@ XQ_HD bool suicide_fast(const FastCtx& f, int from, int to) {
 // are the only possible attackers, exactly the ones the masks hold.
 XQ_HD bool check_fast(const FastCtx& f, int player) {
   FastCtx c = f;
-  c.geo = -player;
-  c.side_ok = player == 1 ? f.kr >= 5 : f.kr < 5;  // a crossed pawn of the OTHER side (:242,:247)
-  c.same_file = false;
+  set_pawn_masks(c, -player);  // the attackers' own geometry
+  c.facing = 0xFFFFFFFFu;
   return suicide_fast(c, -1, -1);
 }
 
@@ -800,14 +794,14 @@ __device__ __forceinline__ int movegen(WarpSmem& w, Game& g, const uint32_t* __r
         const int t = base + lane;
         bool flag = false;
         if (t < 12) {
-          const int d = t < 8 ? t >> 1 : t - 8;
+          const int d = t & 3;  // tasks 0-3: K+(2a,b), 4-7: K+(a,2b), 8-11: the leg K+(a,b)
           const int a = (d & 2) ? 1 : -1, b = (d & 1) ? 1 : -1;
           const int lr = f.kr + a, lc = f.kc + b;
           const bool lon = lr >= 0 && lr <= 9 && lc >= 0 && lc <= 8;
           if (t >= 8) {
             flag = !lon || w.sq[lr * 9 + lc] != 0;
           } else if (lon) {
-            const int r2 = (t & 1) ? lr : f.kr + 2 * a, c2 = (t & 1) ? f.kc + 2 * b : lc;
+            const int r2 = (t & 4) ? lr : f.kr + 2 * a, c2 = (t & 4) ? f.kc + 2 * b : lc;
             flag = r2 >= 0 && r2 <= 9 && c2 >= 0 && c2 <= 8 && w.sq[r2 * 9 + c2] == es * KNIGHT;
           }
         }
@@ -815,15 +809,7 @@ __device__ __forceinline__ int movegen(WarpSmem& w, Game& g, const uint32_t* __r
         f.ekn |= b2 & 0xFFu;
         f.legocc |= (b2 >> 8) & 0xFu;
       }
-      f.side_ok = player == 1 ? f.kr < 5 : f.kr >= 5;
-      const int ek = player == 1 ? g.black_king : g.red_king;
-      f.same_file = false;
-      f.between = 0;
-      if (ek >= 0 && ek % 9 == f.kc) {
-        const int er = ek / 9, lo = min(er, f.kr), hi = max(er, f.kr);
-        f.same_file = true;
-        f.between = ((1u << hi) - 1u) & ~((2u << lo) - 1u);
-      }
+      finish_fast_ctx(f, player, player == 1 ? g.black_king : g.red_king);
     }
     // B.1: classify — king move / touches the king's lines / cannot matter
     int nwl = 0;
