@@ -815,7 +815,7 @@ def run_ours(args):
             cpu_baseline["reference_unavailable"] = "Python reference not timed (absent, --no-python or N>1)"
 
     kc = kernel_counts()
-    mode = os.environ.get("XQ_PLAYOUT_MODE") or ("pairs" if n >= 32768 else "warp")
+    mode = os.environ.get("XQ_PLAYOUT_MODE") or ("pairs" if n >= 24576 else "warp")
     kinfo = kc.get(mode, {})
     plies_per_launch = total_plies / (args.steps * world)
     kern_s = kern_ms * 1e-3 / args.steps

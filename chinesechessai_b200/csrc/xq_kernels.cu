@@ -40,7 +40,7 @@ constexpr int kThreads = kWarpsPerCta * 32;
 #define XQ_PAIR_MIN_GAMES 40960
 #endif
 #ifndef XQ_SM_MIN_GAMES
-#define XQ_SM_MIN_GAMES 32768
+#define XQ_SM_MIN_GAMES 24576  // measured crossover with the warp mapping: 4.3e8 vs 4.1e8 here, 3.0e8 vs 4.0e8 at 16,384
 #endif
 
 // ---------------------------------------------------------------------------
@@ -1522,8 +1522,8 @@ int xq_playout(int8_t* board, xq_meta* meta, uint64_t* pos_hist, int hist_cap, u
   // path stopped firing in play — 6.7 vs 6.5 ms at 65,536 boards)
   const bool pairq = !trace && mode_env != nullptr && strcmp(mode_env, "pairq") == 0;
   // "pairs": lane pairs scheduled inside each SM (playout_sm_kernel) — the default once the batch
-  // gives every SM a full set of groups (measured: 4.5e8 vs 4.1e8 for the warp mapping at 32,768
-  // boards, 8.1e8 vs 7.1e8 for the one-wave pair kernel at 65,536)
+  // gives the SMs enough groups (measured: 5.7e8 vs 4.2e8 for the warp mapping at 32,768 boards,
+  // 1.05e9 vs 9.4e8 for the one-wave pair kernel at 65,536)
   const bool pairs = !trace && (mode_env ? strcmp(mode_env, "pairs") == 0 : n_games >= XQ_SM_MIN_GAMES);
   if (pairs) return launch_playout_sm(board, meta, pos_hist, hist_cap, seed, first_game_id, max_plies,
                                       capture_bias, results, n_games, st);

@@ -577,8 +577,8 @@ struct Item {
 };
 
 // Leaper table (generated, xq_leap_table.inc): entry [side][piece type][from][d] =
-// t1 | t2<<8 | blocker<<16, each a square or 0xFF: the targets of generator slot d that are
-// on-board and inside the zone the generator enforces (palace :127-147, own river side
+// t1 | t2<<8 | blocker<<16: the targets of generator slot d (a square, or the piece's own square
+// for "none") that are on-board and inside the zone the generator enforces (palace :127-147, own river side
 // :159-170, pawn direction/crossing :240-249) and the square that must be empty (knight leg
 // :189-195, bishop eye :171-174).  23 KB, read through the L1/read-only path.
 constexpr int kLeapEntries = 2 * 8 * 90 * 4;
@@ -628,9 +628,10 @@ XQ_HD Item gen_item(const W& w, const Tables& tb, int player, int from, int d) {
 #endif
   const uint32_t bk = (e >> 16) & 0xFFu;
   if (bk != 0xFFu && w.sq[bk] != 0) return it;  // blocked leg / eye
+  // a slot without a target names the piece's own square, which the own-piece test rejects
   const uint32_t t1 = e & 0xFFu, t2 = (e >> 8) & 0xFFu;
-  if (t1 != 0xFFu && (int)w.sq[t1] * player <= 0) it.e1 = (int)t1;  // :116
-  if (t2 != 0xFFu && (int)w.sq[t2] * player <= 0) it.e2 = (int)t2;
+  if ((int)w.sq[t1] * player <= 0) it.e1 = (int)t1;  // :116
+  if ((int)w.sq[t2] * player <= 0) it.e2 = (int)t2;
   return it;
 }
 

@@ -27,8 +27,11 @@ for r in csv.reader(open(path, errors="replace")):
     if r[0] in ("File Name", "Function Name") or hdr is None or not r[0].strip().isdigit():
         continue
     g = lambda k: float(r[hdr[k]] or 0) if hdr.get(k) is not None and r[hdr[k]] not in ("-", "") else 0.0
-    rows.append((cur_file, int(r[0]), r[1].strip(), g("Instructions Executed"),
-                 g("Thread Instructions Executed"), g("Warp Stall Sampling (All Samples)")))
+    try:
+        rows.append((cur_file, int(r[0]), r[1].strip(), g("Instructions Executed"),
+                     g("Thread Instructions Executed"), g("Warp Stall Sampling (All Samples)")))
+    except (ValueError, IndexError):
+        pass  # a source line whose quotes (inline asm) defeat ncu's CSV escaping
 tot = sum(x[3] for x in rows)
 st = sum(x[5] for x in rows)
 unit = plies if plies else 1.0
