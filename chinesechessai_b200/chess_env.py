@@ -117,6 +117,58 @@ class _Device1:
         torch.cuda.current_stream(self.dev).synchronize()
 
 
+class _LazyThreats(list):
+    """One entry of ``chase_history`` (chess_env.py:344-345: ``_get_threatened_pieces`` of the side
+    that has just moved), computed on first use.
+
+    The reference fills it on every ply and never reads it (its only consumer returns False first,
+    :674), which is ~70 % of its ``make_move`` time.  Here the entry keeps a snapshot of the
+    position after the move and asks the engine only if somebody looks: the mover's legal moves
+    (same generators, same suicide filter, geometry of the mover) that capture a non-king piece,
+    in scan order, as ``((r, c), (to_r, to_c))`` pairs.  ``_is_protected`` can never be true in
+    the reference — a piece cannot "move" onto a piece of its own side, :116 — so every such
+    capture is listed, exactly as the reference lists it."""
+    __slots__ = ("_snap",)
+
+    def _fill(self) -> None:
+        snap = getattr(self, "_snap", None)
+        if snap is None:
+            return
+        self._snap = None
+        board, mover, red, black = snap
+        env = ChineseChess.__new__(ChineseChess)
+        env.board, env.current_player = board, mover
+        env.red_king_pos, env.black_king_pos = red, black
+        env.winner, env.move_count, env.no_capture_count, env.consecutive_checks = None, 0, 0, 0
+        env.check_history, env.position_history = [], []
+        for fr, fc, tr, tc in env.get_legal_moves():
+            target = int(board[tr, tc])
+            if target * mover < 0 and abs(target) != 1:
+                list.append(self, ((fr, fc), (tr, tc)))
+
+    def _filled(name):  # noqa: N805
+        base = getattr(list, name)
+
+        def method(self, *a, **k):
+            self._fill()
+            return base(self, *a, **k)
+        method.__name__ = name
+        return method
+
+    for _n in ("__getitem__", "__iter__", "__len__", "__contains__", "__eq__", "__ne__", "__repr__",
+               "__reversed__", "__add__", "__setitem__", "__delitem__", "append", "extend", "index", "count",
+               "copy", "pop", "insert", "remove", "sort", "reverse"):
+        locals()[_n] = _filled(_n)
+    del _n, _filled
+
+    def __bool__(self) -> bool:
+        return self.__len__() > 0
+
+    def __reduce__(self):
+        self._fill()
+        return (list, (list(self),))
+
+
 class ChineseChess:
     def __init__(self) -> None:
         self.reset()
@@ -128,7 +180,7 @@ class ChineseChess:
         self.position_history: List[int] = []
         self.no_capture_count = 0
         self.check_history: List[bool] = []
-        self.chase_history: List[list] = []  # the reference's chase scan is dead work (:345,:674)
+        self.chase_history: List[list] = []  # entries are computed on first use (_LazyThreats)
         self.consecutive_checks = 0
         self.red_king_pos: Optional[Tuple[int, int]] = (9, 4)
         self.black_king_pos: Optional[Tuple[int, int]] = (0, 4)
@@ -212,7 +264,9 @@ class ChineseChess:
         if n_hist > n_before:
             self.position_history.append(int(dev.h_hist[n_hist - 1]))
         self.check_history.append(bool(int(m["check_bits"]) & 1))
-        self.chase_history.append([])
+        threats = _LazyThreats()   # :344-345, evaluated for the mover before the side switch
+        threats._snap = (self.board.copy(), -int(m["player"]), self.red_king_pos, self.black_king_pos)
+        self.chase_history.append(threats)
         self.current_player = int(m["player"])
         self.move_count = int(m["move_count"])
         done = bool(flags & 1)

@@ -930,8 +930,9 @@ __global__ void __launch_bounds__(kSmWarps * 32, 1)
     // ---- take the free resident group with the least progress
     int slot = -1;
     for (;;) {
+      const int busy_now = vbusy[lane];  // flag first: a free slot's progress only changes under the flag
       const int pr = vprog[lane];
-      int key = (vbusy[lane] || pr == kSlotDead) ? kSlotDead : pr;
+      int key = (busy_now || pr == kSlotDead) ? kSlotDead : pr;
       const bool live = __any_sync(0xffffffffu, pr != kSlotDead);
       int who = lane;
 #pragma unroll
@@ -944,8 +945,20 @@ __global__ void __launch_bounds__(kSmWarps * 32, 1)
         __nanosleep(200);
         continue;
       }
+      // The table was read without the flag: between that read and the CAS the slot may have been
+      // taken, advanced and released again — or its group may have ended with no group left to
+      // refill it.  So the slot is validated under the flag, and given back if it is dead.
       int won = 0;
-      if (lane == 0) won = atomicCAS(&sc.busy[who], 0, 1) == 0 ? 1 : 0;
+      if (lane == 0) {
+        won = atomicCAS(&sc.busy[who], 0, 1) == 0 ? 1 : 0;
+        if (won) {
+          __threadfence_block();
+          if (vprog[who] == kSlotDead) {
+            vbusy[who] = 0;
+            won = 0;
+          }
+        }
+      }
       if (__shfl_sync(0xffffffffu, won, 0)) { slot = who; break; }
     }
     // acquire: everything the previous owner wrote (slab, meta / results / carry rows, history)

@@ -357,6 +357,33 @@ def gen_positions(pool, n_jobs, per_job):
 
 
 
+
+# ---- chase_history (dead bookkeeping of the reference, kept observable) ---------------------
+def chase_job(args):
+    """chess_env.py:262,344-345: the threat lists make_move appends to chase_history, for one
+    random game (shared pick rule)."""
+    game_id, bias = args
+    chess_env, _ = import_reference()
+    env = chess_env.ChineseChess()
+    moves = []
+    for ply in range(70):
+        legal = env.get_legal_moves()
+        if not legal:
+            break
+        packed = [pack(m) for m in legal]
+        idx = pick_index(env.board, packed, SEED, game_id, ply, bias)
+        moves.append(packed[idx])
+        _, _, done = env.make_move(legal[idx])
+        if done:
+            break
+    chase = [[[a[0] * 9 + a[1], b[0] * 9 + b[1]] for a, b in entry] for entry in env.chase_history]
+    return dict(game_id=game_id, bias=bias, moves=moves, chase=chase)
+
+
+def gen_chase(pool, quick):
+    jobs = [(70000 + i, b) for i, b in enumerate([0, 160] if quick else [0, 0, 128, 192, 224, 255])]
+    return pool.map(chase_job, jobs, chunksize=1)
+
 # ---- compare_models.play_match --------------------------------------------------------------
 def play_match_job(args):
     """The reference's UNCHANGED compare_models.play_match (compare_models.py:13-92) with two
@@ -652,6 +679,11 @@ def main():
             np.savez_compressed(os.path.join(HERE, "mcts.npz"), **mc)
             manifest["mcts_searches"] = int(len(mc["player"]))
             print("mcts", len(mc["player"]), time.time() - t0, flush=True)
+        if not only or "chase" in only:
+            ch = gen_chase(pool, a.quick)
+            json.dump(ch, open(os.path.join(HERE, "chase.json"), "w"))
+            manifest["chase_games"] = len(ch)
+            print("chase", len(ch), time.time() - t0, flush=True)
         if not only or "play_match" in only:
             pm = gen_play_match(pool, a.quick)
             json.dump(pm, open(os.path.join(HERE, "play_match.json"), "w"), ensure_ascii=False)

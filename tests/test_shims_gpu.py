@@ -412,3 +412,24 @@ def test_mcts_device_path_equals_predict_batch_path(pkg):
                 for p in net.parameters():
                     p.mul_(1.01)
     assert fast._fast[30]._graph is not None and fast._fast[30].ev._version >= 2
+
+
+def test_chase_history_equals_reference(pkg):
+    """chase_history (chess_env.py:344-345) is dead bookkeeping in the reference but an observable
+    attribute: the shim's lazily computed entries equal the lists the unmodified reference
+    appended, ply by ply, for games recorded by gen_golden.py (uniform and capture-biased)."""
+    chess_env, _ = pkg
+    from chinesechessai_b200.engine import unpack_move
+    games = json.load(open(os.path.join(GOLDEN, "chase.json")))
+    assert len(games) >= 2
+    threats = 0
+    for g in games:
+        env = chess_env.ChineseChess()
+        for mv in g["moves"]:
+            env.make_move(unpack_move(mv))
+        assert len(env.chase_history) == len(g["chase"])
+        for got, want in zip(env.chase_history, g["chase"]):
+            assert [[a[0] * 9 + a[1], b[0] * 9 + b[1]] for a, b in got] == want
+            threats += len(want)
+        assert env.chase_history[-1] == [tuple(map(tuple, x)) for x in env.chase_history[-1]]
+    assert threats > 100
