@@ -1524,9 +1524,9 @@ int xq_playout(int8_t* board, xq_meta* meta, uint64_t* pos_hist, int hist_cap, u
   const dim3 block(kThreads);
   // Mapping of the fused kernel, measured on B200 (profiles/r1/playout_mappings_by_batch.txt):
   // a tile of XQ_PLAYOUT_LPB lanes per board ("warp") is fastest while the batch is too small
-  // to fill the SMs with independent boards, two lanes per board ("pair") from ~40 k boards
-  // up; one thread per board ("tpb") issues the fewest instructions but is latency-bound.
-  // XQ_PLAYOUT_MODE overrides the choice (all three give identical results).
+  // to fill the SMs with independent boards, two lanes per board ("pair"; "pairs" = the same
+  // scheduled per SM, below) above; one thread per board ("tpb") issues the fewest instructions
+  // but is latency-bound.  XQ_PLAYOUT_MODE overrides the choice (all give identical results).
   const char* mode_env = getenv("XQ_PLAYOUT_MODE");
   const bool pair = use_pair_mapping(n_games);
   const bool tpb = mode_env != nullptr && strcmp(mode_env, "tpb") == 0;

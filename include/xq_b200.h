@@ -166,8 +166,10 @@ int xq_debug_playout_timing(uint64_t *device_buf);
  * make_move) per game in ONE launch, state in shared memory
  * (the loop of self_play.py:203-256 with the search replaced by the pick rule).
  * The library maps boards to lanes by batch size (one warp per board below
- * 40,960 boards, two lanes per board above; environment XQ_PLAYOUT_MODE =
- * warp | tpb | pair forces one) - results are identical in every mapping.
+ * 24,576 boards; two lanes per board, scheduled per SM, above - with traces
+ * the one-wave lane-pair kernel from 40,960 boards; environment
+ * XQ_PLAYOUT_MODE = warp | tpb | pair | pairq | pairs forces one) - results
+ * are identical in every mapping.
  * A game whose meta.flags gets XQ_F_OVERFLOW (more than XQ_MAX_MOVES candidate
  * moves or a full history; unreachable from legal chess positions) keeps
  * running on in-range but unspecified moves.
