@@ -317,8 +317,9 @@ PRECISIONS = ("bf16", "tf32", "fp32")
 
 def make_evaluator(torch, net, precision):
     """bf16: BN-folded channels-last inference copy (own stem / residual-epilogue kernels);
-    tf32: the module as given with TF32 tensor cores for cuDNN and cuBLAS; fp32: strict IEEE
-    float32 everywhere (TF32 off) — the reference's arithmetic (neural_network.py:47-71)."""
+    tf32: float32 storage, BN-folded channels-last copy, TF32 tensor cores for cuDNN and cuBLAS;
+    fp32: the module as given, strict IEEE float32 everywhere (TF32 off) — the reference's
+    arithmetic (neural_network.py:47-71)."""
     from chinesechessai_b200.mcts import NetEvaluator
     if precision == "bf16":
         return NetEvaluator(net, torch.bfloat16)

@@ -166,8 +166,10 @@ class NetEvaluator:
     ``dtype=float32`` runs the module as given (the reference's precision).  ``tf32`` = True /
     False forces TF32 tensor cores on / off for cuDNN and cuBLAS during the forward; None leaves
     PyTorch's switches alone, which is what the reference itself gets on a GPU (convolutions in
-    TF32 by default, matmuls in strict fp32).  A lower-precision dtype builds a folded
-    inference copy (BN folded, ``dtype`` weights, channels-last).  The copy is rebuilt whenever
+    TF32 by default, matmuls in strict fp32).  A lower-precision dtype — or float32 with
+    ``tf32=True``, whose rounding is coarser than the BN folding's — builds a folded
+    inference copy (BN folded, ``dtype`` weights, channels-last, conv+bias+ReLU(+residual) as
+    one cuDNN call each; ``folded`` overrides the choice).  The copy is rebuilt whenever
     the module's weights have changed since it was made — optimizer steps, ``load_state_dict``
     and the NCCL weight broadcast all bump the tensors' version counters, which is what
     ``version`` watches — so an evaluator kept across training iterations never plays with stale
@@ -175,10 +177,11 @@ class NetEvaluator:
     self_play.py:339,346): BatchNorm batch statistics must not leak into the search."""
 
     def __init__(self, net: torch.nn.Module, dtype: torch.dtype = torch.float32,
-                 tf32: Optional[bool] = None):
+                 tf32: Optional[bool] = None, folded: Optional[bool] = None):
         self.net = net
         self.dtype = dtype
         self.tf32 = tf32      # None: PyTorch's own switches (cuDNN TF32 on, cuBLAS off by default)
+        self.folded = (dtype != torch.float32 or tf32 is True) if folded is None else bool(folded)
         self._fast = None
         self._seen = None     # weight fingerprint the folded copy / captured graphs belong to
         self._version = 0
@@ -207,17 +210,15 @@ class NetEvaluator:
             raise RuntimeError("NetEvaluator: the network is in train() mode; call network.eval() before "
                                "self-play (BatchNorm would use and update batch statistics)")
         _ = self.version
-        if self.dtype == torch.float32:
-            planes = encode_planes(leaf_board, leaf_player, dtype=self.dtype)
-            if self.tf32 is None:
-                logits, value = self.net(planes)
-            else:
-                with _tf32(self.tf32):
-                    logits, value = self.net(planes)
+        if self.folded:
+            with _tf32(self.tf32):
+                if self._fast is None:
+                    self._fast = _FoldedNet(self.net, self.dtype)
+                logits, value = self._fast.forward_boards(leaf_board, leaf_player)
         else:
-            if self._fast is None:
-                self._fast = _FoldedNet(self.net, self.dtype)
-            logits, value = self._fast.forward_boards(leaf_board, leaf_player)
+            planes = encode_planes(leaf_board, leaf_player, dtype=self.dtype)
+            with _tf32(self.tf32):
+                logits, value = self.net(planes)
         if logits.stride(1) != 1:
             logits = logits.contiguous()
         if logits.dtype not in (torch.float32, torch.bfloat16):
@@ -229,16 +230,18 @@ class NetEvaluator:
 class _tf32:
     """Scope for the TF32 switches of cuDNN convolutions and cuBLAS matmuls."""
 
-    def __init__(self, on: bool):
-        self.on = bool(on)
+    def __init__(self, on: Optional[bool]):
+        self.on = on          # None: leave PyTorch's switches alone
 
     def __enter__(self):
         self.prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
-        torch.backends.cudnn.allow_tf32 = self.on
-        torch.backends.cuda.matmul.allow_tf32 = self.on
+        if self.on is not None:
+            torch.backends.cudnn.allow_tf32 = bool(self.on)
+            torch.backends.cuda.matmul.allow_tf32 = bool(self.on)
 
     def __exit__(self, *exc):
-        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = self.prev
+        if self.on is not None:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = self.prev
         return False
 
 

@@ -612,10 +612,23 @@ def parallel_self_play(network, num_games, temperature=1.0, num_simulations=None
             net.eval()
     red_only = opponent_network is not None
     # The search runs the network as given — float32, the reference's precision — unless the
-    # caller opts into the folded bf16 inference copy (about 10x the simulations per second;
-    # numerics of the forward are outside the parity boundary).
-    dtype = {"fp32": torch.float32, "bf16": torch.bfloat16}[os.environ.get("XQ_SELFPLAY_DTYPE", "fp32")]
-    sp = BatchedSelfPlay(network, num_games, n_sims, temperature, opponent_network, net_dtype=dtype)
+    # caller opts into a folded inference copy: "bf16" (about 10x the simulations per second) or
+    # "tf32" (float32 storage, TF32 tensor cores); numerics of the forward are outside the parity
+    # boundary, SURVEY B.5.
+    prec = os.environ.get("XQ_SELFPLAY_DTYPE", "fp32")
+    if prec not in ("fp32", "bf16", "tf32"):
+        raise ValueError(f"XQ_SELFPLAY_DTYPE={prec!r}: expected fp32, tf32 or bf16")
+    dtype = torch.bfloat16 if prec == "bf16" else torch.float32
+    if prec == "tf32":
+        network.eval()
+        players = [NetEvaluator(network, torch.float32, tf32=True)]
+        if opponent_network is not None:
+            opponent_network.eval()
+            players.append(NetEvaluator(opponent_network, torch.float32, tf32=True))
+        sp = BatchedSelfPlay(players[0], num_games, n_sims, temperature,
+                             players[1] if len(players) > 1 else None)
+    else:
+        sp = BatchedSelfPlay(network, num_games, n_sims, temperature, opponent_network, net_dtype=dtype)
     _progress(0, num_games, 0)
     try:
         # a few plies per slice so that the progress line moves and Ctrl-C is honoured promptly

@@ -334,3 +334,40 @@ def test_folded_net_matches_module(mods):
     pri = eng.policy_priors(p, mv, nm)
     assert float((pri - pri_ref).abs().max()) < 0.02
     assert float((pri.argmax(1) == pri_ref.argmax(1)).float().mean()) > 0.95
+
+
+def test_folded_float32_copy_matches_module(mods):
+    """The folded inference copy at float32 (BN folded, channels-last, fused cuDNN calls; what the
+    TF32 evaluator runs): with TF32 off it equals the module up to the re-association of the BN
+    fold; with TF32 on it stays within TF32 rounding and the search gives the n-8 visit law."""
+    import torch
+    eng, mcts = mods
+    from chinesechessai_b200.neural_network import ChessNet
+    torch.manual_seed(0)
+    net = ChessNet().cuda().eval()
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(); m.running_var.uniform_(0.5, 2.0)
+    bb = eng.BoardBatch(256)
+    bb.playout(5, 12)
+    pl = bb.meta[:, 0].view(torch.int8).contiguous()
+    mv, nm = bb.legal_moves()
+    strict = mcts.NetEvaluator(net, torch.float32, tf32=False)
+    assert not strict.folded
+    pri_ref, val_ref = strict(bb.board, pl, mv, nm)
+    folded = mcts.NetEvaluator(net, torch.float32, tf32=False, folded=True)
+    pri, val = folded(bb.board, pl, mv, nm)
+    assert folded._fast is not None and folded._fast.fused and not folded._fast.own_epilogue
+    assert folded._fast.policy_fc.weight.dtype == torch.float32
+    assert float((pri - pri_ref).abs().max()) < 2e-5 and float((val - val_ref).abs().max()) < 2e-4
+    fast = mcts.NetEvaluator(net, torch.float32, tf32=True)
+    assert fast.folded
+    pri_t, val_t = fast(bb.board, pl, mv, nm)
+    assert float((pri_t - pri_ref).abs().max()) < 5e-3 and float((val_t - val_ref).abs().max()) < 2e-2
+    prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    fast(bb.board, pl, mv, nm)
+    assert prev == (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    s = mcts.BatchedMCTS(32, 15)
+    b32 = eng.BoardBatch(32)
+    _, vis, nc = s.search(b32.board, b32.meta, fast)
+    assert (nc.cpu().numpy() == 44).all() and (vis.cpu().numpy().sum(1) == 7).all()
