@@ -13,7 +13,7 @@ from __future__ import annotations
 import gc
 import os
 import sys
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -451,16 +451,31 @@ class BatchedSelfPlay:
         plies = int(self.rec_played[:self.plies].sum())
         return {"plies": plies, "sims": plies * self.n_sims}
 
-    def materialise(self, red_only: bool = False) -> List[Tuple[list, int, str]]:
-        """-> [(game_data, winner, end_reason)] in the reference's format (self_play.py:312)."""
+    def outcome_counts(self) -> torch.Tensor:
+        """Device tensor int64[5] = (red wins, black wins, draws, plies played, games): the
+        statistics ``Trainer.collect_self_play_data`` returns (trainer.py:211-296), without a
+        host read — summed over ranks with one all_reduce by the multi-GPU loop."""
+        w = self.boards.meta[:, 1].view(torch.int8)
+        return torch.stack([(w == 1).sum(), (w == -1).sum(), ((w == 0) | (w == _lib.WINNER_NONE)).sum(),
+                            self.rec_played[:self.plies].sum(),
+                            torch.tensor(self.n, device=self.device)]).to(torch.int64)
+
+    def materialise(self, red_only: bool = False, games: Optional[Sequence[int]] = None
+                    ) -> List[Tuple[list, int, str]]:
+        """-> [(game_data, winner, end_reason)] in the reference's format (self_play.py:312);
+        ``games`` restricts it to those games of the batch (in that order)."""
         P = self.plies
         meta = self.boards.meta_host()
+        if games is None:
+            sel = lambda t: t[:P].cpu().numpy()
+        else:
+            idx = torch.as_tensor(list(games), dtype=torch.int64, device=self.device)
+            sel = lambda t: t[:P].index_select(1, idx).cpu().numpy()
+            meta = meta[np.asarray(list(games), dtype=np.int64)]
         return materialise_arrays(
-            self.rec_board[:P].cpu().numpy(), self.rec_player[:P].cpu().numpy(),
-            self.rec_moves[:P].cpu().numpy(), self.rec_visits[:P].cpu().numpy(),
-            self.rec_n[:P].cpu().numpy(), self.rec_reward[:P].cpu().numpy(),
-            self.rec_played[:P].cpu().numpy(), meta["winner"], meta["reason"], meta["player"],
-            meta["move_count"], self.temperature, red_only)
+            sel(self.rec_board), sel(self.rec_player), sel(self.rec_moves), sel(self.rec_visits),
+            sel(self.rec_n), sel(self.rec_reward), sel(self.rec_played), meta["winner"],
+            meta["reason"], meta["player"], meta["move_count"], self.temperature, red_only)
 
 
 _MOVE_TUPLES: List[Move] = []

@@ -23,7 +23,7 @@ import time
 
 def main() -> None:
     ap = argparse.ArgumentParser()
-    ap.add_argument("--mode", choices=["consumers", "cfg5"], default="consumers")
+    ap.add_argument("--mode", choices=["consumers", "cfg5", "readers"], default="consumers")
     ap.add_argument("--games", type=int, default=8)
     ap.add_argument("--sims", type=int, default=15)
     ap.add_argument("--workers", type=int, default=4)
@@ -36,6 +36,8 @@ def main() -> None:
     import torch
     out = {"mode": a.mode}
     chatter = io.StringIO()
+    if a.mode == "readers":
+        return readers(out, chatter)
     with contextlib.redirect_stdout(chatter):
         import config
         import chess_env
@@ -102,6 +104,62 @@ def main() -> None:
                         "cores": os.cpu_count(), "torch_threads": torch.get_num_threads()})
         t.close()
     sys.stderr.write(chatter.getvalue()[-4000:])
+    print(json.dumps(out, ensure_ascii=False))
+
+
+def readers(out, chatter) -> None:
+    """The reference's own READERS on files written by chinesechessai_b200.train_loop in cwd:
+    Trainer.__init__ -> load_model (trainer.py:77-78,451-459), plot_progress.parse_training_log
+    (:16-63), view_best_games.load_best_games / list_best_games (:15-80) and the move replay of
+    GameReplayer.replay_game (:201-213).  matplotlib and pygame are not in this image; the
+    functions used here never touch them, so empty stand-in modules satisfy the imports."""
+    import types
+    import numpy as np
+    for name in ("matplotlib", "matplotlib.pyplot", "pygame"):
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except ImportError:
+                sys.modules[name] = types.ModuleType(name)
+    if not hasattr(sys.modules["matplotlib"], "rcParams"):
+        sys.modules["matplotlib"].rcParams = {}
+        sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    with contextlib.redirect_stdout(chatter):
+        import config
+        import chess_env
+        import plot_progress
+        import trainer
+        import view_best_games
+        out["modules"] = {m.__name__: os.path.dirname(os.path.abspath(m.__file__))
+                          for m in (config, chess_env, trainer, plot_progress, view_best_games)}
+        t = trainer.Trainer()                                   # loads models/latest.pt
+        out["total_games"], out["training_steps"] = int(t.total_games), int(t.training_steps)
+        out["adam_steps"] = sorted({int(v["step"]) for v in t.optimizer.state_dict()["state"].values()})
+        t.close()
+        data = plot_progress.parse_training_log(os.path.join(config.LOG_DIR, "training.log"))
+        out["log"] = data
+        games = view_best_games.load_best_games()
+        view_best_games.list_best_games(games)
+        out["best_games"] = len(games)
+        replayed = []
+        for g in games[:4]:                                     # view_best_games.py:201-213
+            env = chess_env.ChineseChess()
+            env.reset()
+            n = 0
+            for board_state, move_probs, player in g["game_data"]:
+                assert np.array_equal(np.asarray(board_state), env.board), "recorded board != replayed board"
+                if move_probs:
+                    # the viewer replays the arg-max move; the game itself sampled, so follow
+                    # the recorded boards instead and only check that the arg-max is legal
+                    best_move = max(move_probs.items(), key=lambda x: x[1])[0]
+                    assert best_move in env.get_legal_moves()
+                    assert type(move_probs) is dict and abs(sum(move_probs.values()) - 1.0) < 1e-9
+                n += 1
+                break                                           # boards after ply 0 depend on the sampled move
+            replayed.append({"winner": int(g["winner"]), "moves": int(g["moves"]), "type": g["type"],
+                             "samples": len(g["game_data"]), "timestamp": g["timestamp"].isoformat()})
+        out["replayed"] = replayed
+    sys.stderr.write(chatter.getvalue()[-3000:])
     print(json.dumps(out, ensure_ascii=False))
 
 
