@@ -127,31 +127,42 @@ __device__ __forceinline__ int pair_movegen(ThreadBoard& w, Game& g, const uint3
   // block of candidates (contiguous) is noted on the way
   const int dir = sub ? -1 : 1, base = sub ? kTpbMoveCap - 1 : 0;
   const Tables tb{leap, g_ray};
-  const int half = (n_own >> 1) * 4;
-  const int t_end = sub ? n_own * 4 : half;
+  // one piece per iteration, its four generator slots unrolled (gen_piece / gen_dir)
+  const int p_half = n_own >> 1, p_end = sub ? n_own : p_half;
   int nc = 0, kfirst = 0, kcount = 0;
 #pragma unroll 1
-  for (int t = sub ? half : 0; t < t_end; ++t) {
-    const int pi = t >> 2;
-    const Item it = gen_item(w, tb, player, w.own[pi < own0 ? pi : kHalfOwn + (pi - own0)], t & 3);
-    const int cnt = it.empties + (it.e1 >= 0) + (it.e2 >= 0);
-    if (nc + cnt > kTpbMoveCap) {
-      g.flags |= XQ_F_OVERFLOW;
-      break;
-    }
-    if (it.from == ownK) {
-      if (kcount == 0) kfirst = nc;
-      kcount += cnt;
-    }
-    // a quiet ray reserves its `empties` slots and leaves ONE descriptor in the first of them
-    // (from<<8 | 0x80 | d<<5 | empties); the flat pass below expands it in place
-    const unsigned fs = (unsigned)it.from << 8;
+  for (int pi = sub ? p_half : 0; pi < p_end; ++pi) {
+    const int from = w.own[pi < own0 ? pi : kHalfOwn + (pi - own0)];
+    const PieceGen pg = gen_piece(w, tb, player, from);
+    const int nc_piece = nc;
+    // a piece has at most 17 candidates (a rook with both lines open); only a list that close to
+    // its capacity needs the exact per-slot accounting
+    const bool tight = nc + 17 > kTpbMoveCap;
+    const unsigned fs = (unsigned)from << 8;
     uint16_t* out = &w.mv[base + dir * nc];
-    if (it.empties > 0) *out = (uint16_t)(fs | 0x80u | ((unsigned)(t & 3) << 5) | (unsigned)it.empties);
-    out += dir * it.empties;
-    if (it.e1 >= 0) { *out = (uint16_t)(fs | (unsigned)it.e1); out += dir; }
-    if (it.e2 >= 0) *out = (uint16_t)(fs | (unsigned)it.e2);
-    nc += cnt;
+    bool full = false;
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      const Item it = gen_dir(w, pg, player, d);
+      const int cnt = it.empties + (it.e1 >= 0) + (it.e2 >= 0);
+      if (tight && nc + cnt > kTpbMoveCap) {
+        g.flags |= XQ_F_OVERFLOW;
+        full = true;
+        break;
+      }
+      // a quiet ray reserves its `empties` slots and leaves ONE descriptor in the first of them
+      // (from<<8 | 0x80 | d<<5 | empties); the flat pass below expands it in place
+      if (it.empties > 0) *out = (uint16_t)(fs | 0x80u | ((unsigned)d << 5) | (unsigned)it.empties);
+      out += dir * it.empties;
+      if (it.e1 >= 0) { *out = (uint16_t)(fs | (unsigned)it.e1); out += dir; }
+      if (it.e2 >= 0) { *out = (uint16_t)(fs | (unsigned)it.e2); out += dir; }
+      nc += cnt;
+    }
+    if (from == ownK && nc > nc_piece) {
+      if (kcount == 0) kfirst = nc_piece;
+      kcount += nc - nc_piece;
+    }
+    if (full) break;
   }
   {  // expand the ray descriptors: one slot per iteration, all lanes in step
     unsigned v = 0, delta = 0;

@@ -19,10 +19,10 @@ static void stage(WarpSmem& w, const int8_t* board) {
       }
 }
 
-static const uint32_t h_leap[kLeapEntries] = {
+alignas(16) static const uint32_t h_leap[kLeapEntries] = {
 #include "../../chinesechessai_b200/csrc/xq_leap_table.inc"
 };
-static const uint16_t h_ray[kRayEntries] = {
+alignas(16) static const uint16_t h_ray[kRayEntries] = {
 #include "../../chinesechessai_b200/csrc/xq_ray_table.inc"
 };
 static const Tables h_tables{h_leap, h_ray};
@@ -174,4 +174,23 @@ extern "C" int xqh_check_fast(const int8_t* board, int player, int red_king, int
   }
   if (exotic || !regular_king(w, player, ownK, n_kings)) return -1;
   return check_fast(make_fast_ctx(w, g, h_touch), player) ? 1 : 0;
+}
+
+// gen_piece() + gen_dir() (the lane-pair engine's per-piece generator) against gen_item() on every
+// square that holds a piece of `player` (any code, poked boards included).  Returns the number of
+// (square, slot) items that differ.
+extern "C" int xqh_gen_piece_mismatches(const int8_t* board, int player) {
+  WarpSmem w;
+  stage(w, board);
+  int bad = 0;
+  for (int s = 0; s < XQ_NSQ; ++s) {
+    if ((int)w.sq[s] * player <= 0) continue;
+    const PieceGen pg = gen_piece(w, h_tables, player, s);
+    for (int d = 0; d < 4; ++d) {
+      const Item a = gen_item(w, h_tables, player, s, d), b = gen_dir(w, pg, player, d);
+      bad += a.from != b.from || a.empties != b.empties || a.e1 != b.e1 || a.e2 != b.e2 ||
+             (a.empties > 0 && a.delta != b.delta);
+    }
+  }
+  return bad;
 }

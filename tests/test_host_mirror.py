@@ -15,6 +15,7 @@ def hm():
     lib.xqh_in_check.argtypes = [C.c_void_p] + [C.c_int] * 4
     lib.xqh_in_check_dirs.argtypes = [C.c_void_p] + [C.c_int] * 4
     lib.xqh_check_fast.argtypes = [C.c_void_p] + [C.c_int] * 3
+    lib.xqh_gen_piece_mismatches.argtypes = [C.c_void_p, C.c_int]
     lib.xqh_position_change.argtypes = [C.c_int] * 5
     lib.xqh_position_change.restype = C.c_double
     return lib
@@ -73,6 +74,7 @@ def test_fuzz_playouts_vs_oracle(hm, xo, bias):
             fast = hm.xqh_check_fast(b.ctypes.data, e.s.player, e.s.red_king, e.s.black_king)
             assert fast == hm.xqh_in_check(b.ctypes.data, e.s.player, -e.s.player, e.s.red_king, e.s.black_king), (g, ply)
             n_fast[0] += fast >= 0
+            assert hm.xqh_gen_piece_mismatches(b.ctypes.data, e.s.player) == 0, (g, ply)
             if len(lm) == 0:
                 break
             idx = xo.lib().xqo_pick_move(e.s, lm.ctypes.data, len(lm), 99, g, ply, bias)
@@ -90,6 +92,13 @@ def test_fuzz_arbitrary_boards_vs_oracle(hm, xo):
         sq = rng.choice(90, size=k, replace=False)
         board[sq] = rng.integers(1, 8, size=k) * rng.choice([-1, 1], size=k)
         player = int(rng.choice([-1, 1]))
+        # the per-piece generator of the lane-pair engine == the per-slot one, also for piece codes
+        # outside 1..7 (nothing is generated for them)
+        odd = board.copy()
+        if it % 8 == 0:
+            odd[sq[0]] = int(rng.integers(8, 100)) * int(rng.choice([-1, 1]))
+        for who in (1, -1):
+            assert hm.xqh_gen_piece_mismatches(odd.ctypes.data, who) == 0, it
 
         def cache(code):
             u = rng.random()
