@@ -39,6 +39,12 @@ constexpr int kThreads = kWarpsPerCta * 32;
 #ifndef XQ_PAIR_MIN_GAMES
 #define XQ_PAIR_MIN_GAMES 40960
 #endif
+// plies a warp plays on a group before it puts the group back and picks again (playout_sm_kernel);
+// measured at 65,536 boards: 1 -> 3.72 ms, 2 -> 3.79, 3 -> 3.81, 4 -> 3.79 (the pick is cheaper
+// than the imbalance a longer turn leaves)
+#ifndef XQ_SM_TURN
+#define XQ_SM_TURN 1
+#endif
 #ifndef XQ_SM_MIN_GAMES
 #define XQ_SM_MIN_GAMES 24576  // measured crossover with the warp mapping: 4.3e8 vs 4.1e8 here, 3.0e8 vs 4.0e8 at 16,384
 #endif
@@ -1014,8 +1020,9 @@ __global__ void __launch_bounds__(kSmWarps * 32, 1)
         uint64_t* hist = pos_hist + (size_t)g * hist_cap;
         const uint32_t gid = first_game_id + (uint32_t)g;
         fin = false;
-        // ---- ONE iteration of the loop of playout_lane_kernel<false, true>
-        {
+        // ---- XQ_SM_TURN iterations of the loop of playout_lane_kernel<false, true>
+#pragma unroll 1
+        for (int rep = 0; rep < XQ_SM_TURN && !fin; ++rep) {
           bool checking = false;
           int n = -1, n0 = 0;
           unsigned lsum = 0;
@@ -1075,7 +1082,7 @@ __global__ void __launch_bounds__(kSmWarps * 32, 1)
       }
     }
     // ---- put the group back, or refill the slot when every game of the group is over
-    const bool group_over = __all_sync(0xffffffffu, fin) || it + 1 >= iters;
+    const bool group_over = __all_sync(0xffffffffu, fin) || it + XQ_SM_TURN >= iters;
     // release: every lane's writes are performed (fence), every lane has passed its fence
     // (__syncwarp: the vote above synchronises execution but orders no memory), then lane 0
     // publishes the slot
@@ -1093,7 +1100,7 @@ __global__ void __launch_bounds__(kSmWarps * 32, 1)
           vprog[slot] = kSlotDead;
         }
       } else {
-        vprog[slot] = it + 1;
+        vprog[slot] = it + XQ_SM_TURN;
       }
       __threadfence_block();
       vbusy[slot] = 0;

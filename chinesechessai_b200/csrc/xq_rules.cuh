@@ -589,9 +589,13 @@ XQ_HD int leap_index(int player, int pt, int from, int d) {
 // Ray table (generated, xq_ray_table.inc): entry [orientation][position][occupancy mask][backward]
 // = empties | first << 4 | second << 8 for a rook / cannon ray (see gen_ray_table.py).  58 KB.
 constexpr int kRayRowEntries = 9 * 512 * 2, kRayEntries = kRayRowEntries + 10 * 1024 * 2;
+// Knight table (generated, xq_knight_table.inc): entry [T][diagonal] = leg | knight_a << 8 |
+// knight_b << 16, the squares from which a knight attacks T (0xFF = off the board).  1.4 KB.
+constexpr int kKnightEntries = 90 * 4;
 struct Tables {
   const uint32_t* leap;
   const uint16_t* ray;
+  const uint32_t* knight = nullptr;  // only king_move_fast() reads it
 };
 
 // One generator slot of one piece, branch-free: the lanes of a warp work on different piece types
@@ -704,6 +708,67 @@ XQ_HD Item gen_dir(const W& w, const PieceGen& g, int player, int d) {
   return it;
 }
 
+// _is_move_suicide (chess_env.py:431-464) for the king's OWN move K -> T on a regular position
+// (exotic_window: no enemy K/A/B can reach the squares the king can step to), as straight-line
+// table code instead of the eight probes of attacked(): the two ray words of T's row and column
+// (with K vacated) name the nearest and second piece in the four directions — rook / adjacent pawn
+// under the mover's geometry (quirk A.3) / cannon behind its screen —, the knight table names the
+// four legs and eight knight squares, and the kings-facing test (:466-495) uses the refreshed
+// cache of the moving king (:448-451) against the enemy's cached square `ek`.
+template <class W>
+XQ_HD bool king_move_fast(const W& w, const Tables& tb, int player, int K, int T, int ek) {
+  const int es = -player;
+  const int kr = (K * 57) >> 9, kc = K - kr * 9, tr = (T * 57) >> 9, tc = T - tr * 9;
+  unsigned rowm = w.rows[tr], colm = w.cols[tc];
+  rowm &= ~(kr == tr ? 1u << kc : 0u);  // the king has left K (the tables ignore T's own bit)
+  colm &= ~(kc == tc ? 1u << kr : 0u);
+  const uint32_t* ray32 = reinterpret_cast<const uint32_t*>(tb.ray);
+  const int hi = tc * 512 + (int)rowm, vi = kRayRowEntries / 2 + tr * 1024 + (int)colm;
+#if defined(__CUDA_ARCH__)
+  const uint32_t h = __ldg(ray32 + hi), v = __ldg(ray32 + vi);
+  const uint4 kn = __ldg(reinterpret_cast<const uint4*>(tb.knight) + T);
+  const uint32_t kn4[4] = {kn.x, kn.y, kn.z, kn.w};
+#else
+  const uint32_t h = ray32[hi], v = ray32[vi];
+  const uint32_t* kn4 = tb.knight + T * 4;
+#endif
+  // pawns: sideways only from a crossed row, vertically only toward the king (:240-249 with the
+  // mover's geometry: the defender's forward direction)
+  const bool side_ok = player == 1 ? tr < 5 : tr >= 5;
+  bool hit = false;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int d = 0; d < 4; ++d) {
+    const uint32_t e = d == 0 ? h & 0xFFFFu : d == 1 ? h >> 16 : d == 2 ? v & 0xFFFFu : v >> 16;
+    const int delta = (d < 2 ? 1 : 9) * ((d & 1) ? -1 : 1);
+    const int first = (int)((e >> 4) & 15u), second = (int)((e >> 8) & 15u);
+    const int q1 = w.sq[T + first * delta], q2 = w.sq[T + second * delta];
+    const bool pawn_ok = d < 2 ? side_ok : player == (d == 2 ? 1 : -1);
+    hit |= first != 0 && (q1 == es * ROOK || (first == 1 && pawn_ok && q1 == es * PAWN));
+    hit |= second != 0 && q2 == es * CANNON;
+  }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 4; ++i) {
+    // an off-board square reads K instead: the own king is no enemy knight, and K counts as an
+    // empty leg anyway (the king has left it)
+    const uint32_t e = kn4[i];
+    const int leg = (int)(e & 0xFFu), a = (int)((e >> 8) & 0xFFu), b = (int)((e >> 16) & 0xFFu);
+    const int legs = leg == 0xFF ? K : leg, as = a == 0xFF ? K : a, bs = b == 0xFF ? K : b;
+    const bool free_leg = legs == K || w.sq[legs] == 0;
+    hit |= free_leg && (w.sq[as] == es * KNIGHT || w.sq[bs] == es * KNIGHT);
+  }
+  if (ek >= 0) {
+    const int er = (ek * 57) >> 9, ec = ek - er * 9;
+    const int lo = xq_min(tr, er), hi_r = xq_max(tr, er);
+    const unsigned between = ((1u << hi_r) - 1u) & ~((2u << lo) - 1u);
+    hit |= ec == tc && (colm & between) == 0;
+  }
+  return hit;
+}
+
 // Warp-uniform hint for suicide(): can an enemy K/A/B ever matter?  They reach squares within
 // two rows of themselves (bishop 2, advisor / king 1).  The squares that count in a regular
 // position (exactly one own king piece, standing on its cached square) are the king's own square
@@ -748,6 +813,9 @@ static __device__ const uint32_t g_touch[kTouchEntries] = {
 };
 static __device__ __align__(16) const uint16_t g_ray[kRayEntries] = {
 #include "xq_ray_table.inc"
+};
+static __device__ __align__(16) const uint32_t g_knight[kKnightEntries] = {
+#include "xq_knight_table.inc"
 };
 
 // Cold paths are kept out of line: the fused loop's hot code has to stay small enough for the

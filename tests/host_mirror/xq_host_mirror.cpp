@@ -25,7 +25,10 @@ alignas(16) static const uint32_t h_leap[kLeapEntries] = {
 alignas(16) static const uint16_t h_ray[kRayEntries] = {
 #include "../../chinesechessai_b200/csrc/xq_ray_table.inc"
 };
-static const Tables h_tables{h_leap, h_ray};
+alignas(16) static const uint32_t h_knight[kKnightEntries] = {
+#include "../../chinesechessai_b200/csrc/xq_knight_table.inc"
+};
+static const Tables h_tables{h_leap, h_ray, h_knight};
 static const uint32_t h_touch[kTouchEntries] = {
 #include "../../chinesechessai_b200/csrc/xq_touch_table.inc"
 };
@@ -191,6 +194,34 @@ extern "C" int xqh_gen_piece_mismatches(const int8_t* board, int player) {
       bad += a.from != b.from || a.empties != b.empties || a.e1 != b.e1 || a.e2 != b.e2 ||
              (a.empties > 0 && a.delta != b.delta);
     }
+  }
+  return bad;
+}
+
+// king_move_fast() against the general suicide() for every candidate of the own king on a regular
+// position.  Returns the number of candidates that differ, -1 when the position is not regular.
+extern "C" int xqh_king_move_mismatches(const int8_t* board, int player, int red_king, int black_king) {
+  WarpSmem w;
+  stage(w, board);
+  Game g{};
+  g.player = player;
+  g.red_king = red_king;
+  g.black_king = black_king;
+  const int ownK = player == 1 ? red_king : black_king, ek = player == 1 ? black_king : red_king;
+  int n_kings = 0;
+  bool exotic = false;
+  for (int s = 0; s < XQ_NSQ; ++s) {
+    n_kings += w.sq[s] == player * KING;
+    exotic |= exotic_piece(w.sq[s], s, player, ownK < 0 ? 0 : ownK);
+  }
+  if (exotic || !regular_king(w, player, ownK, n_kings)) return -1;
+  int bad = 0;
+  for (int d = 0; d < 4; ++d) {
+    const Item it = gen_item(w, h_tables, player, ownK, d);
+    const int ts[2] = {it.e1, it.e2};
+    for (int k = 0; k < 2; ++k)
+      if (ts[k] >= 0)
+        bad += king_move_fast(w, h_tables, player, ownK, ts[k], ek) != suicide(w, g, ownK, ts[k], false);
   }
   return bad;
 }

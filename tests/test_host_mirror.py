@@ -16,6 +16,7 @@ def hm():
     lib.xqh_in_check_dirs.argtypes = [C.c_void_p] + [C.c_int] * 4
     lib.xqh_check_fast.argtypes = [C.c_void_p] + [C.c_int] * 3
     lib.xqh_gen_piece_mismatches.argtypes = [C.c_void_p, C.c_int]
+    lib.xqh_king_move_mismatches.argtypes = [C.c_void_p] + [C.c_int] * 3
     lib.xqh_position_change.argtypes = [C.c_int] * 5
     lib.xqh_position_change.restype = C.c_double
     return lib
@@ -75,6 +76,8 @@ def test_fuzz_playouts_vs_oracle(hm, xo, bias):
             assert fast == hm.xqh_in_check(b.ctypes.data, e.s.player, -e.s.player, e.s.red_king, e.s.black_king), (g, ply)
             n_fast[0] += fast >= 0
             assert hm.xqh_gen_piece_mismatches(b.ctypes.data, e.s.player) == 0, (g, ply)
+            # the king's own moves: table test == the general probes (regular positions only)
+            assert hm.xqh_king_move_mismatches(b.ctypes.data, e.s.player, e.s.red_king, e.s.black_king) == 0, (g, ply)
             if len(lm) == 0:
                 break
             idx = xo.lib().xqo_pick_move(e.s, lm.ctypes.data, len(lm), 99, g, ply, bias)
@@ -86,6 +89,7 @@ def test_fuzz_playouts_vs_oracle(hm, xo, bias):
 
 def test_fuzz_arbitrary_boards_vs_oracle(hm, xo):
     rng = np.random.default_rng(123)
+    n_regular = 0
     for it in range(4000):
         board = np.zeros(90, np.int8)
         k = int(rng.integers(2, 30))
@@ -118,3 +122,38 @@ def test_fuzz_arbitrary_boards_vs_oracle(hm, xo):
         fast = hm.xqh_check_fast(board.ctypes.data, player, red, black)
         if fast >= 0:
             assert fast == hm.xqh_in_check(board.ctypes.data, player, -player, red, black), it
+        km = hm.xqh_king_move_mismatches(board.ctypes.data, player, red, black)
+        assert km <= 0 and (km < 0) == (fast < 0), it
+        n_regular += km == 0
+    assert n_regular > 150
+
+
+def test_fuzz_king_moves_on_regular_boards(hm):
+    """king_move_fast() == suicide() for the king's own moves on dense regular positions: both
+    kings in their palaces (cached), no other K/A/B of the enemy, rooks / cannons / knights / pawns
+    of both sides scattered — around the king as well, so that screens, legs, adjacent pawns from
+    every side and the kings' file are all exercised."""
+    rng = np.random.default_rng(77)
+    n_cand = 0
+    for it in range(6000):
+        board = np.zeros(90, np.int8)
+        player = int(rng.choice([-1, 1]))
+        rk = int(rng.integers(7, 10)) * 9 + int(rng.integers(3, 6))
+        bk = int(rng.integers(0, 3)) * 9 + int(rng.integers(3, 6))
+        board[rk], board[bk] = 1, -1
+        own = rk if player == 1 else bk
+        kr, kc = divmod(own, 9)
+        k = int(rng.integers(3, 26))
+        near = [r * 9 + c for r in range(max(0, kr - 3), min(10, kr + 4)) for c in range(max(0, kc - 3), min(9, kc + 4))]
+        for _ in range(k):
+            s = int(rng.choice(near)) if rng.random() < 0.6 else int(rng.integers(0, 90))
+            if board[s] == 0:
+                board[s] = int(rng.choice([4, 5, 6, 7])) * int(rng.choice([-1, 1]))
+        if rng.random() < 0.3:   # own advisors / bishops are harmless to the regular test
+            s = int(rng.choice(near))
+            if board[s] == 0:
+                board[s] = player * int(rng.choice([2, 3]))
+        km = hm.xqh_king_move_mismatches(board.ctypes.data, player, rk, bk)
+        assert km == 0, (it, board.reshape(10, 9), player)
+        n_cand += 1
+    assert n_cand == 6000
