@@ -938,14 +938,11 @@ __global__ void __launch_bounds__(kSmWarps * 32, 1)
     for (;;) {
       const int busy_now = vbusy[lane];  // flag first: a free slot's progress only changes under the flag
       const int pr = vprog[lane];
-      int key = (busy_now || pr == kSlotDead) ? kSlotDead : pr;
+      // least progress, lowest slot on ties: one warp-wide integer min of (progress, slot)
+      const int mine = (busy_now || pr == kSlotDead) ? kSlotDead : (pr << 5) | lane;
       const bool live = __any_sync(0xffffffffu, pr != kSlotDead);
-      int who = lane;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const int ok = __shfl_xor_sync(0xffffffffu, key, o), ow = __shfl_xor_sync(0xffffffffu, who, o);
-        if (ok < key || (ok == key && ow < who)) { key = ok; who = ow; }
-      }
+      const int key = __reduce_min_sync(0xffffffffu, mine);
+      const int who = key & 31;
       if (key == kSlotDead) {
         if (!live) return;  // every group of this SM is over
         __nanosleep(200);
