@@ -537,8 +537,10 @@ __global__ void __launch_bounds__(kLaneThreads, PAIR ? 7 : 1)
     bool checking = false;
     int n = -1, n0 = 0;  // n0: lane 0's share of the pair's list
     unsigned lsum = 0;   // digest term of the legal list
+    [[maybe_unused]] PairLegal lazy;  // fused playouts without traces keep the list uncompacted
     if (!kingcap) {
-      if constexpr (PAIR) n = pair_movegen(w, G, g_leap, pending, checking, n0, lsum);
+      if constexpr (PAIR && !TRACE) n = pair_movegen<true>(w, G, g_leap, pending, checking, n0, lsum, &lazy);
+      else if constexpr (PAIR) n = pair_movegen(w, G, g_leap, pending, checking, n0, lsum);
       else n = tpb_movegen(w, G, g_leap, pending ? &checking : nullptr);
     }
     if (pending) {
@@ -565,7 +567,9 @@ __global__ void __launch_bounds__(kLaneThreads, PAIR ? 7 : 1)
     if (ply >= max_plies || n == 0) break;  // self_play.py:203,207
     max_legal = max(max_legal, n);
     unsigned cm;
-    if constexpr (PAIR) {
+    if constexpr (PAIR && !TRACE) {
+      cm = pair_pick_lazy(w, lazy, n, seed, gid, (uint32_t)ply, capture_bias);
+    } else if constexpr (PAIR) {
       cm = pair_move_at(w, pair_pick(w, n, n0, seed, gid, (uint32_t)ply, capture_bias), n0);
     } else {
       cm = w.mv[tpb_pick(w, n, seed, gid, (uint32_t)ply, capture_bias)];
@@ -823,7 +827,8 @@ __global__ void __launch_bounds__(kLaneThreads, 7)
       bool checking = false;
       int n = -1, n0 = 0;
       unsigned lsum = 0;
-      if (!kingcap) n = pair_movegen(w, G, g_leap, pending, checking, n0, lsum);
+      PairLegal lazy;
+      if (!kingcap) n = pair_movegen<true>(w, G, g_leap, pending, checking, n0, lsum, &lazy);
       if (pending) {
         tpb_finish<true, true>(w, G, o, n, checking, hist);
         pending = false;
@@ -838,7 +843,7 @@ __global__ void __launch_bounds__(kLaneThreads, 7)
       }
       if (ply >= max_plies || n == 0) { fin = true; break; }  // self_play.py:203,207
       max_legal = max(max_legal, n);
-      const unsigned cm = pair_move_at(w, pair_pick(w, n, n0, seed, gid, (uint32_t)ply, capture_bias), n0);
+      const unsigned cm = pair_pick_lazy(w, lazy, n, seed, gid, (uint32_t)ply, capture_bias);
       const int mv = tpb_packed(cm);
       word_a = (uint64_t)lsum | ((uint64_t)n << 32) | ((uint64_t)mv << 40) | ((uint64_t)(ply + 1) << 54);
       o = tpb_apply<true>(w, G, (int)(cm >> 8), (int)(cm & 0x7fu), hist, hist_cap);
@@ -1023,7 +1028,8 @@ __global__ void __launch_bounds__(kSmWarps * 32, 1)
           bool checking = false;
           int n = -1, n0 = 0;
           unsigned lsum = 0;
-          if (!kingcap) n = pair_movegen(w, G, g_leap, pending, checking, n0, lsum);
+          PairLegal lazy;
+          if (!kingcap) n = pair_movegen<true>(w, G, g_leap, pending, checking, n0, lsum, &lazy);
           if (pending) {
             tpb_finish<true>(w, G, o, n, checking, hist);
             pending = false;
@@ -1039,7 +1045,7 @@ __global__ void __launch_bounds__(kSmWarps * 32, 1)
           if (!fin && (ply >= max_plies || n == 0)) fin = true;  // self_play.py:203,207
           if (!fin) {
             max_legal = max(max_legal, n);
-            const unsigned cm = pair_move_at(w, pair_pick(w, n, n0, seed, gid, (uint32_t)ply, capture_bias), n0);
+            const unsigned cm = pair_pick_lazy(w, lazy, n, seed, gid, (uint32_t)ply, capture_bias);
             const int mv = tpb_packed(cm);
             word_a = (uint64_t)lsum | ((uint64_t)n << 32) | ((uint64_t)mv << 40) | ((uint64_t)(ply + 1) << 54);
             o = tpb_apply<true>(w, G, (int)(cm >> 8), (int)(cm & 0x7fu), hist, hist_cap);

@@ -30,6 +30,27 @@ __device__ __forceinline__ unsigned pair_move_at(const ThreadBoard& w, int i, in
   return w.mv[i < n0 ? i : kTpbMoveCap - 1 - (i - n0)];
 }
 
+// The legal list WITHOUT compaction (fused playouts): the candidates stay where move generation
+// put them, each lane keeps the verdicts of its half of the list (entries j0 .. of the pair's
+// numbering: lane 0's run, then lane 1's) as a bit mask.  The digest term is summed inside the
+// legality loop and the one move a ply needs is found by rank in the mask, so the per-slot
+// compaction pass (8 % of the instructions of a ply, at 17 of 32 lanes) is not run at all.
+struct PairLegal {
+  unsigned long long mask;  // bit t: entry j0 + t is legal
+  int j0;                   // first entry of this lane's half
+  int nc0;                  // length of lane 0's run (address of entry j: pair_entry_addr)
+  int n_a;                  // legal entries in lane 0's half
+};
+__device__ __forceinline__ int pair_entry_addr(int j, int nc0) {
+  return j < nc0 ? j : kTpbMoveCap - 1 - (j - nc0);
+}
+// position of the k-th (0-based) set bit
+__device__ __forceinline__ int nth_bit64(unsigned long long m, int k) {
+  const unsigned lo = (unsigned)m, hi = (unsigned)(m >> 32);
+  const int cl = __popc(lo);
+  return k < cl ? (int)__fns(lo, 0u, k + 1) : 32 + (int)__fns(hi, 0u, k - cl + 1);
+}
+
 __device__ __forceinline__ void pair_load(ThreadBoard& w, const int8_t* __restrict__ row) {
   const int sub = Pair::sub();
 #pragma unroll
@@ -75,9 +96,10 @@ __device__ __forceinline__ uint64_t pair_board_key(const ThreadBoard& w) {
 // get_legal_moves (chess_env.py:76-121) by a pair.  Returns the total count; n_first = lane 0's
 // share, checked as in tpb_movegen, lsum = sum over the list of (move_i + 1) * (2 i + 1) mod 2^32
 // (the digest's list term, folded into the compaction loop).
+template <bool LAZY = false>
 __device__ __forceinline__ int pair_movegen(ThreadBoard& w, Game& g, const uint32_t* __restrict__ leap,
                                             bool want_check, bool& checked, int& n_first,
-                                            unsigned& lsum) {
+                                            unsigned& lsum, PairLegal* lazy = nullptr) {
   constexpr int kHalfOwn = kTpbOwnCap / 2;
   const int sub = Pair::sub();
   const int player = g.player;
@@ -205,6 +227,75 @@ __device__ __forceinline__ int pair_movegen(ThreadBoard& w, Game& g, const uint3
   }
   Pair::sync();
 
+  if constexpr (LAZY) {
+    // legality (:118) + the digest's list term in ONE pass over equal halves of the list; the
+    // verdicts go into a register mask, the list is left as it is
+    int chk = 0, n = 0;
+    unsigned s0 = 0, s1 = 0;
+    unsigned long long legal = 0, bit = 1;
+    const int cut = (total + 1) >> 1, j0 = sub ? cut : 0, j_end = sub ? total : cut;
+    if (!exotic) {
+      const FastCtx f = make_fast_ctx(w, g, g_touch);
+      if (want_check) chk = check_fast(f, player) ? 1 : 0;
+      // the king's own moves first (:448-451, table test): marked in place, the lanes take
+      // alternating candidates
+      const int ek = player == 1 ? g.black_king : g.red_king;
+#pragma unroll 1
+      for (int q = sub; q < k_total; q += 2) {
+        const int a = XQ_PAIR_ADDR(k_start + q);
+        const unsigned c = w.mv[a];
+        if (king_move_fast(w, tb, player, ownK, (int)(c & 0x7fu), ek)) w.mv[a] = (uint16_t)(c | kCandIllegal);
+      }
+      Pair::sync();
+#pragma unroll 1
+      for (int j = j0; j < j_end; ++j, bit <<= 1) {
+        const unsigned c = w.mv[XQ_PAIR_ADDR(j)];
+        const int from = (int)((c >> 8) & 0x7fu), to = (int)(c & 0x7fu);
+        const bool bad = from == ownK ? (c & kCandIllegal) != 0 : suicide_fast(f, from, to);
+        if (!bad) {
+          legal |= bit;
+          const unsigned p1 = (unsigned)tpb_packed(c) + 1u;
+          s0 += p1;
+          s1 += p1 * (unsigned)(2 * n + 1);
+          ++n;
+        }
+      }
+    } else {
+      // irregular boards: the general test on the lane's own run (marks), then the same pass
+#pragma unroll 1
+      for (int j = 0; j < nc; ++j) {
+        const unsigned c = w.mv[base + dir * j];
+        if (suicide(w, g, (int)(c >> 8), (int)(c & 0x7fu), true)) w.mv[base + dir * j] = (uint16_t)(c | kCandIllegal);
+      }
+      if (want_check && ownK >= 0 && sub == 0)
+        chk = attacked(w, ownK, -player, -player, -1, -1, 0, true, nullptr) ? 1 : 0;
+      Pair::sync();
+#pragma unroll 1
+      for (int j = j0; j < j_end; ++j, bit <<= 1) {
+        const unsigned c = w.mv[XQ_PAIR_ADDR(j)];
+        if (!(c & kCandIllegal)) {
+          legal |= bit;
+          const unsigned p1 = (unsigned)tpb_packed(c) + 1u;
+          s0 += p1;
+          s1 += p1 * (unsigned)(2 * n + 1);
+          ++n;
+        }
+      }
+    }
+    chk |= Pair::other(chk);
+    checked = chk != 0;
+    const int n_other = Pair::other(n);
+    n_first = sub ? n_other : n;
+    const unsigned part = sub ? s1 + 2u * (unsigned)n_first * s0 : s1;  // lane 1's i = n_a + local i
+    lsum = part + Pair::other(part);
+    g.flags |= Pair::other(g.flags);
+    lazy->mask = legal;
+    lazy->j0 = j0;
+    lazy->nc0 = nc0;
+    lazy->n_a = n_first;
+    Pair::sync();
+    return n + n_other;
+  }
   // legality (:118): verdicts are MARKED in place (kCandIllegal), nothing moves yet
   int chk = 0;
   if (!exotic) {
@@ -267,6 +358,50 @@ __device__ __forceinline__ int pair_movegen(ThreadBoard& w, Game& g, const uint3
   g.flags |= Pair::other(g.flags);
   Pair::sync();
   return n + n_other;
+}
+
+// shared pick rule on the uncompacted list: returns the picked entry (from << 8 | to)
+// in both lanes.  The i-th legal move is the i-th set bit of the two lanes' masks taken together.
+__device__ __forceinline__ unsigned pair_pick_lazy(const ThreadBoard& w, const PairLegal& L, int n,
+                                                   uint64_t seed, uint32_t game_id, uint32_t ply,
+                                                   int capture_bias) {
+  const int sub = Pair::sub();
+  uint32_t x[4];
+  philox4x32(game_id, ply, 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), x);
+  unsigned mine = 0;
+  int owner = -1;
+  if (capture_bias > 0 && (int)(x[1] & 0xFFu) < capture_bias) {
+    int cap = 0;
+#pragma unroll 1
+    for (unsigned long long m = L.mask; m; m &= m - 1) {
+      const unsigned c = w.mv[pair_entry_addr(L.j0 + __ffsll((long long)m) - 1, L.nc0)];
+      cap += w.sq[c & 0x7fu] != 0;
+    }
+    const int cap_o = Pair::other(cap), cap_a = sub ? cap_o : cap, ncap = cap + cap_o;
+    if (ncap > 0) {
+      const int k = (int)(x[0] % (uint32_t)ncap);
+      owner = k < cap_a ? 0 : 1;
+      int kk = owner ? k - cap_a : k;
+      if (sub == owner) {
+#pragma unroll 1
+        for (unsigned long long m = L.mask; m; m &= m - 1) {
+          const unsigned c = w.mv[pair_entry_addr(L.j0 + __ffsll((long long)m) - 1, L.nc0)];
+          if (w.sq[c & 0x7fu] != 0 && kk-- == 0) {
+            mine = c;
+            break;
+          }
+        }
+      }
+    }
+  }
+  if (owner < 0) {
+    const int k = (int)(x[0] % (uint32_t)n);
+    owner = k < L.n_a ? 0 : 1;
+    const int kk = owner ? k - L.n_a : k;
+    if (sub == owner) mine = w.mv[pair_entry_addr(L.j0 + nth_bit64(L.mask, kk), L.nc0)];
+  }
+  const unsigned theirs = Pair::other(mine);
+  return (sub == owner ? mine : theirs) & ~(unsigned)kCandIllegal;
 }
 
 // shared pick rule: index into the pair's list; both lanes compute the same value
