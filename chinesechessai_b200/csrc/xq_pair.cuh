@@ -7,13 +7,17 @@
 // half the dependent chain per lane:
 //   * own-piece scan: lane 0 the squares of words 0..11, lane 1 words 12..22 (four squares per
 //     32-bit load, branch-free append), each into its half of the own list;
-//   * candidate generation: by halves of the piece list; lane 0's candidates grow up from
-//     mv[0], lane 1's down from mv[127]; a quiet ray is one descriptor expanded by a flat pass;
-//   * legality: suicide_fast over EQUAL halves of the whole candidate list (verdicts marked in
-//     place), the probe round (check test + king moves, one attacked() call site) by alternating
-//     items;
-//   * one compaction pass per lane that also sums the digest's list term; the repetition scan
-//     by alternating history entries.
+//   * candidate generation: by halves of the piece list, one PIECE per iteration (gen_piece /
+//     gen_dir: type, row / column and the four table words derived once, four slots unrolled);
+//     lane 0's candidates grow up from mv[0], lane 1's down from mv[127]; a quiet ray is one
+//     descriptor expanded by a flat pass;
+//   * legality: suicide_fast over EQUAL halves of the whole candidate list; make_move's check
+//     test from the same masks (check_fast); the king's own moves by table (king_move_fast), the
+//     lanes taking alternating candidates; the general probes only on irregular (poked) boards;
+//   * the fused playouts (pair_movegen<LAZY>) keep the verdicts in a per-lane bit mask, sum the
+//     digest's list term inside the legality loop and pick by rank in the mask — no compaction;
+//     the API kernels and the trace mode mark in place and compact each lane's run;
+//   * the repetition scan by alternating history entries.
 // Bookkeeping (make_move's scalar part, the pick) is replicated in both lanes' registers; lane 0
 // writes the slab.  The legal list in the reference's order is lane 0's run followed by lane
 // 1's and is never merged physically (pair_move_at).  Pair-mask shuffles and __syncwarp only.
