@@ -39,12 +39,6 @@ constexpr int kThreads = kWarpsPerCta * 32;
 #ifndef XQ_PAIR_MIN_GAMES
 #define XQ_PAIR_MIN_GAMES 40960
 #endif
-// plies a warp plays on a group before it puts the group back and picks again (playout_sm_kernel);
-// measured at 65,536 boards: 1 -> 3.72 ms, 2 -> 3.79, 3 -> 3.81, 4 -> 3.79 (the pick is cheaper
-// than the imbalance a longer turn leaves)
-#ifndef XQ_SM_TURN
-#define XQ_SM_TURN 1
-#endif
 #ifndef XQ_SM_MIN_GAMES
 #define XQ_SM_MIN_GAMES 24576  // measured crossover with the warp mapping: 4.3e8 vs 4.1e8 here, 3.0e8 vs 4.0e8 at 16,384
 #endif
@@ -978,29 +972,55 @@ __global__ void __launch_bounds__(kSmWarps * 32, 1)
     const int g = gi * kQueueGroup + (lane >> 1);
     bool fin = true;  // pairs without a game count as finished
     if (g < n_games) {
-      // ---- restore (or start) the game
-      uint64_t digest = 0, word_a = 0;
-      double rsum = 0.0;
-      int max_legal = 0, ply = 0;
-      bool pending = false, kingcap = false;
-      TpbStep o;
-      o.done = 0; o.reward = 0.0; o.is_int = 1; o.from = o.to = 0; o.moving = o.captured = 0; o.key_next = 0;
+      // ---- restore (or start) the game.  Move generation is where the kernel sits at its
+      // register cap, so only what it reads is restored before it: side to move, king caches,
+      // flags, the board key and the pending / king-capture bits.  The other scalars of the game
+      // (counters, digest, sums, the pending move's fields) are read from their rows after it.
+      const xq_meta* mrow = meta + g;
+      const uint4* cp = reinterpret_cast<const uint4*>(carry + g);
       Game G;
+      uint32_t bits = 0;
       bool live_game = true;
+      {
+        const uint2 head = *reinterpret_cast<const uint2*>(mrow);
+        G.player = (int8_t)(head.x & 0xff);
+        G.red_king = (int8_t)(head.y & 0xff);
+        G.black_king = (int8_t)((head.y >> 8) & 0xff);
+        G.flags = (head.y >> 16) & 0xff;
+      }
       if (it == 0) {
         pair_load(w, board + (size_t)g * XQ_BOARD_STRIDE);
-        G = load_meta(meta + g);
         G.bkey = pair_board_key(w);
       } else {
-        const uint4* cp = reinterpret_cast<const uint4*>(carry + g);
-        const uint4 c0 = cp[0], c1 = cp[1];  // written by a warp of this CTA (CTA-scope fence)
-        const uint32_t bits = c1.z;
+        const uint4 c1 = cp[1];  // written by a warp of this CTA (CTA-scope fence)
+        bits = c1.z;
         live_game = !(bits & 4u);  // a finished game's rows are final
-        if (live_game) {
+        G.bkey = (uint64_t)c1.x | ((uint64_t)c1.y << 32);
+      }
+      if (live_game) {
+        bool pending = bits & 1u, kingcap = (bits >> 1) & 1u;
+        fin = false;
+        // ---- ONE iteration of the loop of playout_lane_kernel<false, true>
+        bool checking = false;
+        int n = -1, n0 = 0;
+        unsigned lsum = 0;
+        PairLegal lazy;
+        if (!kingcap) n = pair_movegen<true>(w, G, g_leap, pending, checking, n0, lsum, &lazy);
+        // ---- the rest of the game's scalars
+        const int flags_now = G.flags;
+        const uint64_t bkey_now = G.bkey;
+        G = load_meta(mrow);
+        G.flags |= flags_now;
+        G.bkey = bkey_now;
+        uint64_t digest = 0, word_a = 0;
+        double rsum = 0.0;
+        int max_legal = 0, ply = 0;
+        TpbStep o;
+        o.done = 0; o.reward = 0.0; o.is_int = 1; o.from = o.to = 0; o.moving = o.captured = 0;
+        if (it != 0) {
+          const uint4 c0 = cp[0];
           word_a = (uint64_t)c0.x | ((uint64_t)c0.y << 32);
           o.reward = __longlong_as_double((long long)((uint64_t)c0.z | ((uint64_t)c0.w << 32)));
-          pending = bits & 1u;
-          kingcap = (bits >> 1) & 1u;
           o.is_int = (bits >> 3) & 1u;
           o.done = kingcap ? 1 : 0;  // between iterations o.done can only be the king-capture flag
           o.from = (bits >> 5) & 0x7Fu;
@@ -1013,45 +1033,31 @@ __global__ void __launch_bounds__(kSmWarps * 32, 1)
           max_legal = (int)(uint32_t)(r1 >> 32);
           rsum = __longlong_as_double((long long)rp[2]);
           digest = rp[3];
-          G = load_meta(meta + g);
-          G.bkey = (uint64_t)c1.x | ((uint64_t)c1.y << 32);
         }
-      }
-      if (live_game) {
         o.key_next = G.bkey ^ side_key(G.player);
         uint64_t* hist = pos_hist + (size_t)g * hist_cap;
         const uint32_t gid = first_game_id + (uint32_t)g;
-        fin = false;
-        // ---- XQ_SM_TURN iterations of the loop of playout_lane_kernel<false, true>
-#pragma unroll 1
-        for (int rep = 0; rep < XQ_SM_TURN && !fin; ++rep) {
-          bool checking = false;
-          int n = -1, n0 = 0;
-          unsigned lsum = 0;
-          PairLegal lazy;
-          if (!kingcap) n = pair_movegen<true>(w, G, g_leap, pending, checking, n0, lsum, &lazy);
-          if (pending) {
-            tpb_finish<true>(w, G, o, n, checking, hist);
-            pending = false;
-            rsum = __dadd_rn(rsum, o.reward);
-            const uint64_t word_c = (uint64_t)(o.done & 1) | ((uint64_t)(G.winner + 2) << 8) |
-                                    ((uint64_t)G.reason << 16) | ((uint64_t)(o.is_int & 1) << 24);
-            const uint64_t t = word_a * 0x9E3779B97F4A7C15ULL + dbits(o.reward) * 0xC2B2AE3D27D4EB4FULL +
-                               word_c * 0x165667B19E3779F9ULL + o.key_next * 0x27D4EB2F165667C5ULL;
-            digest = mix64(digest ^ t);
-            ++ply;
-            if (o.done) fin = true;
-          }
-          if (!fin && (ply >= max_plies || n == 0)) fin = true;  // self_play.py:203,207
-          if (!fin) {
-            max_legal = max(max_legal, n);
-            const unsigned cm = pair_pick_lazy(w, lazy, n, seed, gid, (uint32_t)ply, capture_bias);
-            const int mv = tpb_packed(cm);
-            word_a = (uint64_t)lsum | ((uint64_t)n << 32) | ((uint64_t)mv << 40) | ((uint64_t)(ply + 1) << 54);
-            o = tpb_apply<true>(w, G, (int)(cm >> 8), (int)(cm & 0x7fu), hist, hist_cap);
-            kingcap = o.done != 0;
-            pending = true;
-          }
+        if (pending) {
+          tpb_finish<true>(w, G, o, n, checking, hist);
+          pending = false;
+          rsum = __dadd_rn(rsum, o.reward);
+          const uint64_t word_c = (uint64_t)(o.done & 1) | ((uint64_t)(G.winner + 2) << 8) |
+                                  ((uint64_t)G.reason << 16) | ((uint64_t)(o.is_int & 1) << 24);
+          const uint64_t t = word_a * 0x9E3779B97F4A7C15ULL + dbits(o.reward) * 0xC2B2AE3D27D4EB4FULL +
+                             word_c * 0x165667B19E3779F9ULL + o.key_next * 0x27D4EB2F165667C5ULL;
+          digest = mix64(digest ^ t);
+          ++ply;
+          if (o.done) fin = true;
+        }
+        if (!fin && (ply >= max_plies || n == 0)) fin = true;  // self_play.py:203,207
+        if (!fin) {
+          max_legal = max(max_legal, n);
+          const unsigned cm = pair_pick_lazy(w, lazy, n, seed, gid, (uint32_t)ply, capture_bias);
+          const int mv = tpb_packed(cm);
+          word_a = (uint64_t)lsum | ((uint64_t)n << 32) | ((uint64_t)mv << 40) | ((uint64_t)(ply + 1) << 54);
+          o = tpb_apply<true>(w, G, (int)(cm >> 8), (int)(cm & 0x7fu), hist, hist_cap);
+          kingcap = o.done != 0;
+          pending = true;
         }
         // ---- hand the scalars over (and, once the game is over, the final board)
         Pair::sync();
@@ -1074,18 +1080,18 @@ __global__ void __launch_bounds__(kSmWarps * 32, 1)
           results[g] = r;
         } else {
           const uint64_t rw = dbits(o.reward);
-          const uint32_t bits = (pending ? 1u : 0u) | (kingcap ? 2u : 0u) | (fin ? 4u : 0u) |
-                                ((uint32_t)(o.is_int & 1) << 3) | ((uint32_t)(o.from & 0x7F) << 5) |
-                                ((uint32_t)(o.to & 0x7F) << 12) | ((uint32_t)((o.moving + 8) & 0xF) << 19) |
-                                ((uint32_t)((o.captured + 8) & 0xF) << 23);
-          uint4* cp = reinterpret_cast<uint4*>(carry + g);
-          cp[0] = make_uint4((uint32_t)word_a, (uint32_t)(word_a >> 32), (uint32_t)rw, (uint32_t)(rw >> 32));
-          cp[1] = make_uint4((uint32_t)G.bkey, (uint32_t)(G.bkey >> 32), bits, 0u);
+          const uint32_t nbits = (pending ? 1u : 0u) | (kingcap ? 2u : 0u) | (fin ? 4u : 0u) |
+                                 ((uint32_t)(o.is_int & 1) << 3) | ((uint32_t)(o.from & 0x7F) << 5) |
+                                 ((uint32_t)(o.to & 0x7F) << 12) | ((uint32_t)((o.moving + 8) & 0xF) << 19) |
+                                 ((uint32_t)((o.captured + 8) & 0xF) << 23);
+          uint4* co = reinterpret_cast<uint4*>(carry + g);
+          co[0] = make_uint4((uint32_t)word_a, (uint32_t)(word_a >> 32), (uint32_t)rw, (uint32_t)(rw >> 32));
+          co[1] = make_uint4((uint32_t)G.bkey, (uint32_t)(G.bkey >> 32), nbits, 0u);
         }
       }
     }
     // ---- put the group back, or refill the slot when every game of the group is over
-    const bool group_over = __all_sync(0xffffffffu, fin) || it + XQ_SM_TURN >= iters;
+    const bool group_over = __all_sync(0xffffffffu, fin) || it + 1 >= iters;
     // release: every lane's writes are performed (fence), every lane has passed its fence
     // (__syncwarp: the vote above synchronises execution but orders no memory), then lane 0
     // publishes the slot
@@ -1103,7 +1109,7 @@ __global__ void __launch_bounds__(kSmWarps * 32, 1)
           vprog[slot] = kSlotDead;
         }
       } else {
-        vprog[slot] = it + XQ_SM_TURN;
+        vprog[slot] = it + 1;
       }
       __threadfence_block();
       vbusy[slot] = 0;
