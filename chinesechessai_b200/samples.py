@@ -6,7 +6,7 @@ turns them into the tensors ``Trainer.train_network`` consumes (trainer.py:311-3
 reward of self_play.py:262-310) without a host round trip, and gathers them across ranks."""
 from __future__ import annotations
 
-from typing import Dict, Optional
+from typing import Dict
 
 import torch
 

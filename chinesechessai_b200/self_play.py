@@ -12,7 +12,6 @@ from __future__ import annotations
 
 import gc
 import os
-import sys
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -22,7 +21,7 @@ from . import _lib
 from ._lib import BOARD_STRIDE, MAX_MOVES, META_DTYPE, check
 from .chess_env import ChineseChess, format_end_reason
 from .config import MAX_MOVES as MAX_PLIES, MCTS_SIMULATIONS
-from .engine import BoardBatch, _ptr, _stream, pack_move, unpack_move
+from .engine import BoardBatch, _ptr, _stream, unpack_move
 from .mcts import WAVE, BatchedMCTS, HashEvaluator, NetEvaluator
 
 PROGRESS_EVERY_PLIES = 10  # parallel_self_play refreshes its progress line this often
