@@ -879,6 +879,12 @@ def run_ours(args):
             c_plies += int(r1.view(torch.int32)[:, 0].sum())
         out["cfg1"] = {"workload": "cfg1: 1,024 games x <= 70 plies (latency-bound: 128 CTAs on 148 SMs)",
                        "value": c_plies / (c_ms * 1e-3), "unit": UNIT, "ms_per_batch": c_ms / 5}
+        if cpu_baseline is not None and cpu_baseline.get("kind") == "reference":
+            # cfg 1 next to the Python reference of the SAME run: its cost per game does not depend
+            # on how many games are played, so its rate on this run's sample is its cfg 1 rate
+            out["cfg1"]["cpu_reference_same_run"] = {
+                "value": cpu_baseline.get("value"), "unit": UNIT, "cores": cpu_baseline.get("cores"),
+                "kind": "reference", "sample": cpu_baseline.get("sample")}
         out["gpu_launches"] += 11
         # the other mappings of the same fused loop
         out["other_mappings"] = {}
